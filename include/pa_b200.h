@@ -1,0 +1,194 @@
+/* pa_b200.h — C ABI of libpa_b200.so, the B200-native engine behind the PartitionedArrays.jl
+ * PSparseMatrix x PVector hot path (mul!, consistent!/assemble!, dot/norm/axpy, HPCG CG loop).
+ *
+ * The reference is pure Julia: the path sits behind multiple dispatch on the "array of parts"
+ * backend type (DebugArray src/debug_array.jl, MPIArray src/mpi_array.jl).  A third backend
+ * (CUDAArray, see INTEGRATION.md for the Julia ccall stubs) binds exactly the entry points
+ * below; each one cites the reference interface it replaces (path:line in the reference tree).
+ *
+ * Conventions
+ *  - every function returns int: 0 = PA_OK, negative = PA_E*; text via pa_last_error() (thread
+ *    local).  Nothing throws or aborts across the ABI (Julia shim turns codes into error(...),
+ *    mirroring the reference's @assert / @boundscheck failures, src/p_sparse_matrix.jl:2091-2093).
+ *  - all index arrays arriving here are 1-based exactly as Julia stores them (local ids, part
+ *    ids, JaggedArray ptrs, SparseMatrixCSR{1} rowptr/colval) unless index_base says otherwise.
+ *  - host arrays are borrowed for the duration of the call only; the library owns all device
+ *    memory behind the opaque handles.  Handles are not thread-safe.
+ *  - a pa_ctx is the backend instance: it holds the parts that live in THIS process (one per
+ *    process in distributed runs = the MPIArray model, src/mpi_array.jl:105-117; all parts in one
+ *    process = the DebugArray model, src/debug_array.jl:7-9).  Every operation is collective over
+ *    the local parts and must be called in the same order by every process (SPMD), like MPI.
+ *  - vectors live in a symmetric, peer-mapped arena (CUDA IPC over NVLink/NVSwitch): a ghost
+ *    value is read straight from the owner's HBM by the consuming kernel; there is no message.
+ */
+#ifndef PA_B200_H
+#define PA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PA_ABI_VERSION 1
+
+#define PA_OK 0
+#define PA_EINVAL (-1)  /* bad argument / dimension mismatch (reference: @assert, @boundscheck) */
+#define PA_ECUDA (-2)   /* CUDA runtime error (sticky: the context is unusable afterwards)      */
+#define PA_ENOMEM (-3)  /* arena or device memory exhausted                                     */
+#define PA_ENCCL (-4)   /* NCCL missing or failed                                               */
+#define PA_ESTATE (-5)  /* object not committed / wrong state                                   */
+
+typedef struct pa_ctx pa_ctx;   /* backend instance (array of parts)                               */
+typedef struct pa_plan pa_plan; /* PRange partition + exchange plan (AssemblyCache/VectorAssemblyCache) */
+typedef struct pa_vec pa_vec;   /* PVector{Vector{Float64}}                                        */
+typedef struct pa_mat pa_mat;   /* PSparseMatrix (per-part CSR, Int32 columns, Float64 values)     */
+
+int pa_abi_version(void);
+const char *pa_last_error(void);
+
+/* ------------------------------------------------------------------ backend / context -------
+ * Replaces distribute_with_debug / with_debug (src/debug_array.jl:7-31) and distribute_with_mpi /
+ * with_mpi (src/mpi_array.jl:42-83).
+ *  nparts_global : number of parts of the whole job (length of `ranks`)
+ *  nlocal        : parts held by this process; part_ids[k] (1-based) their global ids
+ *  device        : CUDA device ordinal for all local parts (one device per process)
+ *  arena_bytes   : size of the symmetric vector arena per local part (0 = 1 GiB)
+ *  stream        : cudaStream_t to enqueue on (NULL = the library creates a non-blocking stream) */
+int pa_ctx_create(int32_t nparts_global, int32_t nlocal, const int32_t *part_ids, int32_t device,
+                  uint64_t arena_bytes, void *stream, pa_ctx **out);
+int pa_ctx_destroy(pa_ctx *ctx);
+/* Block until everything enqueued so far has finished (wait(t) of the reference's tasks). */
+int pa_ctx_sync(pa_ctx *ctx);
+int pa_ctx_stream(pa_ctx *ctx, void **stream_out);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int pa_ctx_launch_count(pa_ctx *ctx, int64_t *out);
+
+/* Peer mapping of remote parts (distributed runs).  Export the 64-byte CUDA IPC handle of local
+ * part k's arena, all-gather the handles on the host (torch.distributed / MPI), then import the
+ * handle of every remote part.  Parts held by this process are linked automatically. */
+int pa_ctx_arena_export(pa_ctx *ctx, int32_t k, void *handle64);
+int pa_ctx_arena_import(pa_ctx *ctx, int32_t part_id, const void *handle64);
+
+/* Scalar all-reduce across processes for dot/norm/sum — replaces reduction_impl / MPI.Allreduce!
+ * (src/mpi_array.jl:478-507).  NCCL is loaded with dlopen only when this is called. */
+int pa_nccl_unique_id(void *id128);
+int pa_ctx_nccl_init(pa_ctx *ctx, const void *id128, int32_t rank, int32_t world);
+
+/* ------------------------------------------------------------------ plan (PRange + cache) ----
+ * Ingests, verbatim, the arrays the reference computes once per partition:
+ * AbstractLocalIndices accessors (src/p_range.jl:32-160) and VectorAssemblyCache
+ * (src/p_vector.jl:418-468; built by assembly_neighbors / assembly_local_indices,
+ * src/p_range.jl:417-531).  All ids 1-based.
+ *  own_to_local / ghost_to_local : NULL means the block layout own = 1..n_own, ghost = the rest.
+ *  *_remote_lids : for every entry of snd_lids (rcv_lids) the local id of the same global id on
+ *     the neighbour (the neighbour's matching rcv (snd) entry).  May be NULL when the neighbour is
+ *     held by this process (derived internally); required for remote neighbours. */
+int pa_plan_create(pa_ctx *ctx, pa_plan **out);
+int pa_plan_set_part(pa_plan *plan, int32_t k, int64_t n_local, int64_t n_own, const int32_t *own_to_local,
+                     const int32_t *ghost_to_local, int32_t n_nbr_snd, const int32_t *nbr_snd,
+                     const int32_t *snd_ptrs, const int32_t *snd_lids, const int32_t *snd_remote_lids,
+                     int32_t n_nbr_rcv, const int32_t *nbr_rcv, const int32_t *rcv_ptrs,
+                     const int32_t *rcv_lids, const int32_t *rcv_remote_lids);
+/* sym_n_local: max n_local over ALL parts of the job (0 = max over the local parts; only valid
+ * when every part is local).  Fixes the symmetric arena stride of vectors on this plan. */
+int pa_plan_commit(pa_plan *plan, int64_t sym_n_local);
+int pa_plan_destroy(pa_plan *plan);
+
+/* ------------------------------------------------------------------ PVector -----------------
+ * PVector(undef, index_partition) / similar (src/p_vector.jl:334-344,758-772). */
+int pa_vec_create(pa_plan *plan, pa_vec **out);
+int pa_vec_destroy(pa_vec *v);
+/* local_values(v)[k] <- host (n_local doubles, reference local order); asynchronous w.r.t. the
+ * device but the host buffer may be reused on return unless it is pinned (then call pa_ctx_sync). */
+int pa_vec_upload(pa_vec *v, int32_t k, const double *host, int64_t n);
+/* host <- local_values(v)[k]; synchronises. */
+int pa_vec_download(const pa_vec *v, int32_t k, double *host, int64_t n);
+/* fill!(v,a) (src/p_vector.jl:816-821), copy!(dst,src) (:800-814), rmul!(v,a) (:1194-1199) —
+ * all local entries (own and ghost). */
+int pa_vec_fill(pa_vec *v, double a);
+int pa_vec_copy(pa_vec *dst, const pa_vec *src);
+int pa_vec_scale(pa_vec *v, double a);
+/* Broadcast updates (src/p_vector.jl:1208-1277; own AND ghost entries are written, :1271-1276):
+ *   axpby : y .= a.*x .+ b.*y        waxpby : w .= a.*x .+ b.*y   (w may alias x or y) */
+int pa_vec_axpby(pa_vec *y, double a, const pa_vec *x, double b);
+int pa_vec_waxpby(pa_vec *w, double a, const pa_vec *x, double b, const pa_vec *y);
+/* dot (src/p_vector.jl:1189-1192), norm(v,2)^2 (:1201-1206), sum (:1178-1187): own entries only,
+ * per-part partial then sum over parts in part order (+ all-reduce across processes). Synchronise. */
+int pa_vec_dot(const pa_vec *x, const pa_vec *y, double *out);
+int pa_vec_norm2(const pa_vec *x, double *out_sumsq);
+int pa_vec_sum(const pa_vec *x, double *out);
+/* consistent!(v) (src/p_vector.jl:747-755) and assemble!(+,v) (:695-708).  Asynchronous: the
+ * returned state is the reference's task; pa_ctx_sync is its wait(). */
+int pa_vec_consistent(pa_vec *v);
+int pa_vec_assemble(pa_vec *v);
+/* v[lid] = hash(gid, seed) in [-1,1) for a box partition (own box lo..hi, 0-based, hi exclusive,
+ * of a gn grid; column-major ids); ghost entries are set to 0.  Test/bench input generator. */
+int pa_vec_fill_hash_box(pa_vec *v, int32_t k, const int64_t *gn, const int64_t *lo, const int64_t *hi,
+                         uint64_t seed);
+
+/* ------------------------------------------------------------------ PSparseMatrix -----------
+ * PSparseMatrix (src/p_sparse_matrix.jl:971-991).  Row plan / column plan = partition(axes(A,1)),
+ * partition(axes(A,2)).  Only assembled matrices (ghost-row blocks empty, :1704-1705). */
+int pa_mat_create(pa_plan *rows, pa_plan *cols, pa_mat **out);
+int pa_mat_destroy(pa_mat *A);
+/* Unsplit local CSR, the HPCG layout (HPCG/src/sparse_matrix.jl:115-121): n_own_rows x n_local_cols,
+ * row i = i-th own row, column ids = local ids of the column partition.
+ * index_base 0/1; ptr_bits and col_bits 32 or 64 (SparseMatrixCSR{Bi,Float64,Ti}). */
+int pa_mat_set_csr(pa_mat *A, int32_t k, int64_t nrows, int64_t ncols, int32_t index_base, int32_t ptr_bits,
+                   int32_t col_bits, const void *rowptr, const void *colval, const double *nzval);
+/* Split format (src/p_sparse_matrix.jl:588-593): own_own (n_own_rows x n_own_cols, own ids) and
+ * own_ghost (n_own_rows x n_ghost_cols, ghost ids).  Rows are merged on upload, own-block entries
+ * first, so the summation order of mul! (:2099-2101) is kept. */
+int pa_mat_set_csr_split(pa_mat *A, int32_t k, int64_t nrows, int32_t index_base, int32_t ptr_bits,
+                         int32_t col_bits, const void *rowptr_oo, const void *colval_oo,
+                         const double *nzval_oo, const void *rowptr_oh, const void *colval_oh,
+                         const double *nzval_oh);
+/* On-device generators of the benchmark operators for a box partition (own box lo..hi of a gn grid,
+ * 0-based, hi exclusive): kind 7 = gallery laplacian_fdm (src/gallery.jl:12-86), kind 27 = HPCG
+ * build_matrix (HPCG/src/sparse_matrix.jl:27-80).  ghost_gid_sorted / ghost_id_of_sorted: the ng
+ * ghost global ids (0-based) sorted ascending and their 0-based ghost ids (reference order).
+ * rhs (nullable): kind 27 -> b = 27 - nnz_row ; kind 7 -> A*ones.  Never materialises COO. */
+int pa_mat_set_stencil(pa_mat *A, int32_t k, int32_t kind, const int64_t *gn, const int64_t *lo,
+                       const int64_t *hi, int64_t ng, const int64_t *ghost_gid_sorted,
+                       const int32_t *ghost_id_of_sorted, pa_vec *rhs);
+int pa_mat_commit(pa_mat *A);
+int pa_mat_nnz(const pa_mat *A, int32_t k, int64_t *out);
+/* Copy the device CSR of part k back (0-based, int64 rowptr; any pointer may be NULL). */
+int pa_mat_download_csr(const pa_mat *A, int32_t k, int64_t *rowptr, int32_t *colval, double *nzval);
+/* LinearAlgebra.fillstored!(A,a) (used by test/p_sparse_matrix_tests.jl:285). */
+int pa_mat_fill_stored(pa_mat *A, double a);
+
+/* flags for pa_spmv / pa_cg */
+#define PA_SPMV_DEFAULT 0u
+#define PA_SPMV_EXPLICIT_EXCHANGE 1u  /* consistent!(x) kernel first, then a purely local SpMV       */
+#define PA_SPMV_SKIP_GHOST_REFRESH 2u /* fused path: do not also write x's local ghost slots          */
+#define PA_CG_REFERENCE_OPS 4u        /* op-for-op sequence of ref_cg.jl (copy,dot,axpby,spmv,dot,...) */
+
+/* mul!(y,A,x) (src/p_sparse_matrix.jl:2090-2103) when alpha=1,beta=0; mul!(y,A,x,alpha,beta)
+ * (:2105-2142) otherwise; HPCG mul_no_lat! (HPCG/src/hpcg_utils.jl:6-17) is the same call.
+ * Default path: ghost columns are loaded from the owner's HBM inside the SpMV kernel (NVLink peer
+ * loads) — no separate exchange; x's ghost slots are refreshed as a side effect like consistent!. */
+int pa_spmv(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, uint32_t flags);
+
+typedef struct {
+  int32_t iters;
+  int32_t converged;
+  double residual0; /* ||b - A x0||  */
+  double residual;  /* ||r|| at exit */
+} pa_cg_result;
+
+/* ref_cg!(x,A,b; tolerance, maxiter, Pl=Identity) (HPCG/src/ref_cg.jl:40-134).  history (nullable)
+ * receives maxiter+1 residual norms (residual0 first).  Stops at maxiter or ||r||/||r0|| <= tol. */
+int pa_cg(pa_mat *A, pa_vec *x, const pa_vec *b, int32_t maxiter, double tol, uint32_t flags,
+          pa_cg_result *result, double *history);
+
+/* Pinned host memory for the end-to-end path (cudaHostAlloc / cudaFreeHost). */
+int pa_host_alloc(void **ptr, size_t bytes);
+int pa_host_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PA_B200_H */

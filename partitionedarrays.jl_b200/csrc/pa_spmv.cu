@@ -1,0 +1,544 @@
+// PSparseMatrix storage, the CSR SpMV kernel (own rows x local columns, ghost columns read from
+// the owner's HBM over NVLink inside the kernel), and on-device generators of the benchmark operators.
+// Reference: mul! src/p_sparse_matrix.jl:2090-2142, spmv_csr! src/sparse_utils.jl:649-669,
+// mul_no_lat! HPCG/src/hpcg_utils.jl:6-17, generators src/gallery.jl:12-86, HPCG/src/sparse_matrix.jl:27-80.
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+
+#include "pa_internal.h"
+
+#define SPMV_BLOCK 256
+
+// ------------------------------------------------------------------ the SpMV kernel
+// CSR-stream: a CTA owns ROWS consecutive rows.  All 256 threads stream the CTA's contiguous slice of
+// nzval/colval with coalesced loads (U = TILE/256 independent 8-byte + 4-byte loads in flight per
+// thread), gather x (L1/L2-resident for banded operators; ghost columns -> NVLink peer load from the
+// owner's arena), and park the products a_ij*x_j in shared memory.  Then one thread per row adds its
+// row's products from shared memory *sequentially in column order*: exactly the reference loop
+// `bi += aij*xj` (separate multiply and add, no FMA), so the result is bit-identical to spmv_csr!.
+// Row lengths 7 and 27 are odd -> the per-row walk through shared memory is bank-conflict free.
+// HBM traffic = the matrix stream once + x + y + rowptr: the kernel is bandwidth bound by design.
+template <typename PtrT>
+struct SpmvArgs {
+  int64_t nrows;
+  const PtrT *rowptr;
+  const int32_t *colval;
+  const double *nzval;
+  const double *x;
+  double *y;
+  const int32_t *rowmap;  // y index of row i (nullptr: i)
+  double alpha, beta;
+  int64_t n_own_cols;     // fused: columns >= n_own_cols are ghosts
+  const int32_t *gslot, *grlid;
+  PeerPtrs peers;
+};
+
+// The matrix stream is read exactly once: keep it out of L1 and mark it evict-first in L2 so the
+// 126 MB L2 is left to x (each x entry is reused by up to 7/27 rows, two grid planes apart).
+__device__ __forceinline__ uint64_t stream_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ double ld_stream_f64(const double *p, uint64_t pol) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int32_t ld_stream_s32(const int32_t *p, uint64_t pol) {
+  int32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
+template <typename PtrT, int ROWS, int TILE, bool FUSED>
+__global__ void __launch_bounds__(SPMV_BLOCK) k_spmv_stream(const SpmvArgs<PtrT> a) {
+  constexpr int U = TILE / SPMV_BLOCK;
+  __shared__ double prod[TILE];
+  const int tid = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * ROWS;
+  const int64_t r1 = min(r0 + (int64_t)ROWS, a.nrows);
+  const int64_t row = r0 + tid;
+  const bool has_row = tid < ROWS && row < r1;
+  int64_t rs = 0, re = 0;
+  if (has_row) {
+    rs = (int64_t)a.rowptr[row];
+    re = (int64_t)a.rowptr[row + 1];
+  }
+  const int64_t s = (int64_t)a.rowptr[r0], e = (int64_t)a.rowptr[r1];
+  double acc = 0.0;
+  const uint64_t pol = stream_policy();
+  for (int64_t base = s; base < e; base += TILE) {
+    double v[U];
+    int32_t c[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = base + tid + u * SPMV_BLOCK;
+      const bool ok = p < e;
+      v[u] = ok ? ld_stream_f64(a.nzval + p, pol) : 0.0;
+      c[u] = ok ? ld_stream_s32(a.colval + p, pol) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      double xv = 0.0;
+      if (c[u] >= 0) {
+        if (FUSED && c[u] >= a.n_own_cols) {
+          const int64_t g = c[u] - a.n_own_cols;
+          xv = __ldcg(a.peers.p[a.gslot[g]] + a.grlid[g]);
+        } else {
+          xv = __ldg(a.x + c[u]);
+        }
+      }
+      prod[tid + u * SPMV_BLOCK] = __dmul_rn(v[u], xv);
+    }
+    __syncthreads();
+    if (has_row) {
+      const int64_t lo = max(rs, base), hi = min(re, base + (int64_t)TILE);
+      for (int64_t p = lo; p < hi; ++p) acc = __dadd_rn(acc, prod[p - base]);
+    }
+    __syncthreads();
+  }
+  if (has_row) {
+    const int64_t yi = a.rowmap ? (int64_t)a.rowmap[row] : row;
+    if (a.alpha == 1.0 && a.beta == 0.0) {
+      a.y[yi] = acc;
+    } else {
+      // mul!(y,A,x,alpha,beta): y = alpha*(A*x) + beta*y
+      const double by = a.beta == 0.0 ? 0.0 : __dmul_rn(a.beta, a.y[yi]);
+      a.y[yi] = __dadd_rn(__dmul_rn(a.alpha, acc), by);
+    }
+  }
+}
+
+template <typename PtrT, bool FUSED>
+static void launch_spmv_t(const SpmvArgs<PtrT> &a, int rows, cudaStream_t st) {
+  const int64_t grid = (a.nrows + rows - 1) / rows;
+  switch (rows) {
+    case 256: k_spmv_stream<PtrT, 256, 2048, FUSED><<<(unsigned)grid, SPMV_BLOCK, 0, st>>>(a); break;
+    case 128: k_spmv_stream<PtrT, 128, 2048, FUSED><<<(unsigned)grid, SPMV_BLOCK, 0, st>>>(a); break;
+    case 64: k_spmv_stream<PtrT, 64, 2048, FUSED><<<(unsigned)grid, SPMV_BLOCK, 0, st>>>(a); break;
+    default: k_spmv_stream<PtrT, 32, 2048, FUSED><<<(unsigned)grid, SPMV_BLOCK, 0, st>>>(a); break;
+  }
+}
+
+int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, bool fused, int, const pa_vec *) {
+  pa_ctx *c = A->ctx;
+  for (int k = 0; k < c->nlocal; ++k) {
+    MatPart &m = A->parts[k];
+    if (m.nrows == 0) continue;
+    const PlanPart &cp = A->cols->parts[k];
+    const PlanPart &rp = A->rows->parts[k];
+    const bool f = fused && cp.n_ghost > 0;
+    int rows = (int)pa_knob(c, "spmv_rows", 0);
+    if (rows != 256 && rows != 128 && rows != 64 && rows != 32) rows = m.rows_per_cta;
+    auto fill = [&](auto &a) {
+      a.nrows = m.nrows;
+      a.colval = m.d_colval;
+      a.nzval = m.d_nzval;
+      a.x = x->d[k];
+      a.y = y->d[k];
+      a.rowmap = rp.prefix ? nullptr : rp.d_own_to_local;
+      a.alpha = alpha;
+      a.beta = beta;
+      a.n_own_cols = cp.n_own;
+      a.gslot = cp.d_gslot_by_gid;
+      a.grlid = cp.d_grlid_by_gid;
+      a.peers = pa_peer_ptrs(x, k);
+    };
+    if (m.ptr64) {
+      SpmvArgs<int64_t> a;
+      a.rowptr = (const int64_t *)m.d_rowptr;
+      fill(a);
+      if (f) launch_spmv_t<int64_t, true>(a, rows, c->stream); else launch_spmv_t<int64_t, false>(a, rows, c->stream);
+    } else {
+      SpmvArgs<int32_t> a;
+      a.rowptr = (const int32_t *)m.d_rowptr;
+      fill(a);
+      if (f) launch_spmv_t<int32_t, true>(a, rows, c->stream); else launch_spmv_t<int32_t, false>(a, rows, c->stream);
+    }
+    c->launches++;
+  }
+  PA_CUDA(cudaGetLastError());
+  return PA_OK;
+}
+
+static int check_mul_args(pa_mat *A, pa_vec *x, pa_vec *y) {
+  PA_CHECK(A && x && y, PA_EINVAL, "pa_spmv: null argument");
+  PA_CHECK(A->committed, PA_ESTATE, "pa_spmv: matrix not committed");
+  PA_CHECK(x != y && x->offset != y->offset, PA_EINVAL, "pa_spmv: x and y must not alias");
+  PA_CHECK(x->plan->ctx == A->ctx && y->plan->ctx == A->ctx, PA_EINVAL, "pa_spmv: operands live on different backends");
+  for (int k = 0; k < A->ctx->nlocal; ++k) {
+    // @boundscheck matching_own_indices / matching_ghost_indices (src/p_sparse_matrix.jl:2091-2093)
+    const PlanPart &cp = A->cols->parts[k], &xp = x->plan->parts[k], &rp = A->rows->parts[k], &yp = y->plan->parts[k];
+    PA_CHECK(cp.n_own == xp.n_own && cp.n_local == xp.n_local, PA_EINVAL,
+             "pa_spmv: x does not match axes(A,2) on part %d (own %lld vs %lld, local %lld vs %lld)", A->ctx->part_ids[k] + 1,
+             (long long)xp.n_own, (long long)cp.n_own, (long long)xp.n_local, (long long)cp.n_local);
+    PA_CHECK(rp.n_own == yp.n_own && (rp.prefix == yp.prefix), PA_EINVAL, "pa_spmv: y does not match axes(A,1) on part %d", A->ctx->part_ids[k] + 1);
+    PA_CHECK(yp.n_local >= rp.n_own, PA_EINVAL, "pa_spmv: y too short");
+  }
+  return PA_OK;
+}
+
+extern "C" int pa_spmv(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, uint32_t flags) {
+  PA_TRY(check_mul_args(A, x, y));
+  pa_ctx *c = A->ctx;
+  PA_CUDA(cudaSetDevice(c->device));
+  PA_TRY(pa_before_write(c));
+  bool fused = !(flags & PA_SPMV_EXPLICIT_EXCHANGE) && pa_knob(c, "no_fuse", 0) == 0;
+  for (int k = 0; k < c->nlocal; ++k) fused = fused && x->plan->parts[k].prefix;
+  // the exchange plan of x is the one that knows where the ghosts live (it equals the column plan)
+  pa_plan *xp = x->plan;
+  PA_TRY(pa_collective_begin(xp));
+  if (!fused) {
+    PA_TRY(pa_launch_consistent(x));
+    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, false, -1, nullptr));
+  } else {
+    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, true, -1, nullptr));
+    if (!(flags & PA_SPMV_SKIP_GHOST_REFRESH)) PA_TRY(pa_launch_consistent(x));
+  }
+  return pa_collective_end(xp);
+}
+
+// ------------------------------------------------------------------ matrix objects
+extern "C" int pa_mat_create(pa_plan *rows, pa_plan *cols, pa_mat **out) {
+  PA_CHECK(rows && cols && out && rows->committed && cols->committed, PA_ESTATE, "pa_mat_create: plans missing or not committed");
+  PA_CHECK(rows->ctx == cols->ctx, PA_EINVAL, "pa_mat_create: row and column plans live on different backends");
+  pa_mat *A = new pa_mat();
+  A->ctx = rows->ctx;
+  A->rows = rows;
+  A->cols = cols;
+  A->parts.resize(A->ctx->nlocal);
+  *out = A;
+  return PA_OK;
+}
+
+static void free_part(MatPart &m) {
+  cudaFree(m.d_rowptr);
+  cudaFree(m.d_colval);
+  cudaFree(m.d_nzval);
+  m = MatPart();
+}
+
+extern "C" int pa_mat_destroy(pa_mat *A) {
+  if (!A) return PA_OK;
+  cudaSetDevice(A->ctx->device);
+  cudaStreamSynchronize(A->ctx->stream);
+  for (auto &m : A->parts) free_part(m);
+  delete A;
+  return PA_OK;
+}
+
+static int64_t rd(const void *p, int bits, int64_t i) { return bits == 64 ? ((const int64_t *)p)[i] : (int64_t)((const int32_t *)p)[i]; }
+
+static int choose_rows(int64_t nrows, int64_t nnz) {
+  double avg = nrows ? (double)nnz / (double)nrows : 0.0;
+  return avg <= 8.0 ? 256 : (avg <= 16.0 ? 128 : (avg <= 32.0 ? 64 : 32));
+}
+
+static int upload_csr(pa_ctx *c, MatPart &m, int64_t nrows, int64_t ncols, const std::vector<int64_t> &rp,
+                      const std::vector<int32_t> &cv, const std::vector<double> &nz) {
+  free_part(m);
+  m.nrows = nrows;
+  m.ncols = ncols;
+  m.nnz = rp[nrows];
+  m.ptr64 = m.nnz >= (1ll << 31);
+  m.rows_per_cta = choose_rows(nrows, m.nnz);
+  if (m.ptr64) {
+    PA_CUDA(cudaMalloc(&m.d_rowptr, (nrows + 1) * sizeof(int64_t)));
+    PA_CUDA(cudaMemcpyAsync(m.d_rowptr, rp.data(), (nrows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+  } else {
+    std::vector<int32_t> r32(rp.begin(), rp.end());
+    PA_CUDA(cudaMalloc(&m.d_rowptr, (nrows + 1) * sizeof(int32_t)));
+    PA_CUDA(cudaMemcpyAsync(m.d_rowptr, r32.data(), (nrows + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    PA_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  if (m.nnz) {
+    PA_CUDA(cudaMalloc((void **)&m.d_colval, m.nnz * sizeof(int32_t)));
+    PA_CUDA(cudaMalloc((void **)&m.d_nzval, m.nnz * sizeof(double)));
+    PA_CUDA(cudaMemcpyAsync(m.d_colval, cv.data(), m.nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    PA_CUDA(cudaMemcpyAsync(m.d_nzval, nz.data(), m.nnz * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
+  PA_CUDA(cudaStreamSynchronize(c->stream));
+  m.set = true;
+  return PA_OK;
+}
+
+static int mat_part_args(pa_mat *A, int32_t k, int64_t nrows, const char *who) {
+  PA_CHECK(A && !A->committed, PA_ESTATE, "%s: matrix missing or already committed", who);
+  PA_CHECK(k >= 0 && k < A->ctx->nlocal, PA_EINVAL, "%s: local part %d out of range", who, k);
+  PA_CHECK(nrows == A->rows->parts[k].n_own, PA_EINVAL, "%s: %lld rows given, the row partition owns %lld", who, (long long)nrows,
+           (long long)A->rows->parts[k].n_own);
+  PA_CUDA(cudaSetDevice(A->ctx->device));
+  return PA_OK;
+}
+
+extern "C" int pa_mat_set_csr(pa_mat *A, int32_t k, int64_t nrows, int64_t ncols, int32_t index_base, int32_t ptr_bits,
+                              int32_t col_bits, const void *rowptr, const void *colval, const double *nzval) {
+  PA_TRY(mat_part_args(A, k, nrows, "pa_mat_set_csr"));
+  PA_CHECK((ptr_bits == 32 || ptr_bits == 64) && (col_bits == 32 || col_bits == 64) && (index_base == 0 || index_base == 1) && rowptr,
+           PA_EINVAL, "pa_mat_set_csr: bad index description");
+  const PlanPart &cp = A->cols->parts[k];
+  PA_CHECK(ncols == cp.n_local, PA_EINVAL, "pa_mat_set_csr: %lld columns given, the column partition has %lld local ids",
+           (long long)ncols, (long long)cp.n_local);
+  std::vector<int64_t> rp(nrows + 1);
+  for (int64_t i = 0; i <= nrows; ++i) rp[i] = rd(rowptr, ptr_bits, i) - index_base;
+  PA_CHECK(rp[0] == 0, PA_EINVAL, "pa_mat_set_csr: rowptr does not start at the index base");
+  for (int64_t i = 0; i < nrows; ++i) PA_CHECK(rp[i + 1] >= rp[i], PA_EINVAL, "pa_mat_set_csr: rowptr not monotone at row %lld", (long long)i);
+  int64_t nnz = rp[nrows];
+  PA_CHECK(nnz == 0 || (colval && nzval), PA_EINVAL, "pa_mat_set_csr: null colval/nzval");
+  std::vector<int32_t> cv(nnz);
+  for (int64_t p = 0; p < nnz; ++p) {
+    int64_t cidx = rd(colval, col_bits, p) - index_base;
+    PA_CHECK(cidx >= 0 && cidx < ncols, PA_EINVAL, "pa_mat_set_csr: column id %lld out of range at entry %lld", (long long)(cidx + index_base), (long long)p);
+    cv[p] = (int32_t)cidx;
+  }
+  std::vector<double> nz(nzval, nzval + nnz);
+  return upload_csr(A->ctx, A->parts[k], nrows, ncols, rp, cv, nz);
+}
+
+extern "C" int pa_mat_set_csr_split(pa_mat *A, int32_t k, int64_t nrows, int32_t index_base, int32_t ptr_bits, int32_t col_bits,
+                                    const void *rowptr_oo, const void *colval_oo, const double *nzval_oo,
+                                    const void *rowptr_oh, const void *colval_oh, const double *nzval_oh) {
+  PA_TRY(mat_part_args(A, k, nrows, "pa_mat_set_csr_split"));
+  PA_CHECK((ptr_bits == 32 || ptr_bits == 64) && (col_bits == 32 || col_bits == 64) && (index_base == 0 || index_base == 1) && rowptr_oo && rowptr_oh,
+           PA_EINVAL, "pa_mat_set_csr_split: bad index description");
+  const PlanPart &cp = A->cols->parts[k];
+  std::vector<int64_t> rp(nrows + 1, 0);
+  for (int64_t i = 0; i < nrows; ++i) {
+    int64_t a = rd(rowptr_oo, ptr_bits, i + 1) - rd(rowptr_oo, ptr_bits, i), b = rd(rowptr_oh, ptr_bits, i + 1) - rd(rowptr_oh, ptr_bits, i);
+    PA_CHECK(a >= 0 && b >= 0, PA_EINVAL, "pa_mat_set_csr_split: rowptr not monotone at row %lld", (long long)i);
+    rp[i + 1] = rp[i] + a + b;
+  }
+  int64_t nnz = rp[nrows];
+  std::vector<int32_t> cv(nnz);
+  std::vector<double> nz(nnz);
+  for (int64_t i = 0; i < nrows; ++i) {
+    int64_t q = rp[i];
+    for (int64_t p = rd(rowptr_oo, ptr_bits, i) - index_base; p < rd(rowptr_oo, ptr_bits, i + 1) - index_base; ++p, ++q) {
+      int64_t o = rd(colval_oo, col_bits, p) - index_base;
+      PA_CHECK(o >= 0 && o < cp.n_own, PA_EINVAL, "pa_mat_set_csr_split: own column id out of range");
+      cv[q] = cp.prefix ? (int32_t)o : cp.own_to_local[o];
+      nz[q] = nzval_oo[p];
+    }
+    for (int64_t p = rd(rowptr_oh, ptr_bits, i) - index_base; p < rd(rowptr_oh, ptr_bits, i + 1) - index_base; ++p, ++q) {
+      int64_t g = rd(colval_oh, col_bits, p) - index_base;
+      PA_CHECK(g >= 0 && g < cp.n_ghost, PA_EINVAL, "pa_mat_set_csr_split: ghost column id out of range");
+      cv[q] = cp.prefix ? (int32_t)(cp.n_own + g) : cp.ghost_to_local[g];
+      nz[q] = nzval_oh[p];
+    }
+  }
+  return upload_csr(A->ctx, A->parts[k], nrows, cp.n_local, rp, cv, nz);
+}
+
+extern "C" int pa_mat_commit(pa_mat *A) {
+  PA_CHECK(A && !A->committed, PA_ESTATE, "pa_mat_commit: matrix missing or already committed");
+  for (int k = 0; k < A->ctx->nlocal; ++k) PA_CHECK(A->parts[k].set, PA_ESTATE, "pa_mat_commit: local part %d not set", k);
+  A->committed = true;
+  return PA_OK;
+}
+
+extern "C" int pa_mat_nnz(const pa_mat *A, int32_t k, int64_t *out) {
+  PA_CHECK(A && out && k >= 0 && k < A->ctx->nlocal && A->parts[k].set, PA_EINVAL, "pa_mat_nnz: bad arguments");
+  *out = A->parts[k].nnz;
+  return PA_OK;
+}
+
+__global__ void k_narrow(const int64_t *in, int32_t *out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int32_t)in[i];
+}
+
+extern "C" int pa_mat_download_csr(const pa_mat *A, int32_t k, int64_t *rowptr, int32_t *colval, double *nzval) {
+  PA_CHECK(A && k >= 0 && k < A->ctx->nlocal && A->parts[k].set, PA_EINVAL, "pa_mat_download_csr: bad arguments");
+  pa_ctx *c = A->ctx;
+  const MatPart &m = A->parts[k];
+  PA_CUDA(cudaSetDevice(c->device));
+  if (rowptr) {
+    if (m.ptr64) {
+      PA_CUDA(cudaMemcpyAsync(rowptr, m.d_rowptr, (m.nrows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    } else {
+      std::vector<int32_t> tmp(m.nrows + 1);
+      PA_CUDA(cudaMemcpyAsync(tmp.data(), m.d_rowptr, (m.nrows + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+      PA_CUDA(cudaStreamSynchronize(c->stream));
+      for (int64_t i = 0; i <= m.nrows; ++i) rowptr[i] = tmp[i];
+    }
+  }
+  if (colval && m.nnz) PA_CUDA(cudaMemcpyAsync(colval, m.d_colval, m.nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (nzval && m.nnz) PA_CUDA(cudaMemcpyAsync(nzval, m.d_nzval, m.nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PA_CUDA(cudaStreamSynchronize(c->stream));
+  return PA_OK;
+}
+
+__global__ void k_fill_f64(double *v, int64_t n, double a) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = a;
+}
+
+extern "C" int pa_mat_fill_stored(pa_mat *A, double a) {
+  PA_CHECK(A, PA_EINVAL, "pa_mat_fill_stored: null matrix");
+  pa_ctx *c = A->ctx;
+  PA_CUDA(cudaSetDevice(c->device));
+  for (auto &m : A->parts)
+    if (m.set && m.nnz) {
+      k_fill_f64<<<148 * 8, 256, 0, c->stream>>>(m.d_nzval, m.nnz, a);
+      c->launches++;
+    }
+  PA_CUDA(cudaGetLastError());
+  return PA_OK;
+}
+
+// ------------------------------------------------------------------ on-device stencil generators
+struct StencilGeom {
+  int kind;
+  int64_t gn[3], lo[3], hi[3], b[3];
+  int64_t n_own, ng;
+  const int64_t *sorted_gid;
+  const int32_t *gid_of_sorted;
+  double diag, off, alpha;
+};
+
+__device__ __forceinline__ int span(int64_t g, int64_t n) { return 3 - (g == 0) - (g == n - 1); }
+
+__global__ void k_stencil_count(StencilGeom s, int64_t *cnt) {
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row <= s.n_own; row += (int64_t)gridDim.x * blockDim.x) {
+    if (row == s.n_own) {
+      cnt[row] = 0;
+      continue;
+    }
+    const int64_t ix = row % s.b[0], iy = (row / s.b[0]) % s.b[1], iz = row / (s.b[0] * s.b[1]);
+    const int64_t gx = s.lo[0] + ix, gy = s.lo[1] + iy, gz = s.lo[2] + iz;
+    const int cx = span(gx, s.gn[0]), cy = span(gy, s.gn[1]), cz = span(gz, s.gn[2]);
+    cnt[row] = s.kind == 27 ? cx * cy * cz : 1 + (cx - 1) + (cy - 1) + (cz - 1);
+  }
+}
+
+template <typename PtrT>
+__global__ void k_stencil_fill(StencilGeom s, const PtrT *rowptr, int32_t *colval, double *nzval, double *rhs, int *err) {
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < s.n_own; row += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ix = row % s.b[0], iy = (row / s.b[0]) % s.b[1], iz = row / (s.b[0] * s.b[1]);
+    const int64_t gx = s.lo[0] + ix, gy = s.lo[1] + iy, gz = s.lo[2] + iz;
+    int64_t p = (int64_t)rowptr[row];
+    const int64_t p0 = p;
+    int32_t gc[27];
+    double gv[27];
+    int ngc = 0;
+    for (int sz = -1; sz <= 1; ++sz)
+      for (int sy = -1; sy <= 1; ++sy)
+        for (int sx = -1; sx <= 1; ++sx) {
+          if (s.kind == 7 && (abs(sx) + abs(sy) + abs(sz)) > 1) continue;
+          const int64_t cx = gx + sx, cy = gy + sy, cz = gz + sz;
+          if (cx < 0 || cx >= s.gn[0] || cy < 0 || cy >= s.gn[1] || cz < 0 || cz >= s.gn[2]) continue;
+          const double v = (sx == 0 && sy == 0 && sz == 0) ? s.diag : s.off;
+          if (cx >= s.lo[0] && cx < s.hi[0] && cy >= s.lo[1] && cy < s.hi[1] && cz >= s.lo[2] && cz < s.hi[2]) {
+            colval[p] = (int32_t)((cx - s.lo[0]) + s.b[0] * ((cy - s.lo[1]) + s.b[1] * (cz - s.lo[2])));
+            nzval[p++] = v;
+          } else {
+            const int64_t gid = cx + s.gn[0] * (cy + s.gn[1] * cz);
+            int64_t l = 0, h = s.ng - 1, g = -1;
+            while (l <= h) {
+              const int64_t mid = (l + h) >> 1;
+              const int64_t t = s.sorted_gid[mid];
+              if (t == gid) { g = s.gid_of_sorted[mid]; break; }
+              if (t < gid) l = mid + 1; else h = mid - 1;
+            }
+            if (g < 0) { *err = 2; g = 0; }
+            const int32_t col = (int32_t)(s.n_own + g);
+            int q = ngc++;
+            while (q > 0 && gc[q - 1] > col) { gc[q] = gc[q - 1]; gv[q] = gv[q - 1]; --q; }
+            gc[q] = col;
+            gv[q] = v;
+          }
+        }
+    for (int q = 0; q < ngc; ++q) { colval[p] = gc[q]; nzval[p++] = gv[q]; }
+    if (rhs) rhs[row] = s.kind == 27 ? 27.0 - (double)(p - p0) : s.alpha * (double)(7 - (p - p0));
+  }
+}
+
+extern "C" int pa_mat_set_stencil(pa_mat *A, int32_t k, int32_t kind, const int64_t *gn, const int64_t *lo, const int64_t *hi,
+                                  int64_t ng, const int64_t *ghost_gid_sorted, const int32_t *ghost_id_of_sorted, pa_vec *rhs) {
+  PA_CHECK(gn && lo && hi && (kind == 7 || kind == 27), PA_EINVAL, "pa_mat_set_stencil: bad arguments");
+  StencilGeom s;
+  s.kind = kind;
+  s.n_own = 1;
+  for (int d = 0; d < 3; ++d) {
+    s.gn[d] = gn[d]; s.lo[d] = lo[d]; s.hi[d] = hi[d]; s.b[d] = hi[d] - lo[d];
+    PA_CHECK(lo[d] >= 0 && hi[d] > lo[d] && hi[d] <= gn[d], PA_EINVAL, "pa_mat_set_stencil: bad box");
+    s.n_own *= s.b[d];
+  }
+  PA_TRY(mat_part_args(A, k, s.n_own, "pa_mat_set_stencil"));
+  pa_ctx *c = A->ctx;
+  const PlanPart &cp = A->cols->parts[k];
+  PA_CHECK(cp.prefix && cp.n_own == s.n_own && cp.n_ghost == ng, PA_EINVAL,
+           "pa_mat_set_stencil: column partition does not match the box (own %lld/%lld, ghost %lld/%lld)", (long long)cp.n_own,
+           (long long)s.n_own, (long long)cp.n_ghost, (long long)ng);
+  PA_CHECK(ng == 0 || (ghost_gid_sorted && ghost_id_of_sorted), PA_EINVAL, "pa_mat_set_stencil: null ghost tables");
+  if (rhs) PA_CHECK(rhs->plan->parts[k].n_own == s.n_own && rhs->plan->parts[k].prefix, PA_EINVAL, "pa_mat_set_stencil: rhs does not match");
+  s.ng = ng;
+  s.alpha = (double)(gn[0] + 1) * (double)(gn[1] + 1) * (double)(gn[2] + 1);  // prod(n_i+1), src/gallery.jl:36
+  s.diag = kind == 7 ? s.alpha * 2 * 3 : 26.0;
+  s.off = kind == 7 ? -s.alpha : -1.0;
+  int64_t *d_sg = nullptr;
+  int32_t *d_sl = nullptr;
+  if (ng) {
+    PA_CUDA(cudaMalloc((void **)&d_sg, ng * sizeof(int64_t)));
+    PA_CUDA(cudaMalloc((void **)&d_sl, ng * sizeof(int32_t)));
+    PA_CUDA(cudaMemcpyAsync(d_sg, ghost_gid_sorted, ng * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    PA_CUDA(cudaMemcpyAsync(d_sl, ghost_id_of_sorted, ng * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  }
+  s.sorted_gid = d_sg;
+  s.gid_of_sorted = d_sl;
+  MatPart &m = A->parts[k];
+  free_part(m);
+  const int64_t n = s.n_own;
+  int64_t *d_cnt = nullptr, *d_rp64 = nullptr;
+  PA_CUDA(cudaMalloc((void **)&d_cnt, (n + 1) * sizeof(int64_t)));
+  PA_CUDA(cudaMalloc((void **)&d_rp64, (n + 1) * sizeof(int64_t)));
+  const int grid = 148 * 8;
+  k_stencil_count<<<grid, 256, 0, c->stream>>>(s, d_cnt);
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_cnt, d_rp64, n + 1, c->stream);
+  void *d_tmp = nullptr;
+  PA_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+  PA_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_cnt, d_rp64, n + 1, c->stream));
+  int64_t nnz = 0;
+  PA_CUDA(cudaMemcpyAsync(&nnz, d_rp64 + n, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  PA_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_tmp);
+  cudaFree(d_cnt);
+  m.nrows = n;
+  m.ncols = cp.n_local;
+  m.nnz = nnz;
+  m.ptr64 = nnz >= (1ll << 31);
+  m.rows_per_cta = choose_rows(n, nnz);
+  PA_CUDA(cudaMalloc((void **)&m.d_colval, std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
+  PA_CUDA(cudaMalloc((void **)&m.d_nzval, std::max<int64_t>(nnz, 1) * sizeof(double)));
+  double *d_rhs = nullptr;
+  if (rhs) {
+    PA_TRY(pa_before_write(c));
+    PA_CUDA(cudaMemsetAsync(rhs->d[k], 0, rhs->plan->parts[k].n_local * sizeof(double), c->stream));
+    d_rhs = rhs->d[k];
+  }
+  if (m.ptr64) {
+    m.d_rowptr = d_rp64;
+    k_stencil_fill<int64_t><<<grid, 256, 0, c->stream>>>(s, d_rp64, m.d_colval, m.d_nzval, d_rhs, c->d_err);
+  } else {
+    PA_CUDA(cudaMalloc(&m.d_rowptr, (n + 1) * sizeof(int32_t)));
+    k_narrow<<<grid, 256, 0, c->stream>>>(d_rp64, (int32_t *)m.d_rowptr, n + 1);
+    k_stencil_fill<int32_t><<<grid, 256, 0, c->stream>>>(s, (const int32_t *)m.d_rowptr, m.d_colval, m.d_nzval, d_rhs, c->d_err);
+    c->launches++;
+  }
+  c->launches += 3;
+  PA_CUDA(cudaGetLastError());
+  PA_CUDA(cudaStreamSynchronize(c->stream));
+  if (!m.ptr64) cudaFree(d_rp64);
+  cudaFree(d_sg);
+  cudaFree(d_sl);
+  int herr = 0;
+  PA_CUDA(cudaMemcpy(&herr, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (herr == 2) {
+    cudaMemset(c->d_err, 0, sizeof(int));
+    pa_set_error("pa_mat_set_stencil: a stencil neighbour outside the own box is missing from the ghost table");
+    return PA_EINVAL;
+  }
+  m.set = true;
+  return PA_OK;
+}

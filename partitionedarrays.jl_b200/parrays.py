@@ -1,0 +1,545 @@
+"""Host-side mirror of the reference's operator API for the hot path, on the CUDAArray backend.
+
+Same names, argument meaning and error behaviour as the reference (file:line in /root/reference):
+  with_cuda / CUDAArray      <-> with_debug / DebugArray (src/debug_array.jl:7-31), with_mpi / MPIArray (src/mpi_array.jl:42-117)
+  PRange                     <-> src/p_range.jl:1776-1842
+  PVector, pvector/pfill/pzeros/pones, own_values/ghost_values/local_values, consistent!, assemble!,
+  dot, norm, sum, copy!, fill!, rmul!, broadcast updates            <-> src/p_vector.jl
+  PSparseMatrix, psparse(…; assembled=true), mul!, fillstored!       <-> src/p_sparse_matrix.jl
+Every data-touching call goes through the C ABI (include/pa_b200.h) into the CUDA library; this module
+holds no arithmetic.  Julia's `f!` is spelled `f_` here (consistent_ = consistent!)."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import check, f64, i32, i64, ptr
+from . import prange as pr
+
+
+class CUDAArray:
+    """The array-of-parts backend.  ``mode='sequential'``: every part lives in this process on one GPU
+    (the DebugArray execution model); ``mode='distributed'``: one part per process / GPU, rank r owns
+    part r+1 (the MPIArray model), peers mapped with CUDA IPC, scalars all-reduced with NCCL."""
+
+    def __init__(self, nparts: int, mode: str = "sequential", device: Optional[int] = None, arena_bytes: int = 1 << 30,
+                 stream: Optional[int] = None, group=None):
+        L = _capi.lib()
+        self.nparts, self.mode = int(nparts), mode
+        self.group = group
+        if mode == "sequential":
+            self.parts = list(range(1, nparts + 1))
+            self.rank, self.world = 0, 1
+            device = 0 if device is None else device
+        elif mode == "distributed":
+            import torch.distributed as dist
+
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+            if self.world != nparts:
+                raise ValueError(f"distributed CUDAArray needs one process per part: {self.world} processes, {nparts} parts")
+            self.parts = [self.rank + 1]
+            device = int(os.environ.get("LOCAL_RANK", self.rank)) if device is None else device
+        else:
+            raise ValueError("mode must be 'sequential' or 'distributed'")
+        self.device = device
+        h = C.c_void_p()
+        ids = i32(self.parts)
+        check(L.pa_ctx_create(nparts, len(self.parts), ptr(ids), device, arena_bytes, stream, C.byref(h)))
+        self.h = h
+        if mode == "distributed" and self.world > 1:
+            self._link_peers()
+
+    # -- distributed plumbing (torch.distributed is only used to move handles around) --
+    def _link_peers(self):
+        import torch.distributed as dist
+
+        L = _capi.lib()
+        handle = np.zeros(64, dtype=np.uint8)
+        check(L.pa_ctx_arena_export(self.h, 0, ptr(handle)))
+        uid = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0:
+            check(L.pa_nccl_unique_id(ptr(uid)))
+        objs = [None] * self.world
+        dist.all_gather_object(objs, (handle.tobytes(), uid.tobytes()), group=self.group)
+        for r, (hb, _) in enumerate(objs):
+            if r != self.rank:
+                hh = np.frombuffer(hb, dtype=np.uint8).copy()
+                check(L.pa_ctx_arena_import(self.h, r + 1, ptr(hh)))
+        uid0 = np.frombuffer(objs[0][1], dtype=np.uint8).copy()
+        check(L.pa_ctx_nccl_init(self.h, ptr(uid0), self.rank, self.world))
+        dist.barrier(group=self.group)
+
+    def gather_all(self, local_objs: list) -> list:
+        """Objects of all parts ordered by part id (setup-time metadata only)."""
+        if self.mode == "sequential" or self.world == 1:
+            return list(local_objs)
+        import torch.distributed as dist
+
+        out = [None] * self.world
+        dist.all_gather_object(out, local_objs, group=self.group)
+        return [o for per_rank in out for o in per_rank]
+
+    def allreduce_max(self, v: int) -> int:
+        if self.mode == "sequential" or self.world == 1:
+            return v
+        return max(self.gather_all([v]))
+
+    # -- reference-like helpers --
+    def linear_indices(self):
+        return list(self.parts)
+
+    def i_am_main(self) -> bool:
+        return 1 in self.parts
+
+    def map(self, f: Callable, *arrays):
+        """map over the local parts (host metadata only, like the reference's map on index arrays)."""
+        return [f(*(a[k] for a in arrays)) for k in range(len(self.parts))]
+
+    def sync(self):
+        check(_capi.lib().pa_ctx_sync(self.h))
+
+    def launch_count(self) -> int:
+        out = C.c_int64()
+        check(_capi.lib().pa_ctx_launch_count(self.h, C.byref(out)))
+        return out.value
+
+    def set_knob(self, key: str, value: int):
+        check(_capi.lib().pa_ctx_set_knob(self.h, key.encode(), int(value)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            _capi.lib().pa_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def with_cuda(f: Callable, nparts: int = 1, **kw):
+    """with_cuda(f) = f(distribute) — mirrors with_debug (src/debug_array.jl:7-9).  ``distribute(ranks)``
+    returns the backend whose ``parts`` are the part ids held by this process."""
+    backend = CUDAArray(nparts, **kw)
+    try:
+        return f(lambda ranks=None: backend)
+    finally:
+        backend.close()
+
+
+class PRange:
+    """PRange(index_partition) (src/p_range.jl:1776-1787) on the CUDA backend: the per-part
+    AbstractLocalIndices plus the device-resident exchange plan (AssemblyCache, :354-387)."""
+
+    def __init__(self, backend: CUDAArray, indices: List[pr.LocalIndices]):
+        assert len(indices) == len(backend.parts)
+        self.backend, self.indices = backend, indices
+        self._plan = None
+        self.plans: Optional[List[pr.PartPlan]] = None
+
+    def partition(self):
+        return self.indices
+
+    def __len__(self):
+        return self.indices[0].n_global
+
+    @property
+    def plan(self):
+        if self._plan is None:
+            L = _capi.lib()
+            b = self.backend
+            self.plans = pr.build_plans(self.indices, b.gather_all)
+            sym = b.allreduce_max(max(ind.n_local for ind in self.indices))
+            h = C.c_void_p()
+            check(L.pa_plan_create(b.h, C.byref(h)))
+            for k, (ind, p) in enumerate(zip(self.indices, self.plans)):
+                o2l = None if ind.own_is_prefix else i32(ind.own_to_local)
+                g2l = None if ind.own_is_prefix else i32(ind.ghost_to_local)
+                arrs = [i32(a) for a in (p.nbr_snd, p.snd_ptrs, p.snd_lids, p.snd_remote_lids, p.nbr_rcv, p.rcv_ptrs, p.rcv_lids, p.rcv_remote_lids)]
+                check(L.pa_plan_set_part(h, k, ind.n_local, ind.n_own, ptr(o2l), ptr(g2l), len(p.nbr_snd), ptr(arrs[0]), ptr(arrs[1]),
+                                         ptr(arrs[2]), ptr(arrs[3]), len(p.nbr_rcv), ptr(arrs[4]), ptr(arrs[5]), ptr(arrs[6]), ptr(arrs[7])))
+            check(L.pa_plan_commit(h, sym))
+            self._plan = h
+        return self._plan
+
+    def __del__(self):
+        try:
+            if self._plan is not None and self.backend.h:
+                _capi.lib().pa_plan_destroy(self._plan)
+        except Exception:
+            pass
+
+
+def uniform_partition(backend: CUDAArray, np_, n, ghost=None, periodic=None) -> PRange:
+    """uniform_partition(ranks,np,n[,ghost,periodic]) (src/p_range.jl:585-599)."""
+    if isinstance(np_, int):
+        np_, n = (np_,), (n,)
+        ghost = None if ghost is None else (ghost,) if isinstance(ghost, bool) else ghost
+        periodic = None if periodic is None else (periodic,) if isinstance(periodic, bool) else periodic
+    assert int(np.prod(np_)) == backend.nparts
+    return PRange(backend, [pr.uniform_partition_part(p, np_, n, ghost, periodic) for p in backend.parts])
+
+
+def variable_partition(backend: CUDAArray, n_own_all: Sequence[int], n_global: int) -> PRange:
+    return PRange(backend, [pr.variable_partition_part(p, n_own_all, n_global) for p in backend.parts])
+
+
+class PVector:
+    """PVector (src/p_vector.jl:324-345): one device-resident local array per part (own + ghost entries in the
+    reference's local order)."""
+
+    def __init__(self, rows: PRange):
+        self.rows = rows
+        h = C.c_void_p()
+        check(_capi.lib().pa_vec_create(rows.plan, C.byref(h)))
+        self.h = h
+
+    # --- construction / transfer ---
+    @property
+    def backend(self):
+        return self.rows.backend
+
+    def set_local_values(self, values: List[np.ndarray]):
+        L = _capi.lib()
+        for k, v in enumerate(values):
+            v = f64(v)
+            check(L.pa_vec_upload(self.h, k, ptr(v), len(v)))
+        self.backend.sync()
+        return self
+
+    def local_values(self) -> List[np.ndarray]:
+        """local_values(v) (src/p_vector.jl:350-373) copied to the host."""
+        L = _capi.lib()
+        out = []
+        for k, ind in enumerate(self.rows.indices):
+            a = np.zeros(ind.n_local, dtype=np.float64)
+            check(L.pa_vec_download(self.h, k, ptr(a), len(a)))
+            out.append(a)
+        return out
+
+    def own_values(self) -> List[np.ndarray]:
+        return [v[ind.own_to_local - 1] for v, ind in zip(self.local_values(), self.rows.indices)]
+
+    def ghost_values(self) -> List[np.ndarray]:
+        return [v[ind.ghost_to_local - 1] for v, ind in zip(self.local_values(), self.rows.indices)]
+
+    def similar(self) -> "PVector":
+        return PVector(self.rows)
+
+    def copy(self) -> "PVector":
+        return PVector(self.rows).copy_(self)
+
+    # --- in-place operations (Julia's f! -> f_) ---
+    def fill_(self, a: float):
+        check(_capi.lib().pa_vec_fill(self.h, float(a)))
+        return self
+
+    def copy_(self, src: "PVector"):
+        check(_capi.lib().pa_vec_copy(self.h, src.h))
+        return self
+
+    def rmul_(self, a: float):
+        check(_capi.lib().pa_vec_scale(self.h, float(a)))
+        return self
+
+    def axpby_(self, a: float, x: "PVector", b: float):
+        """self .= a.*x .+ b.*self"""
+        check(_capi.lib().pa_vec_axpby(self.h, float(a), x.h, float(b)))
+        return self
+
+    def waxpby_(self, a: float, x: "PVector", b: float, y: "PVector"):
+        """self .= a.*x .+ b.*y"""
+        check(_capi.lib().pa_vec_waxpby(self.h, float(a), x.h, float(b), y.h))
+        return self
+
+    def consistent_(self):
+        """consistent!(v) (src/p_vector.jl:747-755); returns a waitable like the reference's task."""
+        check(_capi.lib().pa_vec_consistent(self.h))
+        return _Task(self)
+
+    def assemble_(self):
+        """assemble!(v) (src/p_vector.jl:695-708)."""
+        check(_capi.lib().pa_vec_assemble(self.h))
+        return _Task(self)
+
+    # --- reductions ---
+    def dot(self, other: "PVector") -> float:
+        out = C.c_double()
+        check(_capi.lib().pa_vec_dot(self.h, other.h, C.byref(out)))
+        return out.value
+
+    def norm(self) -> float:
+        out = C.c_double()
+        check(_capi.lib().pa_vec_norm2(self.h, C.byref(out)))
+        return math.sqrt(out.value)
+
+    def sum(self) -> float:
+        out = C.c_double()
+        check(_capi.lib().pa_vec_sum(self.h, C.byref(out)))
+        return out.value
+
+    def collect(self) -> np.ndarray:
+        """collect(v): the global vector (gathered through the host; debugging / tests)."""
+        own = self.own_values()
+        pieces = self.backend.gather_all([(ind.own_to_global, o) for ind, o in zip(self.rows.indices, own)])
+        out = np.zeros(len(self.rows), dtype=np.float64)
+        for g, o in pieces:
+            out[g - 1] = o
+        return out
+
+    def free(self):
+        if getattr(self, "h", None) and self.backend.h:
+            _capi.lib().pa_vec_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class _Task:
+    def __init__(self, obj):
+        self.obj = obj
+
+    def wait(self):
+        self.obj.backend.sync()
+        return self.obj
+
+    fetch = wait
+
+
+def pvector(f: Callable, rows: PRange) -> PVector:
+    """pvector(f, index_partition): f(indices) -> local values (src/p_vector.jl:832-846)."""
+    return PVector(rows).set_local_values([np.asarray(f(ind), dtype=np.float64) for ind in rows.indices])
+
+
+def pfill(a: float, rows: PRange) -> PVector:
+    return PVector(rows).fill_(a)
+
+
+def pzeros(rows: PRange) -> PVector:
+    return pfill(0.0, rows)
+
+
+def pones(rows: PRange) -> PVector:
+    return pfill(1.0, rows)
+
+
+def pvector_from_global(xg: np.ndarray, rows: PRange, ghosts: bool = False) -> PVector:
+    vals = []
+    for ind in rows.indices:
+        v = np.zeros(ind.n_local)
+        v[ind.own_to_local - 1] = xg[ind.own_to_global - 1]
+        if ghosts:
+            v[ind.ghost_to_local - 1] = xg[ind.ghost_to_global - 1]
+        vals.append(v)
+    return PVector(rows).set_local_values(vals)
+
+
+def dot(a: PVector, b: PVector) -> float:
+    return a.dot(b)
+
+
+def norm(a: PVector) -> float:
+    return a.norm()
+
+
+def consistent_(v: PVector):
+    return v.consistent_()
+
+
+def assemble_(v: PVector):
+    return v.assemble_()
+
+
+class PSparseMatrix:
+    """PSparseMatrix (src/p_sparse_matrix.jl:971-991), assembled, per-part CSR on the device."""
+
+    def __init__(self, rows: PRange, cols: PRange):
+        self.rows, self.cols = rows, cols
+        h = C.c_void_p()
+        check(_capi.lib().pa_mat_create(rows.plan, cols.plan, C.byref(h)))
+        self.h = h
+        self.assembled = True
+
+    @property
+    def backend(self):
+        return self.rows.backend
+
+    def axes(self, d: int) -> PRange:
+        return self.rows if d == 1 else self.cols
+
+    def set_csr(self, k: int, rowptr, colval, nzval, index_base: int = 1):
+        """Unsplit local matrix: own rows x local columns (SparseMatrixCSR{Bi,Float64,Ti})."""
+        rowptr, colval = np.ascontiguousarray(rowptr), np.ascontiguousarray(colval)
+        nz = f64(nzval)
+        pb, cb = rowptr.dtype.itemsize * 8, (colval.dtype.itemsize * 8 if len(colval) else 32)
+        check(_capi.lib().pa_mat_set_csr(self.h, k, len(rowptr) - 1, self.cols.indices[k].n_local, index_base, pb, cb, ptr(rowptr),
+                                         ptr(colval), ptr(nz)))
+
+    def set_csr_split(self, k: int, oo, oh, index_base: int = 1):
+        """Split format: oo/oh = (rowptr, colval, nzval) of the own_own and own_ghost blocks."""
+        rp1, cv1, nz1 = (np.ascontiguousarray(a) for a in oo)
+        rp2, cv2, nz2 = (np.ascontiguousarray(a) for a in oh)
+        assert rp1.dtype == rp2.dtype
+        cv2 = cv2.astype(cv1.dtype) if len(cv1) else cv2
+        cv1 = cv1.astype(cv2.dtype)
+        check(_capi.lib().pa_mat_set_csr_split(self.h, k, len(rp1) - 1, index_base, rp1.dtype.itemsize * 8, cv1.dtype.itemsize * 8,
+                                               ptr(rp1), ptr(cv1), ptr(f64(nz1)), ptr(rp2), ptr(cv2), ptr(f64(nz2))))
+
+    def commit(self):
+        check(_capi.lib().pa_mat_commit(self.h))
+        return self
+
+    def nnz(self, k: int = 0) -> int:
+        out = C.c_int64()
+        check(_capi.lib().pa_mat_nnz(self.h, k, C.byref(out)))
+        return out.value
+
+    def download_csr(self, k: int):
+        nnz, nrows = self.nnz(k), self.rows.indices[k].n_own
+        rp, cv, nz = np.zeros(nrows + 1, np.int64), np.zeros(nnz, np.int32), np.zeros(nnz, np.float64)
+        check(_capi.lib().pa_mat_download_csr(self.h, k, ptr(rp), ptr(cv), ptr(nz)))
+        return rp, cv, nz
+
+    def fillstored_(self, a: float):
+        check(_capi.lib().pa_mat_fill_stored(self.h, float(a)))
+        return self
+
+    def free(self):
+        if getattr(self, "h", None) and self.backend.h:
+            _capi.lib().pa_mat_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def mul_(c: PVector, A: PSparseMatrix, b: PVector, alpha: float = 1.0, beta: float = 0.0, flags: int = 0) -> PVector:
+    """mul!(c,A,b[,alpha,beta]) (src/p_sparse_matrix.jl:2090-2142)."""
+    check(_capi.lib().pa_spmv(A.h, b.h, c.h, float(alpha), float(beta), flags))
+    return c
+
+
+def mul_no_lat_(c: PVector, A: PSparseMatrix, b: PVector) -> PVector:
+    """HPCG mul_no_lat! (HPCG/src/hpcg_utils.jl:6-17)."""
+    return mul_(c, A, b)
+
+
+def _coo_to_csr(I, J, V, m, n):
+    """Host COO -> CSR{1} (sorted columns, duplicates summed in input order, ids<1 -> stored (1,1,0));
+    setup-time helper standing in for sparse_matrix/compresscoo (src/sparse_utils.jl:313-405)."""
+    I = np.asarray(I, dtype=np.int64).copy(); J = np.asarray(J, dtype=np.int64).copy(); V = np.asarray(V, dtype=np.float64).copy()
+    bad = (I < 1) | (J < 1)
+    if m * n == 0:
+        I, J, V = I[:0], J[:0], V[:0]
+    else:
+        I[bad], J[bad], V[bad] = 1, 1, 0.0
+    order = np.lexsort((J, I))
+    I, J, V = I[order], J[order], V[order]
+    if len(I):
+        new = np.ones(len(I), dtype=bool)
+        new[1:] = (I[1:] != I[:-1]) | (J[1:] != J[:-1])
+        pos = np.cumsum(new) - 1
+        nz = np.zeros(int(pos[-1]) + 1)
+        np.add.at(nz, pos, V)
+        I, J = I[new], J[new]
+    else:
+        nz = V
+    rowptr = np.ones(m + 1, dtype=np.int64)
+    rowptr[1:] = 1 + np.cumsum(np.bincount(I - 1, minlength=m)) if len(I) else 1
+    return rowptr.astype(np.int32), J.astype(np.int32), nz
+
+
+def psparse(I: List, J: List, V: List, rows: PRange, cols: PRange, assembled: bool = True, split_format: bool = True) -> PSparseMatrix:
+    """psparse(I,J,V,row_partition,col_partition; assembled=true) (src/p_sparse_matrix.jl:1150-1286).
+    Per local part: COO in global ids whose rows are owned by that part.  Ghost columns are discovered with
+    find_owner + union_ghost (:1226-1236).  Non-assembled input (rows owned elsewhere) is the 'next' scope
+    row and is rejected here."""
+    if not assembled:
+        raise NotImplementedError("psparse(...; assembled=false): matrix assembly is outside the hot-path scope")
+    b = rows.backend
+    new_cols = []
+    for ind_c, j in zip(cols.indices, J):
+        j = np.asarray(j, dtype=np.int64)
+        owners = _find_owner(cols, ind_c, j)
+        new_cols.append(pr.union_ghost(ind_c, j, owners))
+    colr = PRange(b, new_cols)
+    A = PSparseMatrix(rows, colr)
+    for k, (ind_r, ind_c) in enumerate(zip(rows.indices, colr.indices)):
+        Ik, Jk = np.asarray(I[k], dtype=np.int64), np.asarray(J[k], dtype=np.int64)
+        li = ind_r.global_to_local(Ik).astype(np.int64)
+        lj = ind_c.global_to_local(Jk).astype(np.int64)
+        li[Ik < 1] = 0
+        lj[Jk < 1] = 0
+        if np.any((li == 0) & (Ik >= 1)):
+            raise ValueError("psparse(assembled=true): a row id is not local to its part")
+        rp, cv, nz = _coo_to_csr(li, lj, V[k], ind_r.n_local, ind_c.n_local)
+        # keep own rows only, in own order (ghost rows of an assembled matrix are empty)
+        o2l = ind_r.own_to_local.astype(np.int64)
+        starts, ends = rp[o2l - 1].astype(np.int64), rp[o2l].astype(np.int64)
+        lens = ends - starts
+        rp2 = np.ones(len(o2l) + 1, dtype=np.int64)
+        rp2[1:] = 1 + np.cumsum(lens)
+        take = np.concatenate([np.arange(s - 1, e - 1) for s, e in zip(starts, ends)]) if len(o2l) and lens.sum() else np.zeros(0, dtype=np.int64)
+        cv2, nz2 = cv[take], nz[take]
+        if split_format:
+            # own_own / own_ghost blocks in own / ghost numbering (src/p_sparse_matrix.jl:823-899)
+            l2o = np.zeros(ind_c.n_local + 1, dtype=np.int64); l2o[ind_c.own_to_local] = np.arange(1, ind_c.n_own + 1)
+            l2g = np.zeros(ind_c.n_local + 1, dtype=np.int64); l2g[ind_c.ghost_to_local] = np.arange(1, ind_c.n_ghost + 1)
+            rowid = np.repeat(np.arange(len(o2l)), lens)
+            isown = l2o[cv2] > 0
+            def block(mask, ids):
+                cnt = np.bincount(rowid[mask], minlength=len(o2l))
+                p = np.ones(len(o2l) + 1, dtype=np.int32); p[1:] = 1 + np.cumsum(cnt)
+                return p, ids[mask].astype(np.int32), nz2[mask]
+            A.set_csr_split(k, block(isown, l2o[cv2]), block(~isown, l2g[cv2]))
+        else:
+            A.set_csr(k, rp2.astype(np.int32), cv2, nz2)
+    return A.commit()
+
+
+def _find_owner(cols: PRange, ind: pr.LocalIndices, gids: np.ndarray) -> np.ndarray:
+    """find_owner (src/p_range.jl:346-348): block formula when available, else a gathered table."""
+    if ind.block is not None:
+        return ind.block.owner_of(gids)
+    b = cols.backend
+    if not hasattr(cols, "_owner_table"):
+        tab = np.zeros(len(cols) + 1, dtype=np.int32)
+        for part, own in b.gather_all([(i.part, i.own_to_global) for i in cols.indices]):
+            tab[own] = part
+        cols._owner_table = tab
+    out = np.zeros(len(gids), dtype=np.int32)
+    ok = gids >= 1
+    out[ok] = cols._owner_table[gids[ok]]
+    return out
+
+
+class CGResult:
+    def __init__(self, iters, converged, residual0, residual, history):
+        self.iters, self.converged, self.residual0, self.residual, self.history = iters, converged, residual0, residual, history
+
+
+def ref_cg_(x: PVector, A: PSparseMatrix, b: PVector, tolerance: float = 0.0, maxiter: Optional[int] = None, flags: int = 0) -> CGResult:
+    """ref_cg!(x,A,b; tolerance, maxiter, Pl=Identity) (HPCG/src/ref_cg.jl:119-134) -> x updated in place."""
+    maxiter = len(A.cols) if maxiter is None else int(maxiter)
+    res = _capi.CGResult()
+    hist = np.zeros(maxiter + 1, dtype=np.float64)
+    check(_capi.lib().pa_cg(A.h, x.h, b.h, maxiter, float(tolerance), flags, C.byref(res), ptr(hist)))
+    return CGResult(res.iters, bool(res.converged), res.residual0, res.residual, hist[: res.iters + 1])
+
+
+def opt_cg_(x, A, b, **kw):
+    """opt_cg! forwards to ref_cg! in the reference (HPCG/src/opt_cg.jl:25-32); here it is the fused schedule."""
+    return ref_cg_(x, A, b, **kw)

