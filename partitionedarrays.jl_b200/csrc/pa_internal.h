@@ -117,6 +117,7 @@ struct MatPart {
   double *d_nzval = nullptr;
   bool set = false;
   int rows_per_cta = 256;
+  std::map<int, int64_t> tile_nnz;  // max nnz of a ROWS-row tile, by ROWS (TMA stage sizing)
 };
 
 struct pa_mat {

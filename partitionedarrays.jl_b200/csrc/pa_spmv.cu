@@ -122,6 +122,203 @@ static void launch_spmv_t(const SpmvArgs<PtrT> &a, int rows, cudaStream_t st) {
   }
 }
 
+// ------------------------------------------------------------------ the TMA-pipelined SpMV kernel
+// Persistent CTAs (a multiple of the 148 SMs), warp specialised:
+//  * one producer lane streams each tile's contiguous nzval/colval slice HBM -> shared memory with
+//    cp.async.bulk (the TMA engine; SASS UBLKCP) into a ring of STAGES buffers, completion on an mbarrier,
+//    L2 evict-first (the matrix is read exactly once);
+//  * ROWS consumer threads, one per row: walk the row's entries in shared memory in column order, gather x
+//    (consecutive rows of a banded operator hit consecutive x entries -> coalesced; ghost columns are
+//    NVLink peer loads from the owner's arena) and accumulate `bi += aij*xj` sequentially with separate
+//    multiply and add — the exact arithmetic of the reference's spmv_csr!.
+// The LSU/L1 only sees the x gather and the conflict-free shared-memory reads; the matrix stream never
+// passes through registers.
+struct TmaCfg {
+  int rows, cap, stages;
+  int64_t ntiles;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+
+template <typename PtrT, bool FUSED>
+__global__ void __launch_bounds__(288) k_spmv_tma(const SpmvArgs<PtrT> a, const TmaCfg cfg) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int ROWS = cfg.rows, CAP = cfg.cap, S = cfg.stages;
+  // layout: val[S][CAP+2] | col[S][CAP+8] | p0[S] (int64) | full[S] | empty[S]
+  double *val_s = reinterpret_cast<double *>(smem_raw);
+  int32_t *col_s = reinterpret_cast<int32_t *>(val_s + (size_t)S * (CAP + 2));
+  int64_t *p0_s = reinterpret_cast<int64_t *>(col_s + (size_t)S * (CAP + 8));
+  uint64_t *full = reinterpret_cast<uint64_t *>(p0_s + S);
+  uint64_t *empty = full + S;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, ROWS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int64_t nloc = first < cfg.ntiles ? (cfg.ntiles - first + stride - 1) / stride : 0;
+  if (tid >= ROWS) {
+    // ---------------- producer warp: one elected lane drives the TMA ring
+    if (tid == ROWS) {
+      const uint64_t pol = stream_policy();
+      for (int64_t j = 0; j < nloc; ++j) {
+        const int s = (int)(j % S);
+        if (j >= S) mbar_wait(empty + s, (uint32_t)(((j / S) - 1) & 1));
+        const int64_t t = first + j * stride;
+        const int64_t r0 = t * ROWS, r1 = min(r0 + (int64_t)ROWS, a.nrows);
+        const int64_t p0 = (int64_t)a.rowptr[r0], p1 = (int64_t)a.rowptr[r1];
+        p0_s[s] = p0;
+        const int64_t pv = p0 & ~(int64_t)1, pc = p0 & ~(int64_t)3;
+        const uint32_t bv = (uint32_t)(((p1 - pv + 1) & ~(int64_t)1) * 8), bc = (uint32_t)(((p1 - pc + 3) & ~(int64_t)3) * 4);
+        const bool any = p1 > p0;
+        mbar_expect_tx(full + s, any ? bv + bc : 0u);
+        if (any) {
+          tma_load_1d(val_s + (size_t)s * (CAP + 2), a.nzval + pv, bv, full + s, pol);
+          tma_load_1d(col_s + (size_t)s * (CAP + 8), a.colval + pc, bc, full + s, pol);
+        }
+      }
+    }
+    return;
+  }
+  // ---------------- consumers: one thread per row
+  int64_t rs_n = 0, re_n = 0;
+  if (nloc > 0) {
+    const int64_t row = first * ROWS + tid;
+    if (row < a.nrows) {
+      rs_n = (int64_t)a.rowptr[row];
+      re_n = (int64_t)a.rowptr[row + 1];
+    }
+  }
+  for (int64_t j = 0; j < nloc; ++j) {
+    const int s = (int)(j % S);
+    const int64_t t = first + j * stride;
+    const int64_t row = t * ROWS + tid;
+    const int64_t rs = rs_n, re = re_n;
+    if (j + 1 < nloc) {  // prefetch the next tile's row pointers while this tile is processed
+      const int64_t rown = (t + stride) * ROWS + tid;
+      rs_n = re_n = 0;
+      if (rown < a.nrows) {
+        rs_n = (int64_t)a.rowptr[rown];
+        re_n = (int64_t)a.rowptr[rown + 1];
+      }
+    }
+    mbar_wait(full + s, (uint32_t)((j / S) & 1));
+    if (row < a.nrows) {
+      const int64_t p0 = p0_s[s];
+      const double *vs = val_s + (size_t)s * (CAP + 2) + (rs - (p0 & ~(int64_t)1));
+      const int32_t *cs = col_s + (size_t)s * (CAP + 8) + (rs - (p0 & ~(int64_t)3));
+      const int len = (int)(re - rs);
+      double acc = 0.0;
+      for (int k0 = 0; k0 < len; k0 += 8) {
+        double v[8], xv[8];
+        int32_t c[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const bool ok = k0 + u < len;
+          c[u] = ok ? cs[k0 + u] : -1;
+          v[u] = ok ? vs[k0 + u] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          xv[u] = 0.0;
+          if (c[u] >= 0) {
+            if (FUSED && c[u] >= a.n_own_cols) {
+              const int64_t g = c[u] - a.n_own_cols;
+              xv[u] = __ldcg(a.peers.p[a.gslot[g]] + a.grlid[g]);
+            } else {
+              xv[u] = __ldg(a.x + c[u]);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (k0 + u < len) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+      }
+      mbar_arrive(empty + s);
+      const int64_t yi = a.rowmap ? (int64_t)a.rowmap[row] : row;
+      if (a.alpha == 1.0 && a.beta == 0.0) {
+        a.y[yi] = acc;
+      } else {
+        const double by = a.beta == 0.0 ? 0.0 : __dmul_rn(a.beta, a.y[yi]);
+        a.y[yi] = __dadd_rn(__dmul_rn(a.alpha, acc), by);
+      }
+    } else {
+      mbar_arrive(empty + s);
+    }
+  }
+}
+
+// largest nnz of any ROWS-row tile (decides whether a tile fits one TMA stage)
+template <typename PtrT>
+__global__ void k_max_tile_nnz(const PtrT *rowptr, int64_t nrows, int rows, unsigned long long *out) {
+  const int64_t ntiles = (nrows + rows - 1) / rows;
+  unsigned long long m = 0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r0 = t * rows, r1 = min(r0 + (int64_t)rows, nrows);
+    m = max(m, (unsigned long long)(rowptr[r1] - rowptr[r0]));
+  }
+  atomicMax(out, m);
+}
+
+static int max_tile_nnz(pa_ctx *c, MatPart &m, int rows, int64_t *out) {
+  auto it = m.tile_nnz.find(rows);
+  if (it == m.tile_nnz.end()) {
+    unsigned long long *d = nullptr, h = 0;
+    PA_CUDA(cudaMalloc((void **)&d, sizeof(h)));
+    PA_CUDA(cudaMemsetAsync(d, 0, sizeof(h), c->stream));
+    if (m.ptr64)
+      k_max_tile_nnz<int64_t><<<148 * 4, 256, 0, c->stream>>>((const int64_t *)m.d_rowptr, m.nrows, rows, d);
+    else
+      k_max_tile_nnz<int32_t><<<148 * 4, 256, 0, c->stream>>>((const int32_t *)m.d_rowptr, m.nrows, rows, d);
+    PA_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    PA_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    it = m.tile_nnz.emplace(rows, (int64_t)h).first;
+  }
+  *out = it->second;
+  return PA_OK;
+}
+
+template <typename PtrT>
+static int launch_spmv_tma(pa_ctx *c, const SpmvArgs<PtrT> &a, bool fused, const TmaCfg &cfg, int ctas_per_sm) {
+  const size_t smem = (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (cfg.cap + 8) * 4 + 8 + 16) + 128;
+  auto kern = fused ? k_spmv_tma<PtrT, true> : k_spmv_tma<PtrT, false>;
+  PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t grid = std::min<int64_t>(cfg.ntiles, (int64_t)148 * ctas_per_sm);
+  kern<<<(unsigned)grid, cfg.rows + 32, smem, c->stream>>>(a, cfg);
+  return PA_OK;
+}
+
 int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, bool fused, int, const pa_vec *) {
   pa_ctx *c = A->ctx;
   for (int k = 0; k < c->nlocal; ++k) {
@@ -132,6 +329,22 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, bo
     const bool f = fused && cp.n_ghost > 0;
     int rows = (int)pa_knob(c, "spmv_rows", 0);
     if (rows != 256 && rows != 128 && rows != 64 && rows != 32) rows = m.rows_per_cta;
+    // TMA pipeline configuration (knobs allow sweeping on the GPU without recompiling)
+    TmaCfg cfg;
+    cfg.rows = (int)pa_knob(c, "tma_rows", m.nnz > 12 * m.nrows ? 128 : 256);
+    cfg.stages = (int)pa_knob(c, "tma_stages", 2);
+    int ctas = (int)pa_knob(c, "tma_ctas", 0);
+    bool use_tma = pa_knob(c, "spmv_kernel", 3) == 3 && cfg.rows >= 32 && cfg.rows <= 256 && cfg.rows % 32 == 0 && cfg.stages >= 2;
+    if (use_tma) {
+      int64_t mt = 0;
+      PA_TRY(max_tile_nnz(c, m, cfg.rows, &mt));
+      cfg.cap = (int)((std::max<int64_t>(mt, 64) + 63) / 64 * 64);
+      cfg.ntiles = (m.nrows + cfg.rows - 1) / cfg.rows;
+      const size_t smem = (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (cfg.cap + 8) * 4 + 8 + 16) + 128;
+      if (smem > 200 * 1024) use_tma = false;  // a tile does not fit: irregular rows -> chunked kernel
+      if (!ctas) ctas = std::max<int>(1, std::min<int>(8, (int)((220 * 1024) / (smem + 1024))));
+      ctas = std::min(ctas, 2048 / (cfg.rows + 32));
+    }
     auto fill = [&](auto &a) {
       a.nrows = m.nrows;
       a.colval = m.d_colval;
@@ -150,12 +363,14 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, bo
       SpmvArgs<int64_t> a;
       a.rowptr = (const int64_t *)m.d_rowptr;
       fill(a);
-      if (f) launch_spmv_t<int64_t, true>(a, rows, c->stream); else launch_spmv_t<int64_t, false>(a, rows, c->stream);
+      if (use_tma) PA_TRY(launch_spmv_tma<int64_t>(c, a, f, cfg, ctas));
+      else if (f) launch_spmv_t<int64_t, true>(a, rows, c->stream); else launch_spmv_t<int64_t, false>(a, rows, c->stream);
     } else {
       SpmvArgs<int32_t> a;
       a.rowptr = (const int32_t *)m.d_rowptr;
       fill(a);
-      if (f) launch_spmv_t<int32_t, true>(a, rows, c->stream); else launch_spmv_t<int32_t, false>(a, rows, c->stream);
+      if (use_tma) PA_TRY(launch_spmv_tma<int32_t>(c, a, f, cfg, ctas));
+      else if (f) launch_spmv_t<int32_t, true>(a, rows, c->stream); else launch_spmv_t<int32_t, false>(a, rows, c->stream);
     }
     c->launches++;
   }
@@ -254,8 +469,8 @@ static int upload_csr(pa_ctx *c, MatPart &m, int64_t nrows, int64_t ncols, const
     PA_CUDA(cudaStreamSynchronize(c->stream));
   }
   if (m.nnz) {
-    PA_CUDA(cudaMalloc((void **)&m.d_colval, m.nnz * sizeof(int32_t)));
-    PA_CUDA(cudaMalloc((void **)&m.d_nzval, m.nnz * sizeof(double)));
+    PA_CUDA(cudaMalloc((void **)&m.d_colval, (m.nnz + 16) * sizeof(int32_t)));
+    PA_CUDA(cudaMalloc((void **)&m.d_nzval, (m.nnz + 16) * sizeof(double)));
     PA_CUDA(cudaMemcpyAsync(m.d_colval, cv.data(), m.nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     PA_CUDA(cudaMemcpyAsync(m.d_nzval, nz.data(), m.nnz * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   }
@@ -509,8 +724,8 @@ extern "C" int pa_mat_set_stencil(pa_mat *A, int32_t k, int32_t kind, const int6
   m.nnz = nnz;
   m.ptr64 = nnz >= (1ll << 31);
   m.rows_per_cta = choose_rows(n, nnz);
-  PA_CUDA(cudaMalloc((void **)&m.d_colval, std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
-  PA_CUDA(cudaMalloc((void **)&m.d_nzval, std::max<int64_t>(nnz, 1) * sizeof(double)));
+  PA_CUDA(cudaMalloc((void **)&m.d_colval, (nnz + 16) * sizeof(int32_t)));
+  PA_CUDA(cudaMalloc((void **)&m.d_nzval, (nnz + 16) * sizeof(double)));
   double *d_rhs = nullptr;
   if (rhs) {
     PA_TRY(pa_before_write(c));
