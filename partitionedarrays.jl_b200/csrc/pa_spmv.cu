@@ -134,7 +134,7 @@ static void launch_spmv_t(const SpmvArgs<PtrT> &a, int rows, cudaStream_t st) {
 // The LSU/L1 only sees the x gather and the conflict-free shared-memory reads; the matrix stream never
 // passes through registers.
 struct TmaCfg {
-  int rows, cap, stages;
+  int rows, cap, stages, batch;
   int64_t ntiles;
 };
 
@@ -166,8 +166,24 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
       : "memory");
 }
 
-template <typename PtrT, bool FUSED>
-__global__ void __launch_bounds__(288) k_spmv_tma(const SpmvArgs<PtrT> a, const TmaCfg cfg) {
+__device__ __forceinline__ void keep_live8(const double *x) {
+  asm volatile("" ::"d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]), "d"(x[4]), "d"(x[5]), "d"(x[6]), "d"(x[7]));
+}
+__device__ __forceinline__ void keep_live16(const double *x) {
+  asm volatile("" ::"d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]), "d"(x[4]), "d"(x[5]), "d"(x[6]), "d"(x[7]), "d"(x[8]), "d"(x[9]),
+               "d"(x[10]), "d"(x[11]), "d"(x[12]), "d"(x[13]), "d"(x[14]), "d"(x[15]));
+}
+template <int N>
+__device__ __forceinline__ void keep_live(const double (&x)[N]) {
+  if (N == 8) keep_live8(x);
+  if (N >= 16) keep_live16(x);
+  if (N >= 32) keep_live16(x + 16);
+}
+
+// minBlocksPerSM is stated explicitly: with maxThreads alone ptxas squeezes the kernel into 32 registers
+// (full-occupancy target) by sinking every load next to its use, which serialises the x gathers.
+template <typename PtrT, bool FUSED, int BATCH>
+__global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (FUSED ? 3 : 4)))) k_spmv_tma(const SpmvArgs<PtrT> a, const TmaCfg cfg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int ROWS = cfg.rows, CAP = cfg.cap, S = cfg.stages;
   // layout: val[S][CAP+2] | col[S][CAP+8] | p0[S] (int64) | full[S] | empty[S]
@@ -239,20 +255,30 @@ __global__ void __launch_bounds__(288) k_spmv_tma(const SpmvArgs<PtrT> a, const 
       const int32_t *cs = col_s + (size_t)s * (CAP + 8) + (rs - (p0 & ~(int64_t)3));
       const int len = (int)(re - rs);
       double acc = 0.0;
-      for (int k0 = 0; k0 < len; k0 += 8) {
-        double v[8], xv[8];
-        int32_t c[8];
+      // BATCH independent (col,val) shared-memory reads and x gathers are issued before the dependent,
+      // strictly in-order accumulation; indices past the row end are clamped to the last entry (a
+      // redundant, cached load) instead of predicating the loads.
+      for (int k0 = 0; k0 < len; k0 += BATCH) {
+        double v[BATCH], xv[BATCH];
+        int32_t c[BATCH];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const bool ok = k0 + u < len;
-          c[u] = ok ? cs[k0 + u] : -1;
-          v[u] = ok ? vs[k0 + u] : 0.0;
+        for (int u = 0; u < BATCH; ++u) {
+          const int kk = min(k0 + u, len - 1);
+          c[u] = cs[kk];
+          v[u] = vs[kk];
         }
+        bool ghost = false;
+        if (FUSED) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          xv[u] = 0.0;
-          if (c[u] >= 0) {
-            if (FUSED && c[u] >= a.n_own_cols) {
+          for (int u = 0; u < BATCH; ++u) ghost |= c[u] >= a.n_own_cols;
+        }
+        if (!FUSED || !ghost) {  // straight-line: all BATCH gathers are in flight together
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u) xv[u] = __ldg(a.x + c[u]);
+        } else {  // boundary rows: ghost columns come from the owner's HBM over NVLink
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u) {
+            if (c[u] >= a.n_own_cols) {
               const int64_t g = c[u] - a.n_own_cols;
               xv[u] = __ldcg(a.peers.p[a.gslot[g]] + a.grlid[g]);
             } else {
@@ -260,9 +286,15 @@ __global__ void __launch_bounds__(288) k_spmv_tma(const SpmvArgs<PtrT> a, const 
             }
           }
         }
+        // ptxas otherwise sinks every load next to its use to hit a 32-register target, serialising the
+        // gathers; pinning all BATCH values live here keeps the loads back to back (memory-level parallelism).
+        keep_live(xv);
+        keep_live(v);
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (k0 + u < len) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+        for (int u = 0; u < BATCH; ++u) {  // branch-free, strictly in column order
+          const double t = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+          acc = (k0 + u < len) ? t : acc;
+        }
       }
       mbar_arrive(empty + s);
       const int64_t yi = a.rowmap ? (int64_t)a.rowmap[row] : row;
@@ -312,9 +344,17 @@ static int max_tile_nnz(pa_ctx *c, MatPart &m, int rows, int64_t *out) {
 template <typename PtrT>
 static int launch_spmv_tma(pa_ctx *c, const SpmvArgs<PtrT> &a, bool fused, const TmaCfg &cfg, int ctas_per_sm) {
   const size_t smem = (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (cfg.cap + 8) * 4 + 8 + 16) + 128;
-  auto kern = fused ? k_spmv_tma<PtrT, true> : k_spmv_tma<PtrT, false>;
+  const int batch = cfg.batch;
+  auto kern = fused ? (batch >= 32 ? k_spmv_tma<PtrT, true, 32> : batch >= 16 ? k_spmv_tma<PtrT, true, 16> : k_spmv_tma<PtrT, true, 8>)
+                    : (batch >= 32 ? k_spmv_tma<PtrT, false, 32> : batch >= 16 ? k_spmv_tma<PtrT, false, 16> : k_spmv_tma<PtrT, false, 8>);
   PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int64_t grid = std::min<int64_t>(cfg.ntiles, (int64_t)148 * ctas_per_sm);
+  if (ctas_per_sm <= 0) {  // persistent grid = SMs x resident CTAs (registers, shared memory and threads permitting)
+    PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, cfg.rows + 32, smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  }
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+  int64_t grid = std::min<int64_t>(cfg.ntiles, (int64_t)nsm * ctas_per_sm);
   kern<<<(unsigned)grid, cfg.rows + 32, smem, c->stream>>>(a, cfg);
   return PA_OK;
 }
@@ -331,8 +371,9 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, bo
     if (rows != 256 && rows != 128 && rows != 64 && rows != 32) rows = m.rows_per_cta;
     // TMA pipeline configuration (knobs allow sweeping on the GPU without recompiling)
     TmaCfg cfg;
-    cfg.rows = (int)pa_knob(c, "tma_rows", m.nnz > 12 * m.nrows ? 128 : 256);
+    cfg.rows = (int)pa_knob(c, "tma_rows", m.nnz > 12 * m.nrows ? 64 : 256);  // measured best: 7-pt 256, 27-pt 64 (profiles/)
     cfg.stages = (int)pa_knob(c, "tma_stages", 2);
+    cfg.batch = (int)pa_knob(c, "tma_batch", m.nnz > 8 * m.nrows ? 16 : 8);
     int ctas = (int)pa_knob(c, "tma_ctas", 0);
     bool use_tma = pa_knob(c, "spmv_kernel", 3) == 3 && cfg.rows >= 32 && cfg.rows <= 256 && cfg.rows % 32 == 0 && cfg.stages >= 2;
     if (use_tma) {
@@ -342,8 +383,6 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, bo
       cfg.ntiles = (m.nrows + cfg.rows - 1) / cfg.rows;
       const size_t smem = (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (cfg.cap + 8) * 4 + 8 + 16) + 128;
       if (smem > 200 * 1024) use_tma = false;  // a tile does not fit: irregular rows -> chunked kernel
-      if (!ctas) ctas = std::max<int>(1, std::min<int>(8, (int)((220 * 1024) / (smem + 1024))));
-      ctas = std::min(ctas, 2048 / (cfg.rows + 32));
     }
     auto fill = [&](auto &a) {
       a.nrows = m.nrows;

@@ -71,9 +71,12 @@ def main():
         b.close()
         return
     run("v1 stream kernel", spmv_kernel=1)
-    rows_opts = (256, 128) if kind == 7 else (128, 64, 96)
-    for rows, stages, ctas in itertools.product(rows_opts, (2, 3, 4), (0, 2, 3, 4, 5, 6)):
-        run(f"tma rows={rows} stages={stages} ctas={ctas}", spmv_kernel=3, tma_rows=rows, tma_stages=stages, tma_ctas=ctas)
+    if kind == 7:
+        combos = [(256, 2, 0, 8), (256, 2, 0, 16), (128, 2, 0, 8), (256, 3, 0, 8), (192, 2, 0, 8), (224, 2, 0, 8), (256, 2, 4, 8), (256, 2, 3, 8)]
+    else:
+        combos = [(r, s_, 0, bt) for r in (32, 64, 96, 128) for s_ in (2, 3) for bt in (16, 32)]
+    for rows, stages, ctas, batch in combos:
+        run(f"tma rows={rows} stages={stages} ctas={ctas} batch={batch}", spmv_kernel=3, tma_rows=rows, tma_stages=stages, tma_ctas=ctas, tma_batch=batch)
     b.close()
 
 
