@@ -33,7 +33,8 @@ int64_t pa_knob(pa_ctx *ctx, const char *key, int64_t dflt) {
   std::string env = std::string("PA_") + key;
   for (auto &c : env) c = (char)toupper(c);
   const char *v = getenv(env.c_str());
-  int64_t r = v ? atoll(v) : dflt;
+  if (!v) return dflt;  // defaults may depend on the caller's matrix: never cached
+  int64_t r = atoll(v);
   ctx->knobs[key] = r;
   return r;
 }
