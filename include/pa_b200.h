@@ -165,11 +165,15 @@ int pa_mat_fill_stored(pa_mat *A, double a);
 #define PA_SPMV_EXPLICIT_EXCHANGE 1u  /* consistent!(x) kernel first, then a purely local SpMV       */
 #define PA_SPMV_SKIP_GHOST_REFRESH 2u /* fused path: do not also write x's local ghost slots          */
 #define PA_CG_REFERENCE_OPS 4u        /* op-for-op sequence of ref_cg.jl (copy,dot,axpby,spmv,dot,...) */
+#define PA_SPMV_INLINE_PEER_LOADS 8u  /* one kernel: ghost columns dereference the owner's arena inside the SpMV */
 
 /* mul!(y,A,x) (src/p_sparse_matrix.jl:2090-2103) when alpha=1,beta=0; mul!(y,A,x,alpha,beta)
  * (:2105-2142) otherwise; HPCG mul_no_lat! (HPCG/src/hpcg_utils.jl:6-17) is the same call.
- * Default path: ghost columns are loaded from the owner's HBM inside the SpMV kernel (NVLink peer
- * loads) — no separate exchange; x's ghost slots are refreshed as a side effect like consistent!. */
+ * Default path = the reference's own latency hiding: consistent!(x) (a peer-load gather over NVLink,
+ * no message, no pack/unpack) runs on a side stream while the own-block product A_oo*x_own streams from
+ * HBM; the ghost-block product A_oh*x_ghost is added afterwards in column order.  x's ghost slots are
+ * consistent on return, like after the reference's mul!.  PA_SPMV_INLINE_PEER_LOADS instead dereferences
+ * the owner's arena for ghost columns inside the single SpMV kernel. */
 int pa_spmv(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, uint32_t flags);
 
 typedef struct {

@@ -51,6 +51,8 @@ struct pa_ctx {
   std::vector<int> local_of_part;  // global part -> local k or -1
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t side = nullptr;            // consistent!(x) overlapped with the own-block product
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   uint64_t arena_bytes = 0, hdr_bytes = 0, bump = 0;
   std::vector<char *> arena;      // per local part (device memory, cudaMalloc, IPC exportable)
   std::vector<char *> peer_base;  // per global part: arena base in this process' address space
@@ -117,7 +119,11 @@ struct MatPart {
   double *d_nzval = nullptr;
   bool set = false;
   int rows_per_cta = 256;
-  std::map<int, int64_t> tile_nnz;  // max nnz of a ROWS-row tile, by ROWS (TMA stage sizing)
+  std::map<int, int64_t> tile_nnz;
+  // rows that reference ghost columns (ghost block of the split product)
+  bool ghost_scanned = false, ghost_tail_ok = true, tma_ok = true;
+  int64_t n_grows = 0;
+  int32_t *d_grows = nullptr;  // max nnz of a ROWS-row tile, by ROWS (TMA stage sizing)
 };
 
 struct pa_mat {
@@ -151,5 +157,4 @@ int64_t pa_knob(pa_ctx *ctx, const char *key, int64_t dflt);
 int pa_launch_consistent(pa_vec *v);  // gather kernel only (no signalling)
 int pa_waxpby_dev(pa_vec *w, Coef ca, const pa_vec *x, Coef cb, const pa_vec *y);
 int pa_reduce_dev_to(const pa_vec *x, const pa_vec *y, int mode, double *d_out);  // mode 0 dot, 1 sumsq, 2 sum
-int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, bool fused, int dot_slot,
-                  const pa_vec *dot_with);
+int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, int mode);

@@ -118,6 +118,9 @@ extern "C" int pa_ctx_create(int32_t nparts_global, int32_t nlocal, const int32_
     PA_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
   }
+  PA_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  PA_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  PA_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   c->arena_bytes = align_up(arena_bytes ? arena_bytes : (1ull << 30), 1 << 20);
   c->hdr_bytes = align_up(2ull * nparts_global * sizeof(unsigned long long), 4096);
   PA_CHECK(c->arena_bytes > c->hdr_bytes, PA_EINVAL, "pa_ctx_create: arena too small");
@@ -177,6 +180,9 @@ extern "C" int pa_ctx_destroy(pa_ctx *c) {
   cudaFree(c->d_err);
   cudaFreeHost(c->h_scal);
   cudaFreeHost(c->h_err);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return PA_OK;

@@ -182,8 +182,11 @@ __device__ __forceinline__ void keep_live(const double (&x)[N]) {
 
 // minBlocksPerSM is stated explicitly: with maxThreads alone ptxas squeezes the kernel into 32 registers
 // (full-occupancy target) by sinking every load next to its use, which serialises the x gathers.
-template <typename PtrT, bool FUSED, int BATCH>
-__global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (FUSED ? 3 : 4)))) k_spmv_tma(const SpmvArgs<PtrT> a, const TmaCfg cfg) {
+// MODE 0: every column is a local x entry (1 part, or ghosts already refreshed)
+// MODE 1: ghost columns are loaded from the owner's arena inside this kernel (inline NVLink loads)
+// MODE 2: own block only (A_oo * x_own); the ghost block is added afterwards by k_spmv_ghost_rows
+template <typename PtrT, int MODE, int BATCH>
+__global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MODE == 1 ? 3 : 4)))) k_spmv_tma(const SpmvArgs<PtrT> a, const TmaCfg cfg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int ROWS = cfg.rows, CAP = cfg.cap, S = cfg.stages;
   // layout: val[S][CAP+2] | col[S][CAP+8] | p0[S] (int64) | full[S] | empty[S]
@@ -268,11 +271,15 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (FU
           v[u] = vs[kk];
         }
         bool ghost = false;
-        if (FUSED) {
+        if (MODE == 1) {
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) ghost |= c[u] >= a.n_own_cols;
         }
-        if (!FUSED || !ghost) {  // straight-line: all BATCH gathers are in flight together
+        if (MODE == 2) {  // own block only: ghost columns are skipped here and added, in order, by k_spmv_ghost_rows
+          const int32_t last_own = (int32_t)a.n_own_cols - 1;
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u) xv[u] = __ldg(a.x + min(c[u], last_own));
+        } else if (MODE == 0 || !ghost) {  // straight-line: all BATCH gathers are in flight together
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) xv[u] = __ldg(a.x + c[u]);
         } else {  // boundary rows: ghost columns come from the owner's HBM over NVLink
@@ -293,7 +300,8 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (FU
 #pragma unroll
         for (int u = 0; u < BATCH; ++u) {  // branch-free, strictly in column order
           const double t = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
-          acc = (k0 + u < len) ? t : acc;
+          const bool take = (k0 + u < len) && (MODE != 2 || c[u] < a.n_own_cols);
+          acc = take ? t : acc;
         }
       }
       mbar_arrive(empty + s);
@@ -342,11 +350,12 @@ static int max_tile_nnz(pa_ctx *c, MatPart &m, int rows, int64_t *out) {
 }
 
 template <typename PtrT>
-static int launch_spmv_tma(pa_ctx *c, const SpmvArgs<PtrT> &a, bool fused, const TmaCfg &cfg, int ctas_per_sm) {
+static int launch_spmv_tma(pa_ctx *c, const SpmvArgs<PtrT> &a, int mode, const TmaCfg &cfg, int ctas_per_sm) {
   const size_t smem = (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (cfg.cap + 8) * 4 + 8 + 16) + 128;
   const int batch = cfg.batch;
-  auto kern = fused ? (batch >= 32 ? k_spmv_tma<PtrT, true, 32> : batch >= 16 ? k_spmv_tma<PtrT, true, 16> : k_spmv_tma<PtrT, true, 8>)
-                    : (batch >= 32 ? k_spmv_tma<PtrT, false, 32> : batch >= 16 ? k_spmv_tma<PtrT, false, 16> : k_spmv_tma<PtrT, false, 8>);
+  auto kern = mode == 1 ? (batch >= 32 ? k_spmv_tma<PtrT, 1, 32> : batch >= 16 ? k_spmv_tma<PtrT, 1, 16> : k_spmv_tma<PtrT, 1, 8>)
+            : mode == 2 ? (batch >= 32 ? k_spmv_tma<PtrT, 2, 32> : batch >= 16 ? k_spmv_tma<PtrT, 2, 16> : k_spmv_tma<PtrT, 2, 8>)
+                        : (batch >= 32 ? k_spmv_tma<PtrT, 0, 32> : batch >= 16 ? k_spmv_tma<PtrT, 0, 16> : k_spmv_tma<PtrT, 0, 8>);
   PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (ctas_per_sm <= 0) {  // persistent grid = SMs x resident CTAs (registers, shared memory and threads permitting)
     PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, cfg.rows + 32, smem));
@@ -359,14 +368,96 @@ static int launch_spmv_tma(pa_ctx *c, const SpmvArgs<PtrT> &a, bool fused, const
   return PA_OK;
 }
 
-int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, bool fused, int, const pa_vec *) {
+// ------------------------------------------------------------------ ghost block: c_own += A_oh * x_ghost
+// Rows that reference ghost columns are listed once per matrix (k_ghost_scan).  Ghost columns are the tail of
+// a row (own columns first: sorted CSR with own ids < ghost ids, or the own_own|own_ghost merge), so adding
+// the tail entries one by one to the stored own-block result reproduces the sequential row sum bit for bit —
+// the same split the reference uses (spmv! on own_own, then muladd! on own_ghost, src/p_sparse_matrix.jl:2099-2101).
+template <typename PtrT>
+__global__ void k_ghost_scan(const PtrT *rowptr, const int32_t *colval, int64_t nrows, int64_t n_own_cols, unsigned char *flag, int *unordered) {
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += (int64_t)gridDim.x * blockDim.x) {
+    bool seen_ghost = false, bad = false;
+    for (int64_t p = (int64_t)rowptr[row]; p < (int64_t)rowptr[row + 1]; ++p) {
+      const bool g = colval[p] >= n_own_cols;
+      bad |= seen_ghost && !g;
+      seen_ghost |= g;
+    }
+    flag[row] = seen_ghost ? 1 : 0;
+    if (bad) *unordered = 1;
+  }
+}
+
+__global__ void k_compact_rows(const unsigned char *flag, int64_t nrows, int32_t *out, unsigned long long *count) {
+  // order of the list is irrelevant (one thread per listed row, rows are independent)
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += (int64_t)gridDim.x * blockDim.x)
+    if (flag[row]) out[atomicAdd(count, 1ull)] = (int32_t)row;
+}
+
+template <typename PtrT>
+__global__ void k_spmv_ghost_rows(const SpmvArgs<PtrT> a, const int32_t *grows, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = grows[i];
+    const int64_t yi = a.rowmap ? (int64_t)a.rowmap[row] : row;
+    double acc = a.y[yi];
+    for (int64_t p = (int64_t)a.rowptr[row]; p < (int64_t)a.rowptr[row + 1]; ++p) {
+      const int32_t col = a.colval[p];
+      if (col >= a.n_own_cols) acc = __dadd_rn(acc, __dmul_rn(a.nzval[p], a.x[col]));  // x ghost slot: refreshed by consistent!
+    }
+    a.y[yi] = acc;
+  }
+}
+
+static int ghost_scan(pa_ctx *c, MatPart &m, int64_t n_own_cols) {
+  if (m.ghost_scanned) return PA_OK;
+  m.ghost_scanned = true;
+  m.n_grows = 0;
+  m.ghost_tail_ok = true;
+  if (m.nrows == 0 || m.nnz == 0) return PA_OK;
+  unsigned char *d_flag = nullptr;
+  unsigned long long *d_count = nullptr, h_count = 0;
+  int *d_bad = nullptr, h_bad = 0;
+  PA_CUDA(cudaMalloc((void **)&d_flag, m.nrows));
+  PA_CUDA(cudaMalloc((void **)&d_count, sizeof(h_count)));
+  PA_CUDA(cudaMalloc((void **)&d_bad, sizeof(int)));
+  PA_CUDA(cudaMemsetAsync(d_count, 0, sizeof(h_count), c->stream));
+  PA_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), c->stream));
+  if (m.ptr64)
+    k_ghost_scan<int64_t><<<148 * 8, 256, 0, c->stream>>>((const int64_t *)m.d_rowptr, m.d_colval, m.nrows, n_own_cols, d_flag, d_bad);
+  else
+    k_ghost_scan<int32_t><<<148 * 8, 256, 0, c->stream>>>((const int32_t *)m.d_rowptr, m.d_colval, m.nrows, n_own_cols, d_flag, d_bad);
+  // upper bound of listed rows is unknown before counting: count first with a dry compaction into a scratch of nrows
+  int32_t *d_tmp = nullptr;
+  PA_CUDA(cudaMalloc((void **)&d_tmp, m.nrows * sizeof(int32_t)));
+  k_compact_rows<<<148 * 8, 256, 0, c->stream>>>(d_flag, m.nrows, d_tmp, d_count);
+  PA_CUDA(cudaMemcpyAsync(&h_count, d_count, sizeof(h_count), cudaMemcpyDeviceToHost, c->stream));
+  PA_CUDA(cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  PA_CUDA(cudaStreamSynchronize(c->stream));
+  m.n_grows = (int64_t)h_count;
+  m.ghost_tail_ok = h_bad == 0;
+  if (m.n_grows) {
+    PA_CUDA(cudaMalloc((void **)&m.d_grows, m.n_grows * sizeof(int32_t)));
+    PA_CUDA(cudaMemcpyAsync(m.d_grows, d_tmp, m.n_grows * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+    PA_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  cudaFree(d_tmp);
+  cudaFree(d_flag);
+  cudaFree(d_count);
+  cudaFree(d_bad);
+  c->launches += 2;
+  return PA_OK;
+}
+
+// mode 0: all columns local; 1: inline NVLink loads; 2: own block only; 3: ghost block only (boundary rows)
+int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, int mode) {
   pa_ctx *c = A->ctx;
   for (int k = 0; k < c->nlocal; ++k) {
     MatPart &m = A->parts[k];
     if (m.nrows == 0) continue;
     const PlanPart &cp = A->cols->parts[k];
     const PlanPart &rp = A->rows->parts[k];
-    const bool f = fused && cp.n_ghost > 0;
+    int kmode = mode;
+    if ((mode == 1 || mode == 2) && cp.n_ghost == 0) kmode = 0;
+    if (mode == 3 && m.n_grows == 0) continue;
     int rows = (int)pa_knob(c, "spmv_rows", 0);
     if (rows != 256 && rows != 128 && rows != 64 && rows != 32) rows = m.rows_per_cta;
     // TMA pipeline configuration (knobs allow sweeping on the GPU without recompiling)
@@ -375,7 +466,7 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, bo
     cfg.stages = (int)pa_knob(c, "tma_stages", 2);
     cfg.batch = (int)pa_knob(c, "tma_batch", m.nnz > 8 * m.nrows ? 16 : 8);
     int ctas = (int)pa_knob(c, "tma_ctas", 0);
-    bool use_tma = pa_knob(c, "spmv_kernel", 3) == 3 && cfg.rows >= 32 && cfg.rows <= 256 && cfg.rows % 32 == 0 && cfg.stages >= 2;
+    bool use_tma = mode != 3 && m.tma_ok && pa_knob(c, "spmv_kernel", 3) == 3 && cfg.rows >= 32 && cfg.rows <= 256 && cfg.rows % 32 == 0 && cfg.stages >= 2;
     if (use_tma) {
       int64_t mt = 0;
       PA_TRY(max_tile_nnz(c, m, cfg.rows, &mt));
@@ -384,6 +475,7 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, bo
       const size_t smem = (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (cfg.cap + 8) * 4 + 8 + 16) + 128;
       if (smem > 200 * 1024) use_tma = false;  // a tile does not fit: irregular rows -> chunked kernel
     }
+    PA_CHECK(use_tma || kmode != 2, PA_ESTATE, "own-block mode needs the TMA kernel");
     auto fill = [&](auto &a) {
       a.nrows = m.nrows;
       a.colval = m.d_colval;
@@ -398,18 +490,30 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, bo
       a.grlid = cp.d_grlid_by_gid;
       a.peers = pa_peer_ptrs(x, k);
     };
+    auto go = [&](auto &a, auto tag) -> int {
+      using PtrT = decltype(tag);
+      if (mode == 3) {
+        const int64_t g = std::min<int64_t>((m.n_grows + 255) / 256, 148 * 8);
+        k_spmv_ghost_rows<PtrT><<<(unsigned)g, 256, 0, c->stream>>>(a, m.d_grows, m.n_grows);
+      } else if (use_tma) {
+        PA_TRY(launch_spmv_tma<PtrT>(c, a, kmode, cfg, ctas));
+      } else if (kmode == 1) {
+        launch_spmv_t<PtrT, true>(a, rows, c->stream);
+      } else {
+        launch_spmv_t<PtrT, false>(a, rows, c->stream);
+      }
+      return PA_OK;
+    };
     if (m.ptr64) {
       SpmvArgs<int64_t> a;
       a.rowptr = (const int64_t *)m.d_rowptr;
       fill(a);
-      if (use_tma) PA_TRY(launch_spmv_tma<int64_t>(c, a, f, cfg, ctas));
-      else if (f) launch_spmv_t<int64_t, true>(a, rows, c->stream); else launch_spmv_t<int64_t, false>(a, rows, c->stream);
+      PA_TRY(go(a, (int64_t)0));
     } else {
       SpmvArgs<int32_t> a;
       a.rowptr = (const int32_t *)m.d_rowptr;
       fill(a);
-      if (use_tma) PA_TRY(launch_spmv_tma<int32_t>(c, a, f, cfg, ctas));
-      else if (f) launch_spmv_t<int32_t, true>(a, rows, c->stream); else launch_spmv_t<int32_t, false>(a, rows, c->stream);
+      PA_TRY(go(a, (int32_t)0));
     }
     c->launches++;
   }
@@ -439,17 +543,46 @@ extern "C" int pa_spmv(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double bet
   pa_ctx *c = A->ctx;
   PA_CUDA(cudaSetDevice(c->device));
   PA_TRY(pa_before_write(c));
-  bool fused = !(flags & PA_SPMV_EXPLICIT_EXCHANGE) && pa_knob(c, "no_fuse", 0) == 0;
-  for (int k = 0; k < c->nlocal; ++k) fused = fused && x->plan->parts[k].prefix;
+  // Strategy (all of them read ghost values straight from the owner's HBM over NVLink; none packs or sends):
+  //  overlap (default): consistent!(x) runs on the side stream (peer-load gather into x's ghost slots) WHILE the
+  //      own-block kernel streams A_oo*x_own; then the ghost-block kernel adds A_oh*x_ghost — the latency hiding of
+  //      the reference's mul! (t=consistent!(b); spmv! own_own; wait(t); muladd! own_ghost), bit-identical row sums.
+  //  inline (PA_SPMV_INLINE_PEER_LOADS): one kernel, ghost columns dereference the peer arena inside the SpMV.
+  //  explicit (PA_SPMV_EXPLICIT_EXCHANGE): consistent!(x) first, then one purely local SpMV (HPCG mul_no_lat!).
+  bool any_ghost = false, prefix = true, tail_ok = true, tma_ok = true;
+  for (int k = 0; k < c->nlocal; ++k) {
+    any_ghost |= x->plan->parts[k].n_ghost > 0;
+    prefix &= x->plan->parts[k].prefix;
+    tail_ok &= A->parts[k].ghost_tail_ok;
+    tma_ok &= A->parts[k].tma_ok;
+  }
+  int strategy = (flags & PA_SPMV_EXPLICIT_EXCHANGE) ? 0 : ((flags & PA_SPMV_INLINE_PEER_LOADS) ? 1 : 2);
+  const int64_t forced = pa_knob(c, "spmv_strategy", -1);
+  if (forced >= 0 && forced <= 2) strategy = (int)forced;
+  if (!prefix) strategy = 0;                                         // permuted layouts: plain local kernel after consistent!
+  if (strategy == 2 && (!tail_ok || !tma_ok || alpha != 1.0 || beta != 0.0 || pa_knob(c, "spmv_kernel", 3) != 3)) strategy = 0;
+  if (!any_ghost) strategy = 0;
   // the exchange plan of x is the one that knows where the ghosts live (it equals the column plan)
   pa_plan *xp = x->plan;
   PA_TRY(pa_collective_begin(xp));
-  if (!fused) {
+  if (strategy == 0) {
     PA_TRY(pa_launch_consistent(x));
-    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, false, -1, nullptr));
-  } else {
-    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, true, -1, nullptr));
+    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 0));
+  } else if (strategy == 1) {
+    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 1));
     if (!(flags & PA_SPMV_SKIP_GHOST_REFRESH)) PA_TRY(pa_launch_consistent(x));
+  } else {
+    PA_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    PA_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    cudaStream_t main_stream = c->stream;
+    c->stream = c->side;  // consistent!(x) on the side stream: NVLink gather overlapped with the own-block product
+    int rc = pa_launch_consistent(x);
+    c->stream = main_stream;
+    PA_TRY(rc);
+    PA_CUDA(cudaEventRecord(c->ev_join, c->side));
+    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 2));
+    PA_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 3));
   }
   return pa_collective_end(xp);
 }
@@ -468,6 +601,7 @@ extern "C" int pa_mat_create(pa_plan *rows, pa_plan *cols, pa_mat **out) {
 }
 
 static void free_part(MatPart &m) {
+  cudaFree(m.d_grows);
   cudaFree(m.d_rowptr);
   cudaFree(m.d_colval);
   cudaFree(m.d_nzval);
@@ -588,6 +722,13 @@ extern "C" int pa_mat_set_csr_split(pa_mat *A, int32_t k, int64_t nrows, int32_t
 extern "C" int pa_mat_commit(pa_mat *A) {
   PA_CHECK(A && !A->committed, PA_ESTATE, "pa_mat_commit: matrix missing or already committed");
   for (int k = 0; k < A->ctx->nlocal; ++k) PA_CHECK(A->parts[k].set, PA_ESTATE, "pa_mat_commit: local part %d not set", k);
+  PA_CUDA(cudaSetDevice(A->ctx->device));
+  for (int k = 0; k < A->ctx->nlocal; ++k) {
+    const PlanPart &cp = A->cols->parts[k];
+    MatPart &m = A->parts[k];
+    m.tma_ok = true;
+    if (cp.prefix && cp.n_ghost > 0) PA_TRY(ghost_scan(A->ctx, m, cp.n_own));
+  }
   A->committed = true;
   return PA_OK;
 }
