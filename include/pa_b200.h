@@ -166,14 +166,19 @@ int pa_mat_fill_stored(pa_mat *A, double a);
 #define PA_SPMV_SKIP_GHOST_REFRESH 2u /* fused path: do not also write x's local ghost slots          */
 #define PA_CG_REFERENCE_OPS 4u        /* op-for-op sequence of ref_cg.jl (copy,dot,axpby,spmv,dot,...) */
 #define PA_SPMV_INLINE_PEER_LOADS 8u  /* one kernel: ghost columns dereference the owner's arena inside the SpMV */
+#define PA_SPMV_OVERLAP 16u           /* consistent!(x) on a side stream || own-block product, then ghost-block product */
 
 /* mul!(y,A,x) (src/p_sparse_matrix.jl:2090-2103) when alpha=1,beta=0; mul!(y,A,x,alpha,beta)
  * (:2105-2142) otherwise; HPCG mul_no_lat! (HPCG/src/hpcg_utils.jl:6-17) is the same call.
- * Default path = the reference's own latency hiding: consistent!(x) (a peer-load gather over NVLink,
- * no message, no pack/unpack) runs on a side stream while the own-block product A_oo*x_own streams from
- * HBM; the ghost-block product A_oh*x_ghost is added afterwards in column order.  x's ghost slots are
- * consistent on return, like after the reference's mul!.  PA_SPMV_INLINE_PEER_LOADS instead dereferences
- * the owner's arena for ghost columns inside the single SpMV kernel. */
+ * Ghost values are always read straight from the owner's HBM over NVLink by a kernel of this call — no
+ * message, no pack/unpack, no MPI/NCCL.  Three schedules (results are bit-identical):
+ *   default                    consistent!(x) as a peer-load gather kernel, then ONE local SpMV over own|ghost
+ *                              columns (the HPCG mul_no_lat! schedule; fastest measured on B200)
+ *   PA_SPMV_OVERLAP            the reference mul! latency hiding: the gather runs on a side stream while the
+ *                              own-block product A_oo*x_own streams from HBM; then A_oh*x_ghost is added in order
+ *   PA_SPMV_INLINE_PEER_LOADS  one kernel: ghost columns dereference the owner's arena inside the SpMV
+ * x's ghost slots are consistent on return, like after the reference's mul! (except with
+ * PA_SPMV_INLINE_PEER_LOADS|PA_SPMV_SKIP_GHOST_REFRESH). */
 int pa_spmv(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, uint32_t flags);
 
 typedef struct {

@@ -18,6 +18,7 @@ PA_SPMV_EXPLICIT_EXCHANGE = 1
 PA_SPMV_SKIP_GHOST_REFRESH = 2
 PA_CG_REFERENCE_OPS = 4
 PA_SPMV_INLINE_PEER_LOADS = 8
+PA_SPMV_OVERLAP = 16
 
 
 class PAError(RuntimeError):

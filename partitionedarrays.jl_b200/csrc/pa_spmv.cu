@@ -556,7 +556,8 @@ extern "C" int pa_spmv(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double bet
     tail_ok &= A->parts[k].ghost_tail_ok;
     tma_ok &= A->parts[k].tma_ok;
   }
-  int strategy = (flags & PA_SPMV_EXPLICIT_EXCHANGE) ? 0 : ((flags & PA_SPMV_INLINE_PEER_LOADS) ? 1 : 2);
+  // default = the fastest measured on B200 (profiles/r01_multigpu_strategies.md): peer-load gather, then one local SpMV
+  int strategy = (flags & PA_SPMV_INLINE_PEER_LOADS) ? 1 : ((flags & PA_SPMV_OVERLAP) ? 2 : 0);
   const int64_t forced = pa_knob(c, "spmv_strategy", -1);
   if (forced >= 0 && forced <= 2) strategy = (int)forced;
   if (!prefix) strategy = 0;                                         // permuted layouts: plain local kernel after consistent!

@@ -102,7 +102,7 @@ def main():
         o.mul_no_lat(Ao, xo, plan, co)
         x = pa.fill_hash(pa.PVector(A.cols), 9)
         y = pa.pzeros(A.rows)
-        for flags in (pa.PA_SPMV_DEFAULT, pa.PA_SPMV_EXPLICIT_EXCHANGE, pa.PA_SPMV_INLINE_PEER_LOADS, pa.PA_SPMV_INLINE_PEER_LOADS | pa.PA_SPMV_SKIP_GHOST_REFRESH):
+        for flags in (pa.PA_SPMV_DEFAULT, pa.PA_SPMV_OVERLAP, pa.PA_SPMV_INLINE_PEER_LOADS, pa.PA_SPMV_INLINE_PEER_LOADS | pa.PA_SPMV_SKIP_GHOST_REFRESH):
             y.fill_(-7.0)
             x2 = pa.fill_hash(pa.PVector(A.cols), 9)
             pa.mul_(y, A, x2, flags=flags)

@@ -187,7 +187,7 @@ def test_stencil_generator_and_mul_bit_exact(pa, kind, nloc, npd):
     o.mul_no_lat(Ao, xo, plan, co)
     want = o.collect(co, Ao.row_partition)
     y = pa.pzeros(A.rows)
-    for flags in (pa.PA_SPMV_DEFAULT, pa.PA_SPMV_EXPLICIT_EXCHANGE, pa.PA_SPMV_INLINE_PEER_LOADS, pa.PA_SPMV_INLINE_PEER_LOADS | pa.PA_SPMV_SKIP_GHOST_REFRESH):
+    for flags in (pa.PA_SPMV_DEFAULT, pa.PA_SPMV_OVERLAP, pa.PA_SPMV_INLINE_PEER_LOADS, pa.PA_SPMV_INLINE_PEER_LOADS | pa.PA_SPMV_SKIP_GHOST_REFRESH):
         y.fill_(-1.0)
         pa.mul_(y, A, x, flags=flags)
         assert np.array_equal(y.collect(), want), f"flags={flags}"
