@@ -157,8 +157,7 @@ extern "C" int pa_cg(pa_mat *A, pa_vec *x, const pa_vec *b, int32_t maxiter, dou
         rho = d_hist + it;  // dot(c,r) with c == r
         rho_prev = it ? d_hist + it - 1 : d_one;
         PA_TRY(pa_waxpby_dev(u, coef_imm(1.0), r, coef_ratio(rho, rho_prev, 1.0), u));
-        PA_TRY(pa_spmv(A, u, cv, 1.0, 0.0, PA_SPMV_SKIP_GHOST_REFRESH));
-        PA_TRY(pa_reduce_dev_to(u, cv, 0, d_uc));
+        PA_TRY(pa_spmv_dot(A, u, cv, 1.0, 0.0, PA_SPMV_SKIP_GHOST_REFRESH, u, d_uc));  // c = A*u and u.c in one pass
         PA_TRY(cg_update(x, u, r, cv, rho, d_uc, d_hist + it + 1));
       }
       iters = it + 1;

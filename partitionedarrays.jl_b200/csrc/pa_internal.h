@@ -13,6 +13,7 @@
 #define PA_NSCAL 16     // device scalar slots per context
 #define PA_RED_BLOCKS 1184  // 148 SMs x 8 resident CTAs: grid of every BLAS-1 reduction
 #define PA_RED_THREADS 256
+#define PA_DOT_PARTS 4096  // >= persistent SpMV grid (SMs x resident CTAs)
 
 void pa_set_error(const char *fmt, ...);
 int pa_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
@@ -123,7 +124,8 @@ struct MatPart {
   // rows that reference ghost columns (ghost block of the split product)
   bool ghost_scanned = false, ghost_tail_ok = true, tma_ok = true;
   int64_t n_grows = 0;
-  int32_t *d_grows = nullptr;  // max nnz of a ROWS-row tile, by ROWS (TMA stage sizing)
+  int32_t *d_grows = nullptr;
+  double *d_dotpart = nullptr;  // per-CTA partials of the fused dot epilogue  // max nnz of a ROWS-row tile, by ROWS (TMA stage sizing)
 };
 
 struct pa_mat {
@@ -157,4 +159,5 @@ int64_t pa_knob(pa_ctx *ctx, const char *key, int64_t dflt);
 int pa_launch_consistent(pa_vec *v);  // gather kernel only (no signalling)
 int pa_waxpby_dev(pa_vec *w, Coef ca, const pa_vec *x, Coef cb, const pa_vec *y);
 int pa_reduce_dev_to(const pa_vec *x, const pa_vec *y, int mode, double *d_out);  // mode 0 dot, 1 sumsq, 2 sum
-int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, int mode);
+int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, int mode, const pa_vec *dotw, double *d_out);
+int pa_spmv_dot(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, uint32_t flags, const pa_vec *dotw, double *d_out);

@@ -32,6 +32,9 @@ struct SpmvArgs {
   int64_t n_own_cols;     // fused: columns >= n_own_cols are ghosts
   const int32_t *gslot, *grlid;
   PeerPtrs peers;
+  // fused dot epilogue (CG: u.c with c = A*u): sum_i y_i * dotw_i, one partial per CTA
+  const double *dotw;
+  double *dot_part;
 };
 
 // The matrix stream is read exactly once: keep it out of L1 and mark it evict-first in L2 so the
@@ -230,6 +233,7 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
     return;
   }
   // ---------------- consumers: one thread per row
+  double dsum = 0.0;
   int64_t rs_n = 0, re_n = 0;
   if (nloc > 0) {
     const int64_t row = first * ROWS + tid;
@@ -308,12 +312,25 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
       const int64_t yi = a.rowmap ? (int64_t)a.rowmap[row] : row;
       if (a.alpha == 1.0 && a.beta == 0.0) {
         a.y[yi] = acc;
+        if (a.dotw) dsum = fma(acc, __ldg(a.dotw + yi), dsum);
       } else {
         const double by = a.beta == 0.0 ? 0.0 : __dmul_rn(a.beta, a.y[yi]);
         a.y[yi] = __dadd_rn(__dmul_rn(a.alpha, acc), by);
       }
     } else {
       mbar_arrive(empty + s);
+    }
+  }
+  if (a.dotw) {  // consumers only (the producer warp has left): fixed-order block reduction, one partial per CTA
+    __shared__ double red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    if ((tid & 31) == 0) red[tid >> 5] = dsum;
+    asm volatile("bar.sync 1, %0;" ::"r"(ROWS) : "memory");
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (ROWS >> 5); ++w) t += red[w];
+      a.dot_part[blockIdx.x] = t;
     }
   }
 }
@@ -350,7 +367,7 @@ static int max_tile_nnz(pa_ctx *c, MatPart &m, int rows, int64_t *out) {
 }
 
 template <typename PtrT>
-static int launch_spmv_tma(pa_ctx *c, const SpmvArgs<PtrT> &a, int mode, const TmaCfg &cfg, int ctas_per_sm) {
+static int launch_spmv_tma(pa_ctx *c, const SpmvArgs<PtrT> &a, int mode, const TmaCfg &cfg, int ctas_per_sm, int64_t *grid_out) {
   const size_t smem = (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (cfg.cap + 8) * 4 + 8 + 16) + 128;
   const int batch = cfg.batch;
   auto kern = mode == 1 ? (batch >= 32 ? k_spmv_tma<PtrT, 1, 32> : batch >= 16 ? k_spmv_tma<PtrT, 1, 16> : k_spmv_tma<PtrT, 1, 8>)
@@ -364,7 +381,9 @@ static int launch_spmv_tma(pa_ctx *c, const SpmvArgs<PtrT> &a, int mode, const T
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
   int64_t grid = std::min<int64_t>(cfg.ntiles, (int64_t)nsm * ctas_per_sm);
+  PA_CHECK(!a.dotw || grid <= PA_DOT_PARTS, PA_ESTATE, "dot epilogue: grid larger than the partial buffer");
   kern<<<(unsigned)grid, cfg.rows + 32, smem, c->stream>>>(a, cfg);
+  *grid_out = grid;
   return PA_OK;
 }
 
@@ -448,7 +467,24 @@ static int ghost_scan(pa_ctx *c, MatPart &m, int64_t n_own_cols) {
 }
 
 // mode 0: all columns local; 1: inline NVLink loads; 2: own block only; 3: ghost block only (boundary rows)
-int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, int mode) {
+// sum of the per-CTA partials of the fused dot epilogue, fixed order
+__global__ void k_sum_parts(const double *part, int n, double *out) {
+  __shared__ double sm[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sm[w];
+    *out = t;
+  }
+}
+
+// dotw/d_out (nullable): fused epilogue *d_out = sum_parts dot(y_own, dotw_own), only with mode 0/1 on the TMA kernel
+int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, int mode, const pa_vec *dotw, double *d_out) {
   pa_ctx *c = A->ctx;
   for (int k = 0; k < c->nlocal; ++k) {
     MatPart &m = A->parts[k];
@@ -489,14 +525,21 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, in
       a.gslot = cp.d_gslot_by_gid;
       a.grlid = cp.d_grlid_by_gid;
       a.peers = pa_peer_ptrs(x, k);
+      a.dotw = dotw ? dotw->d[k] : nullptr;
+      a.dot_part = m.d_dotpart;
     };
+    if (dotw) {
+      PA_CHECK(use_tma && mode != 2 && mode != 3 && rp.prefix && alpha == 1.0 && beta == 0.0, PA_ESTATE, "dot epilogue unavailable for this configuration");
+      if (!m.d_dotpart) PA_CUDA(cudaMalloc((void **)&m.d_dotpart, PA_DOT_PARTS * sizeof(double)));
+    }
+    int64_t grid_used = 0;
     auto go = [&](auto &a, auto tag) -> int {
       using PtrT = decltype(tag);
       if (mode == 3) {
         const int64_t g = std::min<int64_t>((m.n_grows + 255) / 256, 148 * 8);
         k_spmv_ghost_rows<PtrT><<<(unsigned)g, 256, 0, c->stream>>>(a, m.d_grows, m.n_grows);
       } else if (use_tma) {
-        PA_TRY(launch_spmv_tma<PtrT>(c, a, kmode, cfg, ctas));
+        PA_TRY(launch_spmv_tma<PtrT>(c, a, kmode, cfg, ctas, &grid_used));
       } else if (kmode == 1) {
         launch_spmv_t<PtrT, true>(a, rows, c->stream);
       } else {
@@ -516,9 +559,31 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, in
       PA_TRY(go(a, (int32_t)0));
     }
     c->launches++;
+    if (dotw) {
+      k_sum_parts<<<1, 256, 0, c->stream>>>(m.d_dotpart, (int)grid_used, c->nlocal == 1 ? d_out : c->d_partial + k);
+      c->launches++;
+    }
   }
   PA_CUDA(cudaGetLastError());
+  if (dotw) PA_TRY(pa_reduce_finish(c, d_out));
   return PA_OK;
+}
+
+// can pa_spmv_dot fuse the dot into the SpMV for this matrix? (regular rows, own-first layout)
+static bool dot_fusable(pa_mat *A, pa_vec *x) {
+  pa_ctx *c = A->ctx;
+  if (pa_knob(c, "spmv_kernel", 3) != 3 || pa_knob(c, "no_dot_fusion", 0)) return false;
+  for (int k = 0; k < c->nlocal; ++k) {
+    MatPart &m = A->parts[k];
+    if (!x->plan->parts[k].prefix || !A->rows->parts[k].prefix) return false;
+    if (m.nrows == 0) return false;
+    int rows = (int)pa_knob(c, "tma_rows", m.nnz > 12 * m.nrows ? 64 : 256);
+    int64_t mt = 0;
+    if (max_tile_nnz(c, m, rows, &mt) != PA_OK) return false;
+    const int64_t cap = (std::max<int64_t>(mt, 64) + 63) / 64 * 64;
+    if ((size_t)pa_knob(c, "tma_stages", 2) * ((cap + 2) * 8 + (cap + 8) * 4 + 24) + 128 > 200 * 1024) return false;
+  }
+  return true;
 }
 
 static int check_mul_args(pa_mat *A, pa_vec *x, pa_vec *y) {
@@ -538,7 +603,10 @@ static int check_mul_args(pa_mat *A, pa_vec *x, pa_vec *y) {
   return PA_OK;
 }
 
-extern "C" int pa_spmv(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, uint32_t flags) {
+int pa_reduce_dev_to(const pa_vec *x, const pa_vec *y, int mode, double *d_out);
+
+// mul! with an optional fused epilogue *d_out = dot(dotw, y) (device resident; CG's u.c)
+int pa_spmv_dot(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, uint32_t flags, const pa_vec *dotw, double *d_out) {
   PA_TRY(check_mul_args(A, x, y));
   pa_ctx *c = A->ctx;
   PA_CUDA(cudaSetDevice(c->device));
@@ -563,14 +631,16 @@ extern "C" int pa_spmv(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double bet
   if (!prefix) strategy = 0;                                         // permuted layouts: plain local kernel after consistent!
   if (strategy == 2 && (!tail_ok || !tma_ok || alpha != 1.0 || beta != 0.0 || pa_knob(c, "spmv_kernel", 3) != 3)) strategy = 0;
   if (!any_ghost) strategy = 0;
+  const pa_vec *want_dot = dotw;
+  if (dotw && (strategy == 2 || alpha != 1.0 || beta != 0.0 || !dot_fusable(A, x))) dotw = nullptr;
   // the exchange plan of x is the one that knows where the ghosts live (it equals the column plan)
   pa_plan *xp = x->plan;
   PA_TRY(pa_collective_begin(xp));
   if (strategy == 0) {
     PA_TRY(pa_launch_consistent(x));
-    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 0));
+    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 0, dotw, d_out));
   } else if (strategy == 1) {
-    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 1));
+    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 1, dotw, d_out));
     if (!(flags & PA_SPMV_SKIP_GHOST_REFRESH)) PA_TRY(pa_launch_consistent(x));
   } else {
     PA_CUDA(cudaEventRecord(c->ev_fork, c->stream));
@@ -581,11 +651,17 @@ extern "C" int pa_spmv(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double bet
     c->stream = main_stream;
     PA_TRY(rc);
     PA_CUDA(cudaEventRecord(c->ev_join, c->side));
-    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 2));
+    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 2, nullptr, nullptr));
     PA_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 3));
+    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 3, nullptr, nullptr));
   }
-  return pa_collective_end(xp);
+  PA_TRY(pa_collective_end(xp));
+  if (want_dot && !dotw) PA_TRY(pa_reduce_dev_to(want_dot, y, 0, d_out));  // unfused fallback: separate dot pass
+  return PA_OK;
+}
+
+extern "C" int pa_spmv(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, uint32_t flags) {
+  return pa_spmv_dot(A, x, y, alpha, beta, flags, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------ matrix objects
@@ -602,6 +678,7 @@ extern "C" int pa_mat_create(pa_plan *rows, pa_plan *cols, pa_mat **out) {
 }
 
 static void free_part(MatPart &m) {
+  cudaFree(m.d_dotpart);
   cudaFree(m.d_grows);
   cudaFree(m.d_rowptr);
   cudaFree(m.d_colval);

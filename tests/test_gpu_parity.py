@@ -340,3 +340,52 @@ def test_full_size_properties_512(pa):
             v.free()
         A.free()
     b.close()
+
+
+@pytest.mark.parametrize("split", [True, False])
+def test_irregular_rows_and_fallback_kernel(pa, split):
+    """Irregular row lengths (empty rows, FEM-like 4/6/9, a few near-dense rows that do not fit a TMA stage and take
+    the chunked fallback kernel), 4 parts, random ghosts: mul! bit-exact vs the oracle in every schedule."""
+    rng = np.random.default_rng(42)
+    n, P = 6000, 4
+    orows = o.uniform_partition(P, n)
+    tab = o.global_to_owner_table(orows)
+    lens = rng.choice([0, 1, 4, 6, 9, 9, 27, 40], size=n)
+    lens[rng.choice(n, 6, replace=False)] = 5500  # rows longer than any TMA stage
+    I = np.repeat(np.arange(1, n + 1), lens)
+    J = rng.integers(1, n + 1, size=len(I))
+    V = rng.standard_normal(len(I))
+    Is, Js, Vs = [], [], []
+    for p in range(P):
+        m = tab[I] == p + 1
+        Is.append(I[m]); Js.append(J[m]); Vs.append(V[m])
+    Ao = o.psparse(Is, Js, Vs, orows, orows, assembled=True)
+    b = seq(pa, P)
+    rows = pa.uniform_partition(b, P, n)
+    A = pa.psparse(Is, Js, Vs, rows, rows, split_format=split)
+    for k in range(P):
+        assert A.cols.indices[k].ghost_to_global.tolist() == Ao.col_partition[k].ghost_to_global.tolist()
+        rp, cv, nz = A.download_csr(k)
+        assert np.array_equal(rp, Ao.local[k].rowptr.astype(np.int64) - 1) and np.array_equal(cv, Ao.local[k].colval - 1)
+        assert np.array_equal(nz, Ao.local[k].nzval)
+    xg = rng.standard_normal(n)
+    plan = o.assembly_plan(Ao.col_partition)
+    xo = o.pvector_from_global(xg, Ao.col_partition, ghosts=False)
+    co = [np.zeros(ind.n_local) for ind in Ao.row_partition]
+    o.pmul(Ao, xo, plan, co)
+    want = o.collect(co, Ao.row_partition)
+    y = pa.pzeros(A.rows)
+    for flags in (pa.PA_SPMV_DEFAULT, pa.PA_SPMV_OVERLAP, pa.PA_SPMV_INLINE_PEER_LOADS):
+        for kernel in (3, 1):
+            b.set_knob("spmv_kernel", kernel)
+            x = pa.pvector_from_global(xg, A.cols)
+            y.fill_(3.0)
+            pa.mul_(y, A, x, flags=flags)
+            assert np.array_equal(y.collect(), want), (flags, kernel)
+            x.free()
+    # alpha/beta form: y = alpha*A*x + beta*y (tolerance: third-party 5-arg mul! order is unpinned)
+    x = pa.pvector_from_global(xg, A.cols)
+    y.fill_(1.0)
+    pa.mul_(y, A, x, 0.5, 2.0)
+    np.testing.assert_allclose(y.collect(), 0.5 * want + 2.0, rtol=1e-13, atol=1e-13 * np.abs(want).max())
+    b.close()
