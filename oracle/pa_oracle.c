@@ -312,3 +312,26 @@ double pa_oracle_time_spmv(int nparts, pa_oracle_part *parts, int reps) {
   }
   return t;
 }
+
+/* ---------------- Gauss-Seidel sweeps of the HPCG multigrid smoother ---------------------------
+ * PartitionedSolvers gauss_seidel_sweep! / gauss_seidel_sweep_zero! for SparseMatrixCSR
+ * (PartitionedSolvers/src/smoothers.jl:162-176, 248-269): per part, rows in own order (forward 1:n,
+ * backward n:-1:1), unsplit CSR n_own x n_local, ghost entries of x fixed during the sweep.
+ *   full:  s = b[row]; for p in row: s -= a*x[col]; s += d*x[row]; s = s/d; x[row] = s
+ *   zero:  s = b[row]; for p in row with col < row: s -= a*x[col];       s = s/d; x[row] = s   */
+void pa_oracle_gs_sweep(int64_t n, const int64_t *rowptr, const int32_t *colval, const double *nzval,
+                        const double *diag, const double *b, double *x, int backward, int zero_guess) {
+  for (int64_t k = 0; k < n; ++k) {
+    const int64_t row = backward ? n - 1 - k : k;
+    double s = b[row];
+    for (int64_t p = rowptr[row]; p < rowptr[row + 1]; ++p) {
+      const int32_t col = colval[p];
+      if (zero_guess && col >= row) continue;
+      s -= nzval[p] * x[col];
+    }
+    const double d = diag[row];
+    if (!zero_guess) s += d * x[row];
+    s = s / d;
+    x[row] = s;
+  }
+}
