@@ -193,6 +193,29 @@ typedef struct {
 int pa_cg(pa_mat *A, pa_vec *x, const pa_vec *b, int32_t maxiter, double tol, uint32_t flags,
           pa_cg_result *result, double *history);
 
+/* ------------------------------------------------------------------ HPCG multigrid preconditioner ----
+ * (the caller on either side of the SpMV in HPCG/src/ref_cg.jl:48.)
+ * pa_gs  = gauss_seidel(p; iterations=1, sweep=:symmetric) state (PartitionedSolvers/src/smoothers.jl:82-125).
+ *          The sweeps reproduce the reference's sequential per-part sweeps bit for bit (wavefront schedule).
+ * pa_mg  = Mg_preconditioner (HPCG/src/mg_preconditioner.jl:44-63): levels[0] coarsest ... levels[n-1] finest. */
+typedef struct pa_gs pa_gs;
+typedef struct pa_mg pa_mg;
+int pa_gs_create(pa_mat *A, pa_gs **out);
+/* geometry hint (stencil on a local box, x fastest): closed-form wavefront levels; kind 7 or 27 */
+int pa_gs_set_box(pa_gs *gs, int32_t k, int32_t kind, const int64_t *dims);
+int pa_gs_commit(pa_gs *gs);
+int pa_gs_destroy(pa_gs *gs);
+/* smooth!(x, state, b; zero_guess) — one symmetric Gauss-Seidel iteration (smoothers.jl:98-125) */
+int pa_gs_smooth(pa_gs *gs, pa_vec *x, const pa_vec *b, int32_t zero_guess);
+/* dims: nlevels x nlocal x 3 local box dims; restrict!/prolongate! are the f2c injections (:81-101,:224-251) */
+int pa_mg_create(int32_t nlevels, pa_mat **A, pa_gs **gs, const int64_t *dims, pa_mg **out);
+int pa_mg_destroy(pa_mg *mg);
+/* ldiv!(x, P, b) = fill!(x,0); pc_solve!(x,P,b,l; zero_guess=true) (:202-206, :314-328) */
+int pa_mg_apply(pa_mg *mg, pa_vec *x, const pa_vec *b);
+/* ref_cg!(x,A,b; Pl = mg) — mg == NULL is pa_cg */
+int pa_cg_precond(pa_mat *A, pa_vec *x, const pa_vec *b, pa_mg *mg, int32_t maxiter, double tol, uint32_t flags,
+                  pa_cg_result *result, double *history);
+
 /* Pinned host memory for the end-to-end path (cudaHostAlloc / cudaFreeHost). */
 int pa_host_alloc(void **ptr, size_t bytes);
 int pa_host_free(void *ptr);

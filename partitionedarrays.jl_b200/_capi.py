@@ -73,6 +73,15 @@ SIGNATURES = {
     "pa_mat_fill_stored": [_P, _D],
     "pa_spmv": [_P, _P, _P, _D, _D, _U32],
     "pa_cg": [_P, _P, _P, _I32, _D, _U32, _P, _P],
+    "pa_gs_create": [_P, _P],
+    "pa_gs_set_box": [_P, _I32, _I32, _P],
+    "pa_gs_commit": [_P],
+    "pa_gs_destroy": [_P],
+    "pa_gs_smooth": [_P, _P, _P, _I32],
+    "pa_mg_create": [_I32, _P, _P, _P, _P],
+    "pa_mg_destroy": [_P],
+    "pa_mg_apply": [_P, _P, _P],
+    "pa_cg_precond": [_P, _P, _P, _P, _I32, _D, _U32, _P, _P],
     "pa_host_alloc": [_P, C.c_size_t],
     "pa_host_free": [_P],
     # not in the public header: tuning knob used by bench/tests

@@ -90,8 +90,12 @@ static int cg_update(pa_vec *x, const pa_vec *u, pa_vec *r, const pa_vec *cvec, 
   return pa_reduce_finish(c, d_out);
 }
 
-extern "C" int pa_cg(pa_mat *A, pa_vec *x, const pa_vec *b, int32_t maxiter, double tol, uint32_t flags, pa_cg_result *result,
-                     double *history) {
+struct pa_mg;
+extern "C" int pa_mg_apply(pa_mg *M, pa_vec *x, const pa_vec *b);
+
+/* ref_cg!(x,A,b; Pl) with Pl = Identity (mg == NULL) or the HPCG multigrid preconditioner */
+extern "C" int pa_cg_precond(pa_mat *A, pa_vec *x, const pa_vec *b, pa_mg *mg, int32_t maxiter, double tol, uint32_t flags,
+                             pa_cg_result *result, double *history) {
   PA_CHECK(A && x && b && result, PA_EINVAL, "pa_cg: null argument");
   PA_CHECK(A->committed, PA_ESTATE, "pa_cg: matrix not committed");
   PA_CHECK(maxiter >= 0, PA_EINVAL, "pa_cg: negative maxiter");
@@ -142,7 +146,15 @@ extern "C" int pa_cg(pa_mat *A, pa_vec *x, const pa_vec *b, int32_t maxiter, dou
         break;
       }
       const double *rho, *rho_prev;
-      if (ref_ops) {
+      if (mg) {
+        PA_TRY(pa_mg_apply(mg, cv, r));                       // ldiv!(c, Pl, r): one V-cycle
+        PA_TRY(pa_reduce_dev_to(cv, r, 0, d_rho + it + 1));   // rho = dot(c,r)
+        rho = d_rho + it + 1;
+        rho_prev = it ? d_rho + it : d_one;
+        PA_TRY(pa_waxpby_dev(u, coef_imm(1.0), cv, coef_ratio(rho, rho_prev, 1.0), u));  // u .= c .+ beta.*u
+        PA_TRY(pa_spmv_dot(A, u, cv, 1.0, 0.0, PA_SPMV_DEFAULT, u, d_uc));              // c = A*u ; uc = dot(u,c)
+        PA_TRY(cg_update(x, u, r, cv, rho, d_uc, d_hist + it + 1));                     // x += alpha u ; r -= alpha c ; ||r||^2
+      } else if (ref_ops) {
         PA_TRY(pa_vec_copy(cv, r));                       // ldiv!(c, Identity, r)
         PA_TRY(pa_reduce_dev_to(cv, r, 0, d_rho + it + 1));  // rho = dot(c,r)
         rho = d_rho + it + 1;
@@ -193,4 +205,9 @@ extern "C" int pa_cg(pa_mat *A, pa_vec *x, const pa_vec *b, int32_t maxiter, dou
   if (history)
     for (int i = 0; i <= maxiter; ++i) history[i] = i <= iters ? hist[i] : 0.0;
   return PA_OK;
+}
+
+extern "C" int pa_cg(pa_mat *A, pa_vec *x, const pa_vec *b, int32_t maxiter, double tol, uint32_t flags, pa_cg_result *result,
+                     double *history) {
+  return pa_cg_precond(A, x, b, nullptr, maxiter, tol, flags, result, history);
 }

@@ -1,0 +1,430 @@
+// HPCG multigrid preconditioner: symmetric Gauss-Seidel smoother + injection restrict/prolong + V-cycle.
+// Reference: PartitionedSolvers/src/smoothers.jl:82-125 (gauss_seidel step), :162-176 (CSR sweep),
+// :248-269 (zero-guess sweep); HPCG/src/mg_preconditioner.jl:81-101 (f2c), :202-206 (ldiv!),
+// :224-251 (restrict!/prolongate!), :314-328 (pc_solve!).
+//
+// The reference sweeps the own rows of each part sequentially (1:n, then n:-1:1).  A sequential sweep is a
+// dependency DAG: row i needs the NEW values of its lower-numbered neighbours.  We execute exactly that DAG
+// with a wavefront (level) schedule — rows of one level have no mutual dependencies — so every row sees
+// precisely the inputs it sees in the sequential sweep and performs the same arithmetic in the same order
+// (s -= a*x[col] in CSR order, s += d*x[row], s /= d; separate multiply/add).  The result is bit-identical to
+// the reference's sweep; no multi-colouring (which would change the iteration) is used.
+// Persistent CTAs take 256-row chunks of the level-sorted row list from an atomic ticket and wait on a
+// per-level completion counter of the previous level (no grid-wide barrier, no kernel launch per level).
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <array>
+
+#include "pa_internal.h"
+
+#define GS_THREADS 512
+#define GS_CHUNK 256
+
+struct GsPart {
+  int64_t n = 0;
+  int nlev = 0;
+  int64_t nchunks = 0;
+  int32_t *d_rows = nullptr, *d_cbeg = nullptr, *d_cend = nullptr, *d_clev = nullptr, *d_lcount = nullptr;
+  int *d_done = nullptr;       // [nlev] rows finished per level (zeroed before every sweep)
+  unsigned *d_ticket = nullptr;
+  bool geom = false;
+  int64_t dims[3] = {0, 0, 0}, w[3] = {0, 0, 0};
+};
+
+struct pa_gs {
+  pa_mat *A = nullptr;
+  std::vector<GsPart> parts;
+  bool committed = false;
+};
+
+struct pa_mg {
+  pa_ctx *ctx = nullptr;
+  int nlev = 0;
+  std::vector<pa_mat *> A;   // [0] coarsest ... [nlev-1] finest (the reference's 1-based levels minus one)
+  std::vector<pa_gs *> gs;
+  std::vector<pa_vec *> r, x, Axf;
+  std::vector<std::vector<std::array<int64_t, 3>>> dims;  // [level][local part] local box dims
+};
+
+template <typename PtrT>
+struct GsArgs {
+  const PtrT *rowptr;
+  const int32_t *colval;
+  const double *nzval;
+  const double *b;
+  double *x;
+  const int32_t *rows, *cbeg, *cend, *clev, *lcount;
+  int *done;
+  unsigned *ticket;
+  int64_t nchunks;
+  int nlev, backward, zero_guess;
+};
+
+template <typename PtrT>
+__global__ void __launch_bounds__(GS_THREADS) k_gs_sweep(const GsArgs<PtrT> a) {
+  __shared__ long long s_chunk;
+  __shared__ double prod[GS_THREADS / 32][32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (;;) {
+    if (tid == 0) s_chunk = (long long)atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const long long c = s_chunk;
+    if (c >= a.nchunks) break;
+    const long long ci = a.backward ? a.nchunks - 1 - c : c;
+    const int L = a.clev[ci];
+    const int dep = a.backward ? L + 1 : L - 1;
+    if (tid == 0 && dep >= 0 && dep < a.nlev) {
+      const int want = a.lcount[dep];
+      int got;
+      do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(a.done + dep) : "memory");
+      } while (got < want);
+    }
+    __syncthreads();
+    const int beg = a.cbeg[ci], end = a.cend[ci];
+    for (int r = beg + warp; r < end; r += GS_THREADS / 32) {
+      const int64_t row = a.rows[r];
+      const int64_t ps = (int64_t)a.rowptr[row], pe = (int64_t)a.rowptr[row + 1];
+      double s = 0.0, d = 0.0, xold = 0.0;
+      if (lane == 0) {
+        s = a.b[row];
+        xold = __ldcg(a.x + row);
+      }
+      for (int64_t p0 = ps; p0 < pe; p0 += 32) {
+        const int64_t p = p0 + lane;
+        const bool valid = p < pe;
+        const int32_t col = valid ? a.colval[p] : -1;
+        const double v = valid ? a.nzval[p] : 0.0;
+        const bool use = valid && (!a.zero_guess || col < row);
+        const double xv = use ? __ldcg(a.x + col) : 0.0;  // x changes during the sweep: read through L2
+        prod[warp][lane] = __dmul_rn(v, xv);
+        const unsigned usemask = __ballot_sync(0xffffffffu, use);
+        const unsigned dmask = __ballot_sync(0xffffffffu, valid && col == row);
+        if (dmask) d = __shfl_sync(0xffffffffu, v, __ffs(dmask) - 1);
+        __syncwarp();
+        if (lane == 0) {
+          const int cnt = (int)min((int64_t)32, pe - p0);
+          for (int k = 0; k < cnt; ++k)
+            if ((usemask >> k) & 1u) s = __dsub_rn(s, prod[warp][k]);  // s -= a*x[col], in CSR order
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
+        if (!a.zero_guess) s = __dadd_rn(s, __dmul_rn(d, xold));  // s += d*x[row]
+        s = __ddiv_rn(s, d);
+        a.x[row] = s;
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicAdd(a.done + L, end - beg);
+  }
+}
+
+__global__ void k_levels_box(int32_t *lev, int32_t *rows, int64_t n, int64_t bx, int64_t by, int64_t wx, int64_t wy, int64_t wz) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ix = i % bx, iy = (i / bx) % by, iz = i / (bx * by);
+    lev[i] = (int32_t)(wx * ix + wy * iy + wz * iz);
+    rows[i] = (int32_t)i;
+  }
+}
+__global__ void k_iota(int32_t *rows, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) rows[i] = (int32_t)i;
+}
+__global__ void k_hist(const int32_t *lev, int64_t n, int32_t *count) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) atomicAdd(count + lev[i], 1);
+}
+
+static void gs_free_part(GsPart &g) {
+  cudaFree(g.d_rows); cudaFree(g.d_cbeg); cudaFree(g.d_cend); cudaFree(g.d_clev); cudaFree(g.d_lcount); cudaFree(g.d_done); cudaFree(g.d_ticket);
+  g = GsPart();
+}
+
+extern "C" int pa_gs_create(pa_mat *A, pa_gs **out) {
+  PA_CHECK(A && out && A->committed, PA_ESTATE, "pa_gs_create: matrix missing or not committed");
+  pa_gs *g = new pa_gs();
+  g->A = A;
+  g->parts.resize(A->ctx->nlocal);
+  *out = g;
+  return PA_OK;
+}
+
+/* Geometry hint for stencil operators on a box (local dims, x fastest): wavefront weights w such that every
+ * lower-numbered neighbour has a strictly smaller w.(ix,iy,iz): 27-pt (1,2,4), 7-pt (1,1,1). */
+extern "C" int pa_gs_set_box(pa_gs *g, int32_t k, int32_t kind, const int64_t *dims) {
+  PA_CHECK(g && dims && !g->committed && k >= 0 && k < (int)g->parts.size(), PA_EINVAL, "pa_gs_set_box: bad arguments");
+  PA_CHECK(kind == 7 || kind == 27, PA_EINVAL, "pa_gs_set_box: kind must be 7 or 27");
+  GsPart &p = g->parts[k];
+  PA_CHECK(dims[0] * dims[1] * dims[2] == g->A->parts[k].nrows, PA_EINVAL, "pa_gs_set_box: dims do not match the own rows");
+  p.geom = true;
+  for (int d = 0; d < 3; ++d) p.dims[d] = dims[d];
+  p.w[0] = 1;
+  p.w[1] = kind == 27 ? 2 : 1;
+  p.w[2] = kind == 27 ? 4 : 1;
+  return PA_OK;
+}
+
+extern "C" int pa_gs_commit(pa_gs *g) {
+  PA_CHECK(g && !g->committed, PA_ESTATE, "pa_gs_commit: missing or already committed");
+  pa_ctx *c = g->A->ctx;
+  PA_CUDA(cudaSetDevice(c->device));
+  for (int k = 0; k < c->nlocal; ++k) {
+    GsPart &p = g->parts[k];
+    const MatPart &m = g->A->parts[k];
+    p.n = m.nrows;
+    if (p.n == 0) continue;
+    PA_CHECK(p.n < (1ll << 31), PA_EINVAL, "pa_gs_commit: too many rows");
+    int32_t *d_lev = nullptr, *d_lev2 = nullptr, *d_rows0 = nullptr;
+    PA_CUDA(cudaMalloc((void **)&d_lev, p.n * sizeof(int32_t)));
+    PA_CUDA(cudaMalloc((void **)&d_lev2, p.n * sizeof(int32_t)));
+    PA_CUDA(cudaMalloc((void **)&d_rows0, p.n * sizeof(int32_t)));
+    PA_CUDA(cudaMalloc((void **)&p.d_rows, p.n * sizeof(int32_t)));
+    if (p.geom) {
+      k_levels_box<<<148 * 8, 256, 0, c->stream>>>(d_lev, d_rows0, p.n, p.dims[0], p.dims[1], p.w[0], p.w[1], p.w[2]);
+      p.nlev = (int)(p.w[0] * (p.dims[0] - 1) + p.w[1] * (p.dims[1] - 1) + p.w[2] * (p.dims[2] - 1) + 1);
+    } else {
+      // generic matrices: level[i] = 1 + max level[j] over own neighbours j < i (host pass over the CSR)
+      std::vector<int64_t> rp(p.n + 1);
+      std::vector<int32_t> cv(m.nnz);
+      PA_TRY(pa_mat_download_csr(g->A, k, rp.data(), cv.data(), nullptr));
+      std::vector<int32_t> lev(p.n, 0);
+      int mx = 0;
+      for (int64_t i = 0; i < p.n; ++i) {
+        int l = 0;
+        for (int64_t q = rp[i]; q < rp[i + 1]; ++q)
+          if (cv[q] < i) l = std::max(l, lev[cv[q]] + 1);
+        lev[i] = l;
+        mx = std::max(mx, l);
+      }
+      for (int64_t i = 0; i < p.n; ++i)  // the backward sweep reuses the levels in reverse: needs a symmetric pattern
+        for (int64_t q = rp[i]; q < rp[i + 1]; ++q)
+          PA_CHECK(!(cv[q] > i && cv[q] < p.n && lev[cv[q]] <= lev[i]), PA_EINVAL,
+                   "pa_gs_commit: non-symmetric sparsity pattern (row %lld): the wavefront schedule needs a symmetric pattern", (long long)i);
+      p.nlev = mx + 1;
+      PA_CUDA(cudaMemcpyAsync(d_lev, lev.data(), p.n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+      k_iota<<<148 * 8, 256, 0, c->stream>>>(d_rows0, p.n);
+      PA_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    size_t tmp_bytes = 0;
+    int bits = 1;
+    while ((1ll << bits) < p.nlev) ++bits;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_lev, d_lev2, d_rows0, p.d_rows, (int)p.n, 0, bits, c->stream);
+    void *d_tmp = nullptr;
+    PA_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+    PA_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_lev, d_lev2, d_rows0, p.d_rows, (int)p.n, 0, bits, c->stream));
+    PA_CUDA(cudaMalloc((void **)&p.d_lcount, p.nlev * sizeof(int32_t)));
+    PA_CUDA(cudaMemsetAsync(p.d_lcount, 0, p.nlev * sizeof(int32_t), c->stream));
+    k_hist<<<148 * 8, 256, 0, c->stream>>>(d_lev, p.n, p.d_lcount);
+    std::vector<int32_t> lcount(p.nlev);
+    PA_CUDA(cudaMemcpyAsync(lcount.data(), p.d_lcount, p.nlev * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    PA_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_tmp); cudaFree(d_lev); cudaFree(d_lev2); cudaFree(d_rows0);
+    std::vector<int32_t> cbeg, cend, clev;
+    int64_t pos = 0;
+    for (int l = 0; l < p.nlev; ++l) {
+      for (int64_t o = 0; o < lcount[l]; o += GS_CHUNK) {
+        cbeg.push_back((int32_t)(pos + o));
+        cend.push_back((int32_t)(pos + std::min<int64_t>(o + GS_CHUNK, lcount[l])));
+        clev.push_back(l);
+      }
+      pos += lcount[l];
+    }
+    PA_CHECK(pos == p.n, PA_ESTATE, "pa_gs_commit: level histogram does not cover all rows");
+    p.nchunks = (int64_t)cbeg.size();
+    PA_CUDA(cudaMalloc((void **)&p.d_cbeg, p.nchunks * sizeof(int32_t)));
+    PA_CUDA(cudaMalloc((void **)&p.d_cend, p.nchunks * sizeof(int32_t)));
+    PA_CUDA(cudaMalloc((void **)&p.d_clev, p.nchunks * sizeof(int32_t)));
+    PA_CUDA(cudaMemcpyAsync(p.d_cbeg, cbeg.data(), p.nchunks * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    PA_CUDA(cudaMemcpyAsync(p.d_cend, cend.data(), p.nchunks * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    PA_CUDA(cudaMemcpyAsync(p.d_clev, clev.data(), p.nchunks * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    PA_CUDA(cudaMalloc((void **)&p.d_done, p.nlev * sizeof(int)));
+    PA_CUDA(cudaMalloc((void **)&p.d_ticket, sizeof(unsigned)));
+    PA_CUDA(cudaStreamSynchronize(c->stream));
+    c->launches += 3;
+  }
+  g->committed = true;
+  return PA_OK;
+}
+
+extern "C" int pa_gs_destroy(pa_gs *g) {
+  if (!g) return PA_OK;
+  pa_ctx *c = g->A->ctx;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto &p : g->parts) gs_free_part(p);
+  delete g;
+  return PA_OK;
+}
+
+// one sweep over the own rows of every local part (ghost entries of x are inputs only)
+static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero_guess) {
+  pa_ctx *c = g->A->ctx;
+  static int ctas_per_sm = 0;
+  for (int k = 0; k < c->nlocal; ++k) {
+    GsPart &p = g->parts[k];
+    const MatPart &m = g->A->parts[k];
+    if (p.n == 0) continue;
+    PA_CUDA(cudaMemsetAsync(p.d_done, 0, p.nlev * sizeof(int), c->stream));
+    PA_CUDA(cudaMemsetAsync(p.d_ticket, 0, sizeof(unsigned), c->stream));
+    auto launch = [&](auto tag) -> int {
+      using PtrT = decltype(tag);
+      GsArgs<PtrT> a;
+      a.rowptr = (const PtrT *)m.d_rowptr;
+      a.colval = m.d_colval;
+      a.nzval = m.d_nzval;
+      a.b = b->d[k];
+      a.x = x->d[k];
+      a.rows = p.d_rows; a.cbeg = p.d_cbeg; a.cend = p.d_cend; a.clev = p.d_clev; a.lcount = p.d_lcount;
+      a.done = p.d_done;
+      a.ticket = p.d_ticket;
+      a.nchunks = p.nchunks;
+      a.nlev = p.nlev;
+      a.backward = backward;
+      a.zero_guess = zero_guess;
+      if (!ctas_per_sm) {
+        PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_gs_sweep<PtrT>, GS_THREADS, 0));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+      }
+      int nsm = 148;
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+      // every CTA of the grid must be able to become resident (a waiting CTA only waits on running ones)
+      const int64_t grid = std::min<int64_t>(p.nchunks, (int64_t)nsm * ctas_per_sm);
+      k_gs_sweep<PtrT><<<(unsigned)grid, GS_THREADS, 0, c->stream>>>(a);
+      return PA_OK;
+    };
+    if (m.ptr64) PA_TRY(launch((int64_t)0)); else PA_TRY(launch((int32_t)0));
+    c->launches++;
+  }
+  PA_CUDA(cudaGetLastError());
+  return PA_OK;
+}
+
+/* smooth!(x, gauss_seidel state, b; zero_guess): one symmetric iteration (smoothers.jl:98-125):
+ * consistent!(x) unless zero_guess, forward sweep (zero-guess variant when zero_guess), backward sweep. */
+extern "C" int pa_gs_smooth(pa_gs *g, pa_vec *x, const pa_vec *b, int32_t zero_guess) {
+  PA_CHECK(g && x && b && g->committed, PA_ESTATE, "pa_gs_smooth: smoother missing or not committed");
+  pa_ctx *c = g->A->ctx;
+  PA_CUDA(cudaSetDevice(c->device));
+  for (int k = 0; k < c->nlocal; ++k) {
+    const PlanPart &xp = x->plan->parts[k], &cp = g->A->cols->parts[k], &bp = b->plan->parts[k];
+    PA_CHECK(xp.n_local == cp.n_local && xp.n_own == cp.n_own && xp.prefix && bp.n_own == xp.n_own && bp.prefix, PA_EINVAL,
+             "pa_gs_smooth: x/b do not match the (own-first) column partition of A on part %d", c->part_ids[k] + 1);
+  }
+  if (!zero_guess) PA_TRY(pa_vec_consistent(x));
+  PA_TRY(pa_before_write(c));
+  PA_TRY(gs_sweep(g, x, b, 0, zero_guess ? 1 : 0));
+  PA_TRY(gs_sweep(g, x, b, 1, 0));
+  return PA_OK;
+}
+
+// ------------------------------------------------------------------ restrict / prolongate (injection, f2c)
+__global__ void k_restrict(double *rc, const double *bf, const double *axf, int64_t nc, int64_t cx, int64_t cy, int64_t fx, int64_t fy) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ix = i % cx, iy = (i / cx) % cy, iz = i / (cx * cy);
+    const int64_t f = 2 * ix + fx * (2 * iy + fy * 2 * iz);
+    rc[i] = __dsub_rn(bf[f], axf[f]);  // r_c[i] = r_f[v] - Axf[v]
+  }
+}
+__global__ void k_prolong(double *xf, const double *xc, int64_t nc, int64_t cx, int64_t cy, int64_t fx, int64_t fy) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ix = i % cx, iy = (i / cx) % cy, iz = i / (cx * cy);
+    const int64_t f = 2 * ix + fx * (2 * iy + fy * 2 * iz);
+    xf[f] = __dadd_rn(xf[f], xc[i]);  // x_f[v] += x_c[i]
+  }
+}
+
+/* Mg_preconditioner (mg_preconditioner.jl:44-63): levels[0] = coarsest ... levels[n-1] = finest.
+ * dims: nlevels x nlocal x 3 local box dims (x fastest); each level halves the one above. */
+extern "C" int pa_mg_create(int32_t nlevels, pa_mat **A, pa_gs **gs, const int64_t *dims, pa_mg **out) {
+  PA_CHECK(nlevels >= 1 && A && gs && dims && out, PA_EINVAL, "pa_mg_create: bad arguments");
+  pa_mg *M = new pa_mg();
+  M->ctx = A[0]->ctx;
+  M->nlev = nlevels;
+  const int nl = M->ctx->nlocal;
+  for (int l = 0; l < nlevels; ++l) {
+    PA_CHECK(A[l] && gs[l] && A[l]->committed && gs[l]->committed && gs[l]->A == A[l] && A[l]->ctx == M->ctx, PA_ESTATE,
+             "pa_mg_create: level %d not ready", l);
+    M->A.push_back(A[l]);
+    M->gs.push_back(gs[l]);
+    std::vector<std::array<int64_t, 3>> d(nl);
+    for (int k = 0; k < nl; ++k) {
+      for (int q = 0; q < 3; ++q) d[k][q] = dims[((size_t)l * nl + k) * 3 + q];
+      PA_CHECK(d[k][0] * d[k][1] * d[k][2] == A[l]->parts[k].nrows, PA_EINVAL, "pa_mg_create: dims of level %d do not match", l);
+      if (l > 0)
+        for (int q = 0; q < 3; ++q)
+          PA_CHECK(M->dims[l - 1][k][q] * 2 == d[k][q], PA_EINVAL, "pa_mg_create: level %d is not twice level %d", l, l - 1);
+    }
+    M->dims.push_back(d);
+  }
+  M->r.assign(nlevels, nullptr);
+  M->x.assign(nlevels, nullptr);
+  M->Axf.assign(nlevels, nullptr);
+  for (int l = 0; l < nlevels; ++l) {
+    if (l < nlevels - 1) {
+      PA_TRY(pa_vec_create(A[l]->cols, &M->r[l]));
+      PA_TRY(pa_vec_create(A[l]->cols, &M->x[l]));
+      PA_TRY(pa_vec_fill(M->r[l], 0.0));
+      PA_TRY(pa_vec_fill(M->x[l], 0.0));
+    }
+    if (l > 0) {
+      PA_TRY(pa_vec_create(A[l]->cols, &M->Axf[l]));
+      PA_TRY(pa_vec_fill(M->Axf[l], 0.0));
+    }
+  }
+  *out = M;
+  return PA_OK;
+}
+
+extern "C" int pa_mg_destroy(pa_mg *M) {
+  if (!M) return PA_OK;
+  for (int l = M->nlev - 1; l >= 0; --l) {  // reverse creation order (symmetric heap discipline)
+    pa_vec_destroy(M->Axf[l]);
+    pa_vec_destroy(M->x[l]);
+    pa_vec_destroy(M->r[l]);
+  }
+  delete M;
+  return PA_OK;
+}
+
+static int small_grid(int64_t n) {
+  int64_t b = (n + 255) / 256;
+  return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
+}
+
+// pc_solve!(x, s, b, l; zero_guess) — mg_preconditioner.jl:314-328 (l is 0-based here)
+static int pc_solve(pa_mg *M, pa_vec *x, const pa_vec *b, int l, int zero_guess) {
+  pa_ctx *c = M->ctx;
+  PA_TRY(pa_gs_smooth(M->gs[l], x, b, zero_guess));  // bottom solve / pre-smoother
+  if (l == 0) return PA_OK;
+  PA_TRY(pa_spmv(M->A[l], x, M->Axf[l], 1.0, 0.0, PA_SPMV_DEFAULT));  // mul_no_lat!(Axf, A, x)
+  PA_TRY(pa_before_write(c));
+  for (int k = 0; k < c->nlocal; ++k) {
+    const auto &dc = M->dims[l - 1][k], &df = M->dims[l][k];
+    const int64_t nc = dc[0] * dc[1] * dc[2];
+    if (!nc) continue;
+    k_restrict<<<small_grid(nc), 256, 0, c->stream>>>(M->r[l - 1]->d[k], b->d[k], M->Axf[l]->d[k], nc, dc[0], dc[1], df[0], df[1]);
+    c->launches++;
+  }
+  PA_CUDA(cudaGetLastError());
+  PA_TRY(pa_vec_fill(M->x[l - 1], 0.0));
+  PA_TRY(pc_solve(M, M->x[l - 1], M->r[l - 1], l - 1, 1));
+  PA_TRY(pa_before_write(c));
+  for (int k = 0; k < c->nlocal; ++k) {
+    const auto &dc = M->dims[l - 1][k], &df = M->dims[l][k];
+    const int64_t nc = dc[0] * dc[1] * dc[2];
+    if (!nc) continue;
+    k_prolong<<<small_grid(nc), 256, 0, c->stream>>>(x->d[k], M->x[l - 1]->d[k], nc, dc[0], dc[1], df[0], df[1]);
+    c->launches++;
+  }
+  PA_CUDA(cudaGetLastError());
+  return pa_gs_smooth(M->gs[l], x, b, 0);  // post-smoother
+}
+
+/* ldiv!(x, P::Mg_preconditioner, b) — mg_preconditioner.jl:202-206 */
+extern "C" int pa_mg_apply(pa_mg *M, pa_vec *x, const pa_vec *b) {
+  PA_CHECK(M && x && b, PA_EINVAL, "pa_mg_apply: null argument");
+  PA_CUDA(cudaSetDevice(M->ctx->device));
+  PA_TRY(pa_vec_fill(x, 0.0));
+  return pc_solve(M, x, b, M->nlev - 1, 1);
+}
