@@ -4,13 +4,14 @@
 // :224-251 (restrict!/prolongate!), :314-328 (pc_solve!).
 //
 // The reference sweeps the own rows of each part sequentially (1:n, then n:-1:1).  A sequential sweep is a
-// dependency DAG: row i needs the NEW values of its lower-numbered neighbours.  We execute exactly that DAG
-// with a wavefront (level) schedule — rows of one level have no mutual dependencies — so every row sees
-// precisely the inputs it sees in the sequential sweep and performs the same arithmetic in the same order
-// (s -= a*x[col] in CSR order, s += d*x[row], s /= d; separate multiply/add).  The result is bit-identical to
-// the reference's sweep; no multi-colouring (which would change the iteration) is used.
-// Persistent CTAs take 256-row chunks of the level-sorted row list from an atomic ticket and wait on a
-// per-level completion counter of the previous level (no grid-wide barrier, no kernel launch per level).
+// dependency DAG: row i needs the NEW values of its lower-numbered neighbours and the OLD values of the others.
+// We execute exactly that DAG as a dataflow: one warp per row, rows handed out in wavefront (level) order, each
+// lane that needs a NEW value spins on that row's "done in this sweep" flag before loading it.  Every row sees
+// precisely the inputs of the sequential sweep and performs the same arithmetic in the same order
+// (s -= a*x[col] in CSR order, s += d*x[row], s /= d; separate multiply/add), so the result is bit-identical to
+// the reference's sweep; no multi-colouring (which would change the iteration) and no per-level barrier.
+// Deadlock freedom: rows are processed in level order by a persistent grid whose warps are all resident; a warp
+// only ever waits for rows of lower levels, which sit earlier in the order of some resident warp.
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
@@ -18,16 +19,15 @@
 
 #include "pa_internal.h"
 
-#define GS_THREADS 512
-#define GS_CHUNK 256
+#define GS_THREADS 256
+#define GS_SPIN_LIMIT (20000000000LL)  // ~10 s of SM cycles, then give up and flag an error instead of hanging
 
 struct GsPart {
   int64_t n = 0;
   int nlev = 0;
-  int64_t nchunks = 0;
-  int32_t *d_rows = nullptr, *d_cbeg = nullptr, *d_cend = nullptr, *d_clev = nullptr, *d_lcount = nullptr;
-  int *d_done = nullptr;       // [nlev] rows finished per level (zeroed before every sweep)
-  unsigned *d_ticket = nullptr;
+  int32_t *d_rows = nullptr;  // own rows sorted by wavefront level (ascending)
+  int *d_flag = nullptr;      // [n] sweep epoch in which the row was last updated
+  int epoch = 0;
   bool geom = false;
   int64_t dims[3] = {0, 0, 0}, w[3] = {0, 0, 0};
 };
@@ -54,71 +54,70 @@ struct GsArgs {
   const double *nzval;
   const double *b;
   double *x;
-  const int32_t *rows, *cbeg, *cend, *clev, *lcount;
-  int *done;
-  unsigned *ticket;
-  int64_t nchunks;
-  int nlev, backward, zero_guess;
+  const int32_t *rows;
+  int *flag;
+  int *err;
+  int64_t n;
+  int epoch, backward, zero_guess;
 };
 
 template <typename PtrT>
-__global__ void __launch_bounds__(GS_THREADS) k_gs_sweep(const GsArgs<PtrT> a) {
-  __shared__ long long s_chunk;
+__global__ void __launch_bounds__(GS_THREADS) k_gs_flow(const GsArgs<PtrT> a) {
   __shared__ double prod[GS_THREADS / 32][32];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (;;) {
-    if (tid == 0) s_chunk = (long long)atomicAdd(a.ticket, 1u);
-    __syncthreads();
-    const long long c = s_chunk;
-    if (c >= a.nchunks) break;
-    const long long ci = a.backward ? a.nchunks - 1 - c : c;
-    const int L = a.clev[ci];
-    const int dep = a.backward ? L + 1 : L - 1;
-    if (tid == 0 && dep >= 0 && dep < a.nlev) {
-      const int want = a.lcount[dep];
-      int got;
-      do {
-        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(a.done + dep) : "memory");
-      } while (got < want);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t W = (int64_t)gridDim.x * (GS_THREADS / 32);
+  const int64_t w = (int64_t)blockIdx.x * (GS_THREADS / 32) + warp;
+  for (int64_t pos = w; pos < a.n; pos += W) {
+    const int64_t row = a.backward ? a.rows[a.n - 1 - pos] : a.rows[pos];
+    const int64_t ps = (int64_t)a.rowptr[row], pe = (int64_t)a.rowptr[row + 1];
+    double s = 0.0, d = 0.0, xold = 0.0;
+    if (lane == 0) {
+      s = a.b[row];
+      xold = __ldcg(a.x + row);
     }
-    __syncthreads();
-    const int beg = a.cbeg[ci], end = a.cend[ci];
-    for (int r = beg + warp; r < end; r += GS_THREADS / 32) {
-      const int64_t row = a.rows[r];
-      const int64_t ps = (int64_t)a.rowptr[row], pe = (int64_t)a.rowptr[row + 1];
-      double s = 0.0, d = 0.0, xold = 0.0;
-      if (lane == 0) {
-        s = a.b[row];
-        xold = __ldcg(a.x + row);
-      }
-      for (int64_t p0 = ps; p0 < pe; p0 += 32) {
-        const int64_t p = p0 + lane;
-        const bool valid = p < pe;
-        const int32_t col = valid ? a.colval[p] : -1;
-        const double v = valid ? a.nzval[p] : 0.0;
-        const bool use = valid && (!a.zero_guess || col < row);
-        const double xv = use ? __ldcg(a.x + col) : 0.0;  // x changes during the sweep: read through L2
-        prod[warp][lane] = __dmul_rn(v, xv);
-        const unsigned usemask = __ballot_sync(0xffffffffu, use);
-        const unsigned dmask = __ballot_sync(0xffffffffu, valid && col == row);
-        if (dmask) d = __shfl_sync(0xffffffffu, v, __ffs(dmask) - 1);
-        __syncwarp();
-        if (lane == 0) {
-          const int cnt = (int)min((int64_t)32, pe - p0);
-          for (int k = 0; k < cnt; ++k)
-            if ((usemask >> k) & 1u) s = __dsub_rn(s, prod[warp][k]);  // s -= a*x[col], in CSR order
+    for (int64_t p0 = ps; p0 < pe; p0 += 32) {
+      const int64_t p = p0 + lane;
+      const bool valid = p < pe;
+      const int32_t col = valid ? a.colval[p] : -1;
+      const double v = valid ? a.nzval[p] : 0.0;
+      const bool use = valid && (!a.zero_guess || col < row);
+      // NEW value needed: an own row that precedes this one in the sweep order
+      const bool fresh = use && col < a.n && (a.backward ? col > row : col < row);
+      if (fresh) {
+        const int *f = a.flag + col;
+        int got;
+        long long t0 = 0;
+        for (;;) {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(f) : "memory");
+          if (got == a.epoch) break;
+          if (!t0) t0 = clock64();
+          if (clock64() - t0 > GS_SPIN_LIMIT) {
+            *a.err = 3;
+            break;
+          }
+          __nanosleep(32);
         }
-        __syncwarp();
       }
+      const double xv = use ? __ldcg(a.x + col) : 0.0;  // x changes during the sweep: always through L2
+      prod[warp][lane] = __dmul_rn(v, xv);
+      const unsigned usemask = __ballot_sync(0xffffffffu, use);
+      const unsigned dmask = __ballot_sync(0xffffffffu, valid && col == row);
+      if (dmask) d = __shfl_sync(0xffffffffu, v, __ffs(dmask) - 1);
+      __syncwarp();
       if (lane == 0) {
-        if (!a.zero_guess) s = __dadd_rn(s, __dmul_rn(d, xold));  // s += d*x[row]
-        s = __ddiv_rn(s, d);
-        a.x[row] = s;
+        const int cnt = (int)min((int64_t)32, pe - p0);
+        for (int k = 0; k < cnt; ++k)
+          if ((usemask >> k) & 1u) s = __dsub_rn(s, prod[warp][k]);  // s -= a*x[col], in CSR order
       }
+      __syncwarp();
     }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) atomicAdd(a.done + L, end - beg);
+    if (lane == 0) {
+      if (!a.zero_guess) s = __dadd_rn(s, __dmul_rn(d, xold));  // s += d*x[row]
+      s = __ddiv_rn(s, d);
+      a.x[row] = s;
+      __threadfence();
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.flag + row), "r"(a.epoch) : "memory");
+    }
   }
 }
 
@@ -132,12 +131,10 @@ __global__ void k_levels_box(int32_t *lev, int32_t *rows, int64_t n, int64_t bx,
 __global__ void k_iota(int32_t *rows, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) rows[i] = (int32_t)i;
 }
-__global__ void k_hist(const int32_t *lev, int64_t n, int32_t *count) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) atomicAdd(count + lev[i], 1);
-}
 
 static void gs_free_part(GsPart &g) {
-  cudaFree(g.d_rows); cudaFree(g.d_cbeg); cudaFree(g.d_cend); cudaFree(g.d_clev); cudaFree(g.d_lcount); cudaFree(g.d_done); cudaFree(g.d_ticket);
+  cudaFree(g.d_rows);
+  cudaFree(g.d_flag);
   g = GsPart();
 }
 
@@ -197,10 +194,10 @@ extern "C" int pa_gs_commit(pa_gs *g) {
         lev[i] = l;
         mx = std::max(mx, l);
       }
-      for (int64_t i = 0; i < p.n; ++i)  // the backward sweep reuses the levels in reverse: needs a symmetric pattern
+      for (int64_t i = 0; i < p.n; ++i)  // the backward sweep walks the same order in reverse: needs a symmetric pattern
         for (int64_t q = rp[i]; q < rp[i + 1]; ++q)
           PA_CHECK(!(cv[q] > i && cv[q] < p.n && lev[cv[q]] <= lev[i]), PA_EINVAL,
-                   "pa_gs_commit: non-symmetric sparsity pattern (row %lld): the wavefront schedule needs a symmetric pattern", (long long)i);
+                   "pa_gs_commit: non-symmetric sparsity pattern (row %lld): the wavefront order needs a symmetric pattern", (long long)i);
       p.nlev = mx + 1;
       PA_CUDA(cudaMemcpyAsync(d_lev, lev.data(), p.n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
       k_iota<<<148 * 8, 256, 0, c->stream>>>(d_rows0, p.n);
@@ -213,35 +210,12 @@ extern "C" int pa_gs_commit(pa_gs *g) {
     void *d_tmp = nullptr;
     PA_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
     PA_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_lev, d_lev2, d_rows0, p.d_rows, (int)p.n, 0, bits, c->stream));
-    PA_CUDA(cudaMalloc((void **)&p.d_lcount, p.nlev * sizeof(int32_t)));
-    PA_CUDA(cudaMemsetAsync(p.d_lcount, 0, p.nlev * sizeof(int32_t), c->stream));
-    k_hist<<<148 * 8, 256, 0, c->stream>>>(d_lev, p.n, p.d_lcount);
-    std::vector<int32_t> lcount(p.nlev);
-    PA_CUDA(cudaMemcpyAsync(lcount.data(), p.d_lcount, p.nlev * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    PA_CUDA(cudaMalloc((void **)&p.d_flag, p.n * sizeof(int)));
+    PA_CUDA(cudaMemsetAsync(p.d_flag, 0, p.n * sizeof(int), c->stream));
     PA_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(d_tmp); cudaFree(d_lev); cudaFree(d_lev2); cudaFree(d_rows0);
-    std::vector<int32_t> cbeg, cend, clev;
-    int64_t pos = 0;
-    for (int l = 0; l < p.nlev; ++l) {
-      for (int64_t o = 0; o < lcount[l]; o += GS_CHUNK) {
-        cbeg.push_back((int32_t)(pos + o));
-        cend.push_back((int32_t)(pos + std::min<int64_t>(o + GS_CHUNK, lcount[l])));
-        clev.push_back(l);
-      }
-      pos += lcount[l];
-    }
-    PA_CHECK(pos == p.n, PA_ESTATE, "pa_gs_commit: level histogram does not cover all rows");
-    p.nchunks = (int64_t)cbeg.size();
-    PA_CUDA(cudaMalloc((void **)&p.d_cbeg, p.nchunks * sizeof(int32_t)));
-    PA_CUDA(cudaMalloc((void **)&p.d_cend, p.nchunks * sizeof(int32_t)));
-    PA_CUDA(cudaMalloc((void **)&p.d_clev, p.nchunks * sizeof(int32_t)));
-    PA_CUDA(cudaMemcpyAsync(p.d_cbeg, cbeg.data(), p.nchunks * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    PA_CUDA(cudaMemcpyAsync(p.d_cend, cend.data(), p.nchunks * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    PA_CUDA(cudaMemcpyAsync(p.d_clev, clev.data(), p.nchunks * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    PA_CUDA(cudaMalloc((void **)&p.d_done, p.nlev * sizeof(int)));
-    PA_CUDA(cudaMalloc((void **)&p.d_ticket, sizeof(unsigned)));
-    PA_CUDA(cudaStreamSynchronize(c->stream));
-    c->launches += 3;
+    p.epoch = 0;
+    c->launches += 2;
   }
   g->committed = true;
   return PA_OK;
@@ -260,13 +234,11 @@ extern "C" int pa_gs_destroy(pa_gs *g) {
 // one sweep over the own rows of every local part (ghost entries of x are inputs only)
 static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero_guess) {
   pa_ctx *c = g->A->ctx;
-  static int ctas_per_sm = 0;
   for (int k = 0; k < c->nlocal; ++k) {
     GsPart &p = g->parts[k];
     const MatPart &m = g->A->parts[k];
     if (p.n == 0) continue;
-    PA_CUDA(cudaMemsetAsync(p.d_done, 0, p.nlev * sizeof(int), c->stream));
-    PA_CUDA(cudaMemsetAsync(p.d_ticket, 0, sizeof(unsigned), c->stream));
+    p.epoch += 1;
     auto launch = [&](auto tag) -> int {
       using PtrT = decltype(tag);
       GsArgs<PtrT> a;
@@ -275,22 +247,22 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
       a.nzval = m.d_nzval;
       a.b = b->d[k];
       a.x = x->d[k];
-      a.rows = p.d_rows; a.cbeg = p.d_cbeg; a.cend = p.d_cend; a.clev = p.d_clev; a.lcount = p.d_lcount;
-      a.done = p.d_done;
-      a.ticket = p.d_ticket;
-      a.nchunks = p.nchunks;
-      a.nlev = p.nlev;
+      a.rows = p.d_rows;
+      a.flag = p.d_flag;
+      a.err = c->d_err;
+      a.n = p.n;
+      a.epoch = p.epoch;
       a.backward = backward;
       a.zero_guess = zero_guess;
-      if (!ctas_per_sm) {
-        PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_gs_sweep<PtrT>, GS_THREADS, 0));
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-      }
+      int ctas_per_sm = 0;
+      PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_gs_flow<PtrT>, GS_THREADS, 0));
+      if (ctas_per_sm < 1) ctas_per_sm = 1;
       int nsm = 148;
       cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
-      // every CTA of the grid must be able to become resident (a waiting CTA only waits on running ones)
-      const int64_t grid = std::min<int64_t>(p.nchunks, (int64_t)nsm * ctas_per_sm);
-      k_gs_sweep<PtrT><<<(unsigned)grid, GS_THREADS, 0, c->stream>>>(a);
+      // all CTAs of the grid must be co-resident: a waiting warp only waits for rows held by running warps
+      const int64_t want = (p.n + GS_THREADS / 32 - 1) / (GS_THREADS / 32);
+      const int64_t grid = std::min<int64_t>(want, (int64_t)nsm * ctas_per_sm);
+      k_gs_flow<PtrT><<<(unsigned)grid, GS_THREADS, 0, c->stream>>>(a);
       return PA_OK;
     };
     if (m.ptr64) PA_TRY(launch((int64_t)0)); else PA_TRY(launch((int32_t)0));
