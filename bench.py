@@ -372,7 +372,7 @@ def run_ours(args):
         line = {
             "metric": "hpcg_cg_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"gallery {args.kind}-pt Laplacian {n}^3 rows per GPU (global {gn[0]}x{gn[1]}x{gn[2]}), parts {shape}, "
+            "config": {"workload": f"{("gallery 7-pt Laplacian" if args.kind == 7 else "HPCG 27-pt operator")} {n}^3 rows per GPU (global {gn[0]}x{gn[1]}x{gn[2]}), parts {shape}, "
                                    f"CSR fp64/int32, ref_cg! {args.iters} iterations per step, Pl=Identity, x0=0, b=A*ones",
                        "l2_policy": "inputs (matrix 11+ GB, vectors 1 GB each) are far larger than the 126 MB L2; no flush needed",
                        "rows_per_gpu": n_rows, "nnz_per_gpu": nnz, "parallelism": f"row-block partition {shape}, one part per GPU"},
