@@ -145,6 +145,15 @@ int pa_mat_set_csr_split(pa_mat *A, int32_t k, int64_t nrows, int32_t index_base
                          int32_t col_bits, const void *rowptr_oo, const void *colval_oo,
                          const double *nzval_oo, const void *rowptr_oh, const void *colval_oh,
                          const double *nzval_oh);
+/* SparseMatrixCSC local matrices — the reference's DEFAULT storage (src/p_sparse_matrix.jl:1132-1135; spmv_csc!
+ * src/sparse_utils.jl:671-690).  Converted to CSR at upload; rows list their entries by ascending column, which is
+ * the order in which spmv_csc! scatters into b[row], so results stay bit-identical.  Unsplit: n_local_rows x
+ * n_local_cols with own rows first and empty ghost rows.  Split: own_own / own_ghost CSC blocks. */
+int pa_mat_set_csc(pa_mat *A, int32_t k, int64_t nrows, int64_t ncols, int32_t index_base, int32_t ptr_bits,
+                   int32_t idx_bits, const void *colptr, const void *rowval, const double *nzval);
+int pa_mat_set_csc_split(pa_mat *A, int32_t k, int64_t nrows, int32_t index_base, int32_t ptr_bits, int32_t idx_bits,
+                         const void *colptr_oo, const void *rowval_oo, const double *nzval_oo,
+                         const void *colptr_oh, const void *rowval_oh, const double *nzval_oh);
 /* On-device generators of the benchmark operators for a box partition (own box lo..hi of a gn grid,
  * 0-based, hi exclusive): kind 7 = gallery laplacian_fdm (src/gallery.jl:12-86), kind 27 = HPCG
  * build_matrix (HPCG/src/sparse_matrix.jl:27-80).  ghost_gid_sorted / ghost_id_of_sorted: the ng

@@ -797,6 +797,68 @@ extern "C" int pa_mat_set_csr_split(pa_mat *A, int32_t k, int64_t nrows, int32_t
   return upload_csr(A->ctx, A->parts[k], nrows, cp.n_local, rp, cv, nz);
 }
 
+// CSC -> CSR on the host (setup time).  Columns are visited in ascending order, so every CSR row lists its
+// entries by ascending column: the row sum then adds the terms in the order spmv_csc! scatters them
+// (fill!(b,0); for col ascending: b[row] += a*x[col], src/sparse_utils.jl:671-690) — bit-identical results.
+static int csc_to_csr(int64_t nrows, int64_t ncols, int index_base, int ptr_bits, int idx_bits, const void *colptr, const void *rowval,
+                      const double *nzval, int64_t keep_rows, std::vector<int64_t> &rp, std::vector<int32_t> &cv, std::vector<double> &nz) {
+  const int64_t nnz = rd(colptr, ptr_bits, ncols) - index_base;
+  PA_CHECK(rd(colptr, ptr_bits, 0) == index_base && nnz >= 0, PA_EINVAL, "CSC colptr does not start at the index base");
+  rp.assign(keep_rows + 1, 0);
+  for (int64_t p = 0; p < nnz; ++p) {
+    const int64_t r = rd(rowval, idx_bits, p) - index_base;
+    PA_CHECK(r >= 0 && r < nrows, PA_EINVAL, "CSC row id out of range");
+    PA_CHECK(r < keep_rows, PA_EINVAL, "CSC matrix has entries in ghost rows: only assembled matrices are supported");
+    rp[r + 1]++;
+  }
+  for (int64_t r = 0; r < keep_rows; ++r) rp[r + 1] += rp[r];
+  cv.resize(nnz);
+  nz.resize(nnz);
+  std::vector<int64_t> cur(rp.begin(), rp.end() - 1);
+  for (int64_t c = 0; c < ncols; ++c) {
+    const int64_t a = rd(colptr, ptr_bits, c) - index_base, b = rd(colptr, ptr_bits, c + 1) - index_base;
+    PA_CHECK(b >= a, PA_EINVAL, "CSC colptr not monotone");
+    for (int64_t p = a; p < b; ++p) {
+      const int64_t r = rd(rowval, idx_bits, p) - index_base;
+      cv[cur[r]] = (int32_t)c;
+      nz[cur[r]++] = nzval[p];
+    }
+  }
+  return PA_OK;
+}
+
+/* SparseMatrixCSC local matrices (the reference's default storage, src/p_sparse_matrix.jl:1132-1135).
+ * Unsplit: n_local_rows x n_local_cols with own rows first and empty ghost rows. */
+extern "C" int pa_mat_set_csc(pa_mat *A, int32_t k, int64_t nrows, int64_t ncols, int32_t index_base, int32_t ptr_bits, int32_t idx_bits,
+                              const void *colptr, const void *rowval, const double *nzval) {
+  PA_CHECK(A && !A->committed && k >= 0 && k < A->ctx->nlocal, PA_ESTATE, "pa_mat_set_csc: bad matrix/part");
+  PA_CHECK((ptr_bits == 32 || ptr_bits == 64) && (idx_bits == 32 || idx_bits == 64) && (index_base == 0 || index_base == 1) && colptr, PA_EINVAL,
+           "pa_mat_set_csc: bad index description");
+  const PlanPart &rpart = A->rows->parts[k];
+  PA_CHECK(rpart.prefix && nrows >= rpart.n_own, PA_EINVAL, "pa_mat_set_csc: needs own rows first");
+  std::vector<int64_t> rp;
+  std::vector<int32_t> cv;
+  std::vector<double> nz;
+  PA_TRY(csc_to_csr(nrows, ncols, index_base, ptr_bits, idx_bits, colptr, rowval, nzval, rpart.n_own, rp, cv, nz));
+  return pa_mat_set_csr(A, k, rpart.n_own, ncols, 0, 64, 32, rp.data(), cv.data(), nz.data());
+}
+
+/* Split format with CSC blocks: own_own (n_own_rows x n_own_cols) and own_ghost (n_own_rows x n_ghost_cols). */
+extern "C" int pa_mat_set_csc_split(pa_mat *A, int32_t k, int64_t nrows, int32_t index_base, int32_t ptr_bits, int32_t idx_bits,
+                                    const void *colptr_oo, const void *rowval_oo, const double *nzval_oo, const void *colptr_oh,
+                                    const void *rowval_oh, const double *nzval_oh) {
+  PA_CHECK(A && !A->committed && k >= 0 && k < A->ctx->nlocal, PA_ESTATE, "pa_mat_set_csc_split: bad matrix/part");
+  PA_CHECK((ptr_bits == 32 || ptr_bits == 64) && (idx_bits == 32 || idx_bits == 64) && (index_base == 0 || index_base == 1) && colptr_oo && colptr_oh,
+           PA_EINVAL, "pa_mat_set_csc_split: bad index description");
+  const PlanPart &cp = A->cols->parts[k];
+  std::vector<int64_t> rp1, rp2;
+  std::vector<int32_t> cv1, cv2;
+  std::vector<double> nz1, nz2;
+  PA_TRY(csc_to_csr(nrows, cp.n_own, index_base, ptr_bits, idx_bits, colptr_oo, rowval_oo, nzval_oo, nrows, rp1, cv1, nz1));
+  PA_TRY(csc_to_csr(nrows, cp.n_ghost, index_base, ptr_bits, idx_bits, colptr_oh, rowval_oh, nzval_oh, nrows, rp2, cv2, nz2));
+  return pa_mat_set_csr_split(A, k, nrows, 0, 64, 32, rp1.data(), cv1.data(), nz1.data(), rp2.data(), cv2.data(), nz2.data());
+}
+
 extern "C" int pa_mat_commit(pa_mat *A) {
   PA_CHECK(A && !A->committed, PA_ESTATE, "pa_mat_commit: matrix missing or already committed");
   for (int k = 0; k < A->ctx->nlocal; ++k) PA_CHECK(A->parts[k].set, PA_ESTATE, "pa_mat_commit: local part %d not set", k);

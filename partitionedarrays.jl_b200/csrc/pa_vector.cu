@@ -122,10 +122,22 @@ static int same_plan(const pa_vec *a, const pa_vec *b, const char *who) {
   PA_CHECK(a && b, PA_EINVAL, "%s: null vector", who);
   if (a->plan == b->plan) return PA_OK;
   PA_CHECK(a->plan->ctx == b->plan->ctx && a->plan->parts.size() == b->plan->parts.size(), PA_EINVAL, "%s: vectors live on different backends", who);
-  for (size_t k = 0; k < a->plan->parts.size(); ++k)
-    PA_CHECK(a->plan->parts[k].n_local == b->plan->parts[k].n_local && a->plan->parts[k].n_own == b->plan->parts[k].n_own, PA_EINVAL,
-             "%s: partitions do not match (matching_local_indices, src/p_range.jl:1813-1823)", who);
+  for (size_t k = 0; k < a->plan->parts.size(); ++k) {
+    const PlanPart &pa_ = a->plan->parts[k], &pb_ = b->plan->parts[k];
+    // same own ids are required (matching_own_indices, src/p_range.jl:1813-1817); ghost layouts may differ, in which
+    // case broadcast updates touch own entries only (src/p_vector.jl:1271-1276) — needs the own-first layout
+    PA_CHECK(pa_.n_own == pb_.n_own && (pa_.n_local == pb_.n_local || (pa_.prefix && pb_.prefix)), PA_EINVAL,
+             "%s: partitions do not match (matching_own_indices, src/p_range.jl:1813-1823)", who);
+  }
   return PA_OK;
+}
+
+// number of leading local entries a broadcast update touches on part k: all local entries when the vectors share the
+// partition, the own entries only otherwise (BroadcastedPVector materialize!, src/p_vector.jl:1271-1276)
+static int64_t bcast_extent(const pa_vec *w, const pa_vec *x, const pa_vec *y, int k) {
+  const PlanPart &pw = w->plan->parts[k], &px = x->plan->parts[k], &py = y->plan->parts[k];
+  const bool same = (w->plan == x->plan || pw.n_local == px.n_local) && (w->plan == y->plan || pw.n_local == py.n_local);
+  return same ? pw.n_local : pw.n_own;
 }
 
 extern "C" int pa_vec_fill(pa_vec *v, double a) {
@@ -149,7 +161,8 @@ extern "C" int pa_vec_copy(pa_vec *dst, const pa_vec *src) {
   PA_CUDA(cudaSetDevice(c->device));
   PA_TRY(pa_before_write(c));
   for (int k = 0; k < c->nlocal; ++k) {
-    int64_t n = dst->plan->parts[k].n_local;
+    // same partition: all local values; only matching own indices: own values (copyto!, src/p_vector.jl:805-814)
+    int64_t n = bcast_extent(dst, src, src, k);
     if (n && dst->d[k] != src->d[k])
       PA_CUDA(cudaMemcpyAsync(dst->d[k], src->d[k], n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   }
@@ -175,7 +188,7 @@ int pa_waxpby_dev(pa_vec *w, Coef ca, const pa_vec *x, Coef cb, const pa_vec *y)
   pa_ctx *c = w->plan->ctx;
   PA_TRY(pa_before_write(c));
   for (int k = 0; k < c->nlocal; ++k) {
-    int64_t n = w->plan->parts[k].n_local;
+    int64_t n = bcast_extent(w, x, y, k);
     if (!n) continue;
     k_waxpby<<<ew_grid(n), PA_RED_THREADS, 0, c->stream>>>(w->d[k], ca, x->d[k], cb, y->d[k], n);
     c->launches++;

@@ -395,6 +395,21 @@ class PSparseMatrix:
         check(_capi.lib().pa_mat_set_csr_split(self.h, k, len(rp1) - 1, index_base, rp1.dtype.itemsize * 8, cv1.dtype.itemsize * 8,
                                                ptr(rp1), ptr(cv1), ptr(f64(nz1)), ptr(rp2), ptr(cv2), ptr(f64(nz2))))
 
+    def set_csc(self, k: int, nrows: int, colptr, rowval, nzval, index_base: int = 1):
+        """Unsplit SparseMatrixCSC local matrix (n_local_rows x n_local_cols; the reference's default storage)."""
+        colptr, rowval = np.ascontiguousarray(colptr), np.ascontiguousarray(rowval)
+        check(_capi.lib().pa_mat_set_csc(self.h, k, nrows, len(colptr) - 1, index_base, colptr.dtype.itemsize * 8,
+                                         rowval.dtype.itemsize * 8 if len(rowval) else 32, ptr(colptr), ptr(rowval), ptr(f64(nzval))))
+
+    def set_csc_split(self, k: int, nrows: int, oo, oh, index_base: int = 1):
+        """Split format with SparseMatrixCSC blocks: oo/oh = (colptr, rowval, nzval)."""
+        cp1, rv1, nz1 = (np.ascontiguousarray(a) for a in oo)
+        cp2, rv2, nz2 = (np.ascontiguousarray(a) for a in oh)
+        rv2 = rv2.astype(rv1.dtype)
+        cp2 = cp2.astype(cp1.dtype)
+        check(_capi.lib().pa_mat_set_csc_split(self.h, k, nrows, index_base, cp1.dtype.itemsize * 8, rv1.dtype.itemsize * 8,
+                                               ptr(cp1), ptr(rv1), ptr(f64(nz1)), ptr(cp2), ptr(rv2), ptr(f64(nz2))))
+
     def commit(self):
         check(_capi.lib().pa_mat_commit(self.h))
         return self
@@ -462,8 +477,21 @@ def _coo_to_csr(I, J, V, m, n):
     return rowptr.astype(np.int32), J.astype(np.int32), nz
 
 
-def psparse(I: List, J: List, V: List, rows: PRange, cols: PRange, assembled: bool = True, split_format: bool = True) -> PSparseMatrix:
-    """psparse(I,J,V,row_partition,col_partition; assembled=true) (src/p_sparse_matrix.jl:1150-1286).
+def _csr_to_csc(rp, cv, nz, ncols):
+    """1-based CSR (rows sorted by column) -> 1-based CSC (what SparseArrays.sparse builds; setup-time host helper)."""
+    m = len(rp) - 1
+    rowid = np.repeat(np.arange(1, m + 1), np.diff(rp.astype(np.int64)))
+    order = np.lexsort((rowid, cv))
+    colptr = np.ones(ncols + 1, dtype=np.int64)
+    colptr[1:] = 1 + np.cumsum(np.bincount(cv.astype(np.int64) - 1, minlength=ncols)) if len(cv) else 1
+    return colptr, rowid[order].astype(np.int64), nz[order]
+
+
+def psparse(I: List, J: List, V: List, rows: PRange, cols: PRange, assembled: bool = True, split_format: bool = True,
+            local_format: str = "csr") -> PSparseMatrix:
+    """psparse([T,] I,J,V,row_partition,col_partition; assembled=true) (src/p_sparse_matrix.jl:1150-1286).
+    local_format: "csr" = SparseMatrixCSR{1,Float64,Int32} local matrices; "csc" = the reference's default
+    SparseMatrixCSC{Float64,Int} (converted to CSR at upload, summation order of spmv_csc! preserved).
     Per local part: COO in global ids whose rows are owned by that part.  Ghost columns are discovered with
     find_owner + union_ghost (:1226-1236).  Non-assembled input (rows owned elsewhere) is the 'next' scope
     row and is rejected here."""
@@ -504,7 +532,15 @@ def psparse(I: List, J: List, V: List, rows: PRange, cols: PRange, assembled: bo
                 cnt = np.bincount(rowid[mask], minlength=len(o2l))
                 p = np.ones(len(o2l) + 1, dtype=np.int32); p[1:] = 1 + np.cumsum(cnt)
                 return p, ids[mask].astype(np.int32), nz2[mask]
-            A.set_csr_split(k, block(isown, l2o[cv2]), block(~isown, l2g[cv2]))
+            oo, oh = block(isown, l2o[cv2]), block(~isown, l2g[cv2])
+            if local_format == "csc":
+                A.set_csc_split(k, len(o2l), _csr_to_csc(*oo, ind_c.n_own), _csr_to_csc(*oh, ind_c.n_ghost))
+            else:
+                A.set_csr_split(k, oo, oh)
+        elif local_format == "csc":
+            if not ind_r.own_is_prefix:
+                raise ValueError("unsplit CSC upload needs own rows first")
+            A.set_csc(k, ind_r.n_local, *_csr_to_csc(rp, cv, nz, ind_c.n_local))
         else:
             A.set_csr(k, rp2.astype(np.int32), cv2, nz2)
     return A.commit()
