@@ -21,18 +21,45 @@ def nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+def _source_hash() -> str:
+    """Content hash of every source the library is built from (mtimes do not survive a snapshot copy)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "pa_b200.h"), __file__]
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(os.path.basename(f).encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
+STAMP = os.path.join(LIBDIR, ".build_hash")
+
+
 def needs_build() -> bool:
-    if not os.path.exists(SO):
+    if not os.path.exists(SO) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "pa_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as f:
+        return f.read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return SO
+    import fcntl
+
     os.makedirs(LIBDIR, exist_ok=True)
+    with open(os.path.join(LIBDIR, ".build_lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)  # several ranks may import at once: one builds, the others wait
+        try:
+            if not force and not needs_build():
+                return SO
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     objs = []
     common = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"] + ARCH
     if verbose:
@@ -51,8 +78,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    link = [nvcc(), "-shared", "-o", SO] + objs + ARCH + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"]
+    tmp = SO + ".tmp"
+    link = [nvcc(), "-shared", "-o", tmp] + objs + ARCH + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"]
     subprocess.run(link, check=True)
+    os.replace(tmp, SO)  # atomic: a concurrent loader never sees a half-written library
+    with open(STAMP, "w") as f:
+        f.write(_source_hash())
     return SO
 
 
