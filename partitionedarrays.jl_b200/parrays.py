@@ -492,12 +492,33 @@ def psparse(I: List, J: List, V: List, rows: PRange, cols: PRange, assembled: bo
     """psparse([T,] I,J,V,row_partition,col_partition; assembled=true) (src/p_sparse_matrix.jl:1150-1286).
     local_format: "csr" = SparseMatrixCSR{1,Float64,Int32} local matrices; "csc" = the reference's default
     SparseMatrixCSC{Float64,Int} (converted to CSR at upload, summation order of spmv_csc! preserved).
-    Per local part: COO in global ids whose rows are owned by that part.  Ghost columns are discovered with
-    find_owner + union_ghost (:1226-1236).  Non-assembled input (rows owned elsewhere) is the 'next' scope
-    row and is rejected here."""
-    if not assembled:
-        raise NotImplementedError("psparse(...; assembled=false): matrix assembly is outside the hot-path scope")
+    Per local part: COO in global ids.  assembled=True: every row is owned by the part that lists it (what
+    build_p_matrix / fdm_example use, :1249-1270).  assembled=False (the reference's default): rows owned elsewhere are
+    shipped to their owner first.  Ghost columns are discovered with find_owner + union_ghost (:1226-1236).
+    The COO->CSR compression runs on the host at setup time (on-device compression is 'next')."""
     b = rows.backend
+    if not assembled:
+        # Disassembled input (the reference's default, src/p_sparse_matrix.jl:1186-1222 + assemble :1590-1756): triplets whose
+        # row is owned by another part are shipped to the row owner at setup time (host metadata exchange), the owner keeps
+        # its own triplets first and appends the received ones in sender order; ids < 1 are dropped.  The COO->CSR compression
+        # below then combines duplicates in that order (the reference combines per sender first: same sum, other association).
+        outgoing = []
+        for ind_r, i, j, v in zip(rows.indices, I, J, V):
+            i, j, v = np.asarray(i, dtype=np.int64), np.asarray(j, dtype=np.int64), np.asarray(v, dtype=np.float64)
+            ok = (i >= 1) & (j >= 1)
+            i, j, v = i[ok], j[ok], v[ok]
+            owner = _find_owner(rows, ind_r, i)
+            outgoing.append((ind_r.part, {int(q): (i[owner == q], j[owner == q], v[owner == q]) for q in np.unique(owner)}))
+        everyone = dict(b.gather_all(outgoing))
+        I2, J2, V2 = [], [], []
+        for ind_r in rows.indices:
+            me = ind_r.part
+            pieces = [everyone[me].get(me)] + [everyone[q].get(me) for q in sorted(everyone) if q != me]
+            pieces = [p for p in pieces if p is not None]
+            I2.append(np.concatenate([p[0] for p in pieces]) if pieces else np.zeros(0, np.int64))
+            J2.append(np.concatenate([p[1] for p in pieces]) if pieces else np.zeros(0, np.int64))
+            V2.append(np.concatenate([p[2] for p in pieces]) if pieces else np.zeros(0, np.float64))
+        I, J, V = I2, J2, V2
     new_cols = []
     for ind_c, j in zip(cols.indices, J):
         j = np.asarray(j, dtype=np.int64)
