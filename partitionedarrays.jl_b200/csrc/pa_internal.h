@@ -66,6 +66,7 @@ struct pa_ctx {
   unsigned *d_ticket = nullptr;   // [nlocal]
   double *h_scal = nullptr;       // pinned [PA_NSCAL]
   unsigned long long *d_epoch = nullptr;  // [nlocal] device-side op counters (graph-replay safe)
+  unsigned long long *d_red_epoch = nullptr;  // sequence number of the peer-memory scalar all-reduce
   int *d_err = nullptr;           // device error flag (spin timeout)
   int *h_err = nullptr;           // pinned mirror
   // NCCL (dlopen)

@@ -122,7 +122,8 @@ extern "C" int pa_ctx_create(int32_t nparts_global, int32_t nlocal, const int32_
   PA_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   PA_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   c->arena_bytes = align_up(arena_bytes ? arena_bytes : (1ull << 30), 1 << 20);
-  c->hdr_bytes = align_up(2ull * nparts_global * sizeof(unsigned long long), 4096);
+  // header: arrive[nparts] | done[nparts] | red_flag[2][nparts] | red_val[2][nparts]   (8 bytes each)
+  c->hdr_bytes = align_up(6ull * nparts_global * sizeof(unsigned long long), 4096);
   PA_CHECK(c->arena_bytes > c->hdr_bytes, PA_EINVAL, "pa_ctx_create: arena too small");
   c->bump = c->hdr_bytes;
   c->peer_base.assign(nparts_global, nullptr);
@@ -148,6 +149,8 @@ extern "C" int pa_ctx_create(int32_t nparts_global, int32_t nlocal, const int32_
   PA_CUDA(cudaMemsetAsync(c->d_ticket, 0, nlocal * sizeof(unsigned), c->stream));
   PA_CUDA(cudaMalloc((void **)&c->d_epoch, nlocal * sizeof(unsigned long long)));
   PA_CUDA(cudaMemsetAsync(c->d_epoch, 0, nlocal * sizeof(unsigned long long), c->stream));
+  PA_CUDA(cudaMalloc((void **)&c->d_red_epoch, sizeof(unsigned long long)));
+  PA_CUDA(cudaMemsetAsync(c->d_red_epoch, 0, sizeof(unsigned long long), c->stream));
   PA_CUDA(cudaMalloc((void **)&c->d_err, sizeof(int)));
   PA_CUDA(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
   PA_CUDA(cudaHostAlloc((void **)&c->h_scal, PA_NSCAL * sizeof(double), cudaHostAllocDefault));
@@ -178,6 +181,7 @@ extern "C" int pa_ctx_destroy(pa_ctx *c) {
   cudaFree(c->d_ticket);
   cudaFree(c->d_epoch);
   cudaFree(c->d_err);
+  cudaFree(c->d_red_epoch);
   cudaFreeHost(c->h_scal);
   cudaFreeHost(c->h_err);
   if (c->side) cudaStreamDestroy(c->side);
@@ -294,7 +298,76 @@ __global__ void k_sum_partials(const double *partial, int n, double *out) {
   *out = s;
 }
 
+// Scalar all-reduce over NVLink peer memory (replaces ncclAllReduce for the CG scalars when every process holds one
+// part): each part pushes its value and a sequence flag into a double-buffered slot of every part's arena header with
+// system-scope stores, waits for all flags, and adds the P slots in PART ORDER — the order of the reference's sequential
+// `sum` over parts (src/primitives.jl:693-698), bitwise identical on all parts, one kernel, ~NVLink store latency.
+// Buffer parity e&1 is safe: a part can only reach reduction e+2 after every peer has posted e+1, i.e. finished reading e.
+struct RedPeers {
+  unsigned long long *flag[PA_MAX_NBR];
+  double *val[PA_MAX_NBR];
+};
+
+__global__ void k_allreduce_peer(double *inout, unsigned long long *epoch, RedPeers peers, const unsigned long long *my_flag,
+                                 const double *my_val, int me, int nparts, int *err) {
+  __shared__ double got[PA_MAX_NBR];
+  const unsigned long long e = *epoch + 1;
+  const int par = (int)(e & 1ull);
+  const int q = threadIdx.x;
+  __syncthreads();
+  if (q < nparts) {
+    const double v = *inout;
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(peers.val[q] + par * nparts + me), "d"(v) : "memory");
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.flag[q] + par * nparts + me), "l"(e) : "memory");
+    // wait for part q's contribution to arrive in MY header
+    const unsigned long long *f = my_flag + par * nparts + q;
+    unsigned long long seen;
+    long long t0 = clock64();
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
+      if (seen >= e) break;
+      if (clock64() - t0 > PA_SPIN_LIMIT) {
+        *err = 1;
+        break;
+      }
+    }
+    double x;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x) : "l"(my_val + par * nparts + q) : "memory");
+    got[q] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < nparts; ++i) s += got[i];  // part order
+    *inout = s;
+    *epoch = e;
+  }
+}
+
+static bool peer_allreduce_ok(pa_ctx *c) {
+  if (c->world <= 1 || c->nlocal != 1 || c->nparts != c->world || c->nparts > PA_MAX_NBR) return false;
+  if (pa_knob(c, "nccl_allreduce", 0)) return false;
+  for (int p = 0; p < c->nparts; ++p)
+    if (!c->peer_base[p]) return false;
+  return true;
+}
+
 int pa_reduce_finish(pa_ctx *c, double *d_out) {
+  if (peer_allreduce_ok(c)) {
+    RedPeers rp;
+    for (int p = 0; p < c->nparts; ++p) {
+      unsigned long long *hdr = (unsigned long long *)c->peer_base[p];
+      rp.flag[p] = hdr + 2 * c->nparts;
+      rp.val[p] = (double *)(hdr + 4 * c->nparts);
+    }
+    unsigned long long *mine = (unsigned long long *)c->arena[0];
+    k_allreduce_peer<<<1, 32, 0, c->stream>>>(d_out, c->d_red_epoch, rp, mine + 2 * c->nparts, (const double *)(mine + 4 * c->nparts),
+                                              c->part_ids[0], c->nparts, c->d_err);
+    c->launches++;
+    PA_CUDA(cudaGetLastError());
+    return PA_OK;
+  }
   if (c->nlocal > 1) {
     k_sum_partials<<<1, 1, 0, c->stream>>>(c->d_partial, c->nlocal, d_out);
     c->launches++;
@@ -354,7 +427,47 @@ static int wait_all(pa_plan *plan, bool done) {
   return PA_OK;
 }
 
+// publish + wait in ONE launch (one part per process: nobody else's signal has to be enqueued in between)
+__global__ void k_signal_wait(unsigned long long *epoch, FlagPtrs dst, FlagPtrs src, int n, int *err) {
+  unsigned long long e = *epoch + 1ull;
+  __syncthreads();
+  if (threadIdx.x == 0) *epoch = e;
+  __threadfence_system();
+  if ((int)threadIdx.x < n) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst.p[threadIdx.x]), "l"(e) : "memory");
+    const unsigned long long *f = src.p[threadIdx.x];
+    unsigned long long got;
+    long long t0 = clock64();
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(f) : "memory");
+      if (got >= e) break;
+      if (clock64() - t0 > PA_SPIN_LIMIT) {
+        *err = 1;
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __threadfence_system();
+}
+
 int pa_collective_begin(pa_plan *plan) {
+  pa_ctx *c = plan->ctx;
+  if (c->nlocal == 1) {
+    const PlanPart &pp = plan->parts[0];
+    const int n = (int)pp.nbrs.size();
+    if (!n) return PA_OK;
+    FlagPtrs dst, src;
+    for (int i = 0; i < n; ++i) {
+      PA_CHECK(c->peer_base[pp.nbrs[i]], PA_ESTATE, "part %d's arena was never imported (pa_ctx_arena_import)", pp.nbrs[i] + 1);
+      dst.p[i] = flag_addr(c, pp.nbrs[i], c->part_ids[0], false);
+      src.p[i] = flag_addr(c, c->part_ids[0], pp.nbrs[i], false);
+    }
+    k_signal_wait<<<1, 32, 0, c->stream>>>(c->d_epoch, dst, src, n, c->d_err);
+    c->launches++;
+    PA_CUDA(cudaGetLastError());
+    return PA_OK;
+  }
   PA_TRY(signal_all(plan, false));
   return wait_all(plan, false);
 }
