@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=512, help="grid edge per GPU")
+    ap.add_argument("--n", "--grid", dest="n", type=int, default=512, help="grid edge per GPU")
     ap.add_argument("--kind", type=int, default=7, choices=[7, 27])
     ap.add_argument("--iters", type=int, default=50, help="CG iterations per step (HPCG ref_max_iters)")
     ap.add_argument("--spmv-reps", type=int, default=50)
