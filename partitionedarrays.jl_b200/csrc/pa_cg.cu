@@ -93,6 +93,18 @@ static int cg_update(pa_vec *x, const pa_vec *u, pa_vec *r, const pa_vec *cvec, 
 struct pa_mg;
 extern "C" int pa_mg_apply(pa_mg *M, pa_vec *x, const pa_vec *b);
 
+// end of a fused iteration: rotate rho_prev <- rho_cur <- ||r_new||^2, record the history, advance the device-side
+// iteration counter.  With this every kernel of the iteration has iteration-independent arguments, so ONE captured
+// CUDA graph replays the whole loop body (the scalars, epochs and the counter live on the device).
+__global__ void k_cg_commit(double *rho_cur, double *rho_prev, const double *nrm2_new, double *hist, int *it) {
+  const double v = *nrm2_new;
+  *rho_prev = *rho_cur;
+  *rho_cur = v;
+  const int i = *it + 1;
+  hist[i] = v;
+  *it = i;
+}
+
 /* ref_cg!(x,A,b; Pl) with Pl = Identity (mg == NULL) or the HPCG multigrid preconditioner */
 extern "C" int pa_cg_precond(pa_mat *A, pa_vec *x, const pa_vec *b, pa_mg *mg, int32_t maxiter, double tol, uint32_t flags,
                              pa_cg_result *result, double *history) {
@@ -120,6 +132,10 @@ extern "C" int pa_cg_precond(pa_mat *A, pa_vec *x, const pa_vec *b, pa_mg *mg, i
   const double one = 1.0;
   PA_CUDA(cudaMemcpyAsync(d_one, &one, sizeof(double), cudaMemcpyHostToDevice, c->stream));
   double *d_uc = c->d_scal + S_UC;
+  double *d_rho_cur = c->d_scal + S_RHO1, *d_rho_prev = c->d_scal + S_NRM0, *d_nrm2 = c->d_scal + S_NRM2;
+  int *d_it = nullptr;
+  PA_CUDA(cudaMalloc((void **)&d_it, sizeof(int)));
+  PA_CUDA(cudaMemsetAsync(d_it, 0, sizeof(int), c->stream));
   int rc = PA_OK;
   std::vector<double> hist((size_t)maxiter + 1, 0.0);
   int iters = 0, converged = 0;
@@ -136,6 +152,8 @@ extern "C" int pa_cg_precond(pa_mat *A, pa_vec *x, const pa_vec *b, pa_mg *mg, i
     PA_CUDA(cudaStreamSynchronize(c->stream));
     nrm0 = nrm = sqrt(h0);
     hist[0] = nrm0;
+    PA_CUDA(cudaMemcpyAsync(d_rho_cur, d_hist, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    PA_CUDA(cudaMemcpyAsync(d_rho_prev, &one, sizeof(double), cudaMemcpyHostToDevice, c->stream));
     if (nrm0 == 0.0) {  // exact initial guess (the reference would iterate on NaNs here)
       converged = 1;
       return PA_OK;
@@ -166,11 +184,44 @@ extern "C" int pa_cg_precond(pa_mat *A, pa_vec *x, const pa_vec *b, pa_mg *mg, i
         PA_TRY(pa_waxpby_dev(r, coef_imm(1.0), r, coef_ratio(rho, d_uc, -1.0), cv));  // r .-= alpha.*c
         PA_TRY(pa_reduce_dev_to(r, nullptr, 1, d_hist + it + 1));                     // norm(r)
       } else {
-        rho = d_hist + it;  // dot(c,r) with c == r
-        rho_prev = it ? d_hist + it - 1 : d_one;
-        PA_TRY(pa_waxpby_dev(u, coef_imm(1.0), r, coef_ratio(rho, rho_prev, 1.0), u));
-        PA_TRY(pa_spmv_dot(A, u, cv, 1.0, 0.0, PA_SPMV_SKIP_GHOST_REFRESH, u, d_uc));  // c = A*u and u.c in one pass
-        PA_TRY(cg_update(x, u, r, cv, rho, d_uc, d_hist + it + 1));
+        // fused schedule; rho_cur = ||r||^2 = dot(c,r) with c == r, rho_prev from the previous iteration (1 at start)
+        auto fused_iteration = [&]() -> int {
+          PA_TRY(pa_waxpby_dev(u, coef_imm(1.0), r, coef_ratio(d_rho_cur, d_rho_prev, 1.0), u));
+          PA_TRY(pa_spmv_dot(A, u, cv, 1.0, 0.0, PA_SPMV_SKIP_GHOST_REFRESH, u, d_uc));  // c = A*u and u.c in one pass
+          PA_TRY(cg_update(x, u, r, cv, d_rho_cur, d_uc, d_nrm2));
+          k_cg_commit<<<1, 1, 0, c->stream>>>(d_rho_cur, d_rho_prev, d_nrm2, d_hist, d_it);
+          c->launches++;
+          PA_CUDA(cudaGetLastError());
+          return PA_OK;
+        };
+        const bool want_graph = tol <= 0.0 && it == 1 && maxiter >= 4 && pa_knob(c, "cg_graph", 1) != 0;
+        if (want_graph) {
+          // iteration 0 ran eagerly (warm caches, lazy allocations); capture iteration 1 once and replay it for the rest
+          const int64_t l0 = c->launches;
+          cudaGraph_t graph = nullptr;
+          cudaGraphExec_t exec = nullptr;
+          bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+          int rcap = ok ? fused_iteration() : PA_ECUDA;
+          if (ok) ok = cudaStreamEndCapture(c->stream, &graph) == cudaSuccess && rcap == PA_OK && graph;
+          if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+          if (ok) {
+            const int64_t per_iter = c->launches - l0;
+            for (int j = it; j < maxiter && ok; ++j) ok = cudaGraphLaunch(exec, c->stream) == cudaSuccess;
+            c->launches = l0 + per_iter * (maxiter - it);
+          }
+          if (exec) cudaGraphExecDestroy(exec);
+          if (graph) cudaGraphDestroy(graph);
+          if (ok) {
+            iters = maxiter;
+            break;
+          }
+          cudaGetLastError();  // capture unsupported here: fall through to the eager loop
+          PA_CHECK(rcap == PA_OK || rcap == PA_ECUDA, rcap, "%s", pa_last_error());
+          c->launches = l0;
+          c->pending_done.clear();
+          PA_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        PA_TRY(fused_iteration());
       }
       iters = it + 1;
       if (tol > 0.0) {  // the reference checks every iteration (done(), ref_cg.jl:22-26)
@@ -194,6 +245,7 @@ extern "C" int pa_cg_precond(pa_mat *A, pa_vec *x, const pa_vec *b, pa_mg *mg, i
   cudaStreamSynchronize(c->stream);
   cudaFree(d_hist);
   cudaFree(d_rho);
+  cudaFree(d_it);
   pa_vec_destroy(u);
   pa_vec_destroy(cv);
   pa_vec_destroy(r);
