@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=1 << 24, help="rows of the CPU sample")
     ap.add_argument("--no-hpcg27", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the GLOBAL grid is n^3, split over the parts")
     ap.add_argument("--mg", action="store_true", help="also time HPCG multigrid-preconditioned CG (27-pt 512^3, 4 levels)")
     return ap.parse_args()
 
@@ -222,7 +223,7 @@ def run_ours(args):
     N = world
     shape = pa.compute_optimal_shape_xyz(N)
     n = args.n
-    gn = (n * shape[0], n * shape[1], n * shape[2])
+    gn = (n, n, n) if args.strong else (n * shape[0], n * shape[1], n * shape[2])  # --strong: fixed global grid
     stream = torch.cuda.Stream()
     vec_bytes = (n + 2) ** 3 * 8
     backend = pa.CUDAArray(N, mode="distributed" if world > 1 else "sequential", device=local_rank, arena_bytes=8 * vec_bytes + (64 << 20),
@@ -371,7 +372,7 @@ def run_ours(args):
             pass
         line = {
             "metric": "hpcg_cg_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{("gallery 7-pt Laplacian" if args.kind == 7 else "HPCG 27-pt operator")} {n}^3 rows per GPU (global {gn[0]}x{gn[1]}x{gn[2]}), parts {shape}, "
                                    f"CSR fp64/int32, ref_cg! {args.iters} iterations per step, Pl=Identity, x0=0, b=A*ones",
                        "l2_policy": "inputs (matrix 11+ GB, vectors 1 GB each) are far larger than the 126 MB L2; no flush needed",
