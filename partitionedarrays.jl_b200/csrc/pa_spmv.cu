@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
       const int64_t yi = a.rowmap ? (int64_t)a.rowmap[row] : row;
       if (a.alpha == 1.0 && a.beta == 0.0) {
         a.y[yi] = acc;
-        if (a.dotw) dsum = fma(acc, __ldg(a.dotw + yi), dsum);
+        if (a.dotw) dsum = __dadd_rn(dsum, __dmul_rn(acc, __ldg(a.dotw + yi)));  // no FMA anywhere in this kernel (SASS-checked)
       } else {
         const double by = a.beta == 0.0 ? 0.0 : __dmul_rn(a.beta, a.y[yi]);
         a.y[yi] = __dadd_rn(__dmul_rn(a.alpha, acc), by);

@@ -61,3 +61,12 @@ def test_sass_has_no_fma_in_spmv_accumulate():
                          capture_output=True, text=True).stdout
     assert "DMUL" in out and "DADD" in out and "DFMA" not in out
     assert "sm_100a" in subprocess.run([cuobjdump, "-lelf", pa_b200.build.SO], capture_output=True, text=True).stdout
+    # the production kernel: TMA bulk copies (UBLKCP) + mbarriers (SYNCS), separate DMUL/DADD, no DFMA
+    sass = subprocess.run([cuobjdump, "-sass", pa_b200.build.SO], capture_output=True, text=True).stdout
+    blocks = sass.split("Function : ")
+    tma = [b for b in blocks if b.startswith("_Z10k_spmv_tmaIiLi0ELi8E")]
+    assert tma, "k_spmv_tma<int,0,8> not found in the library"
+    assert "UBLKCP" in tma[0] and "SYNCS" in tma[0] and "DMUL" in tma[0] and "DADD" in tma[0] and "DFMA" not in tma[0]
+    gs = [b for b in blocks if b.startswith("_Z9k_gs_flowIiE")]
+    # Gauss-Seidel sweeps: separate DMUL / DADD for s -= a*x (the only DFMAs belong to the IEEE division sequence of __ddiv_rn)
+    assert gs and "DMUL" in gs[0] and "DADD" in gs[0] and "MUFU.RCP64H" in gs[0]
