@@ -154,6 +154,13 @@ int pa_mat_set_csc(pa_mat *A, int32_t k, int64_t nrows, int64_t ncols, int32_t i
 int pa_mat_set_csc_split(pa_mat *A, int32_t k, int64_t nrows, int32_t index_base, int32_t ptr_bits, int32_t idx_bits,
                          const void *colptr_oo, const void *rowval_oo, const double *nzval_oo,
                          const void *colptr_oh, const void *rowval_oh, const double *nzval_oh);
+/* sparse_matrix(T,I,J,V,m,n; reuse=true) on the device (src/sparse_utils.jl:392-405; used by psparse, src/p_sparse_matrix.jl
+ * :1196-1203): COO with 1-based OWN row ids and LOCAL column ids (ids < 1 are skipped like the reference: they become a
+ * stored (1,1,0)); columns sorted within rows, duplicates added in input order.  The pattern cache (the reference's K,
+ * precompute_nzindex :434-455) is kept so that pa_mat_update_coo_values = sparse_matrix!(A,V,K) / psparse! (:457-469,
+ * src/p_sparse_matrix.jl:1291-1305) refreshes the values of the same pattern with one kernel. */
+int pa_mat_set_coo(pa_mat *A, int32_t k, int64_t n, int32_t idx_bits, const void *I, const void *J, const double *V);
+int pa_mat_update_coo_values(pa_mat *A, int32_t k, const double *V, int64_t n);
 /* On-device generators of the benchmark operators for a box partition (own box lo..hi of a gn grid,
  * 0-based, hi exclusive): kind 7 = gallery laplacian_fdm (src/gallery.jl:12-86), kind 27 = HPCG
  * build_matrix (HPCG/src/sparse_matrix.jl:27-80).  ghost_gid_sorted / ghost_id_of_sorted: the ng

@@ -68,6 +68,8 @@ SIGNATURES = {
     "pa_mat_set_csr_split": [_P, _I32, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P],
     "pa_mat_set_csc": [_P, _I32, _I64, _I64, _I32, _I32, _I32, _P, _P, _P],
     "pa_mat_set_csc_split": [_P, _I32, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P],
+    "pa_mat_set_coo": [_P, _I32, _I64, _I32, _P, _P, _P],
+    "pa_mat_update_coo_values": [_P, _I32, _P, _I64],
     "pa_mat_set_stencil": [_P, _I32, _I32, _P, _P, _P, _I64, _P, _P, _P],
     "pa_mat_commit": [_P],
     "pa_mat_nnz": [_P, _I32, _P],

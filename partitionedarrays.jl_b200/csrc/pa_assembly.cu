@@ -1,0 +1,187 @@
+// On-device COO -> CSR compression and value refresh.
+// Reference: sparse_matrix / compresscoo (src/sparse_utils.jl:313-350,392-405: entries with i<1 or j<1 become a stored
+// (1,1,0); columns sorted within rows; duplicates combined with + in input order), precompute_nzindex (:434-455) and
+// sparse_matrix!(A,V,K) (:457-469: fillstored!(A,0); A_nz[K[p]] += V[p] in input order) as used by psparse / psparse!
+// (src/p_sparse_matrix.jl:1196-1203,1291-1305).
+//
+// Device version: 64-bit keys (row<<32 | col), stable radix sort carrying the input position, segment heads -> unique
+// entries, one thread per unique entry adds its duplicates in input order (stable sort keeps it) starting from 0 — the
+// same floating-point sequence as the reference.  The sorted permutation and the segment table are kept so that a
+// later refresh with new values (same pattern) is a single gather-sum kernel: the reference's K cache.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "pa_internal.h"
+
+__global__ void k_coo_keys(const int64_t *I, const int64_t *J, int64_t n, int64_t nrows, int64_t ncols, uint64_t *key, int32_t *pos,
+                           unsigned char *valid, int *err) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = I[p], j = J[p];
+    const bool ok = i >= 1 && j >= 1;
+    if (ok && (i > nrows || j > ncols)) *err = 4;
+    key[p] = ok ? (((uint64_t)(i - 1)) << 32) | (uint64_t)(j - 1) : 0ull;  // skipped entries -> stored (1,1,0)
+    pos[p] = (int32_t)p;
+    valid[p] = ok ? 1 : 0;
+  }
+}
+
+__global__ void k_coo_heads(const uint64_t *key, int64_t n, int32_t *head) {
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x)
+    head[s] = (s == 0 || key[s] != key[s - 1]) ? 1 : 0;
+}
+
+// upos = exclusive scan of head shifted: unique index of sorted entry s is incl[s]-1
+__global__ void k_coo_unique(const uint64_t *key, const int32_t *head, const int32_t *incl, int64_t n, int32_t *ucol, int32_t *segstart,
+                             int64_t *rowcount) {
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x)
+    if (head[s]) {
+      const int32_t u = incl[s] - 1;
+      ucol[u] = (int32_t)(key[s] & 0xffffffffull);
+      segstart[u] = (int32_t)s;
+      atomicAdd((unsigned long long *)(rowcount + (key[s] >> 32)), 1ull);
+    }
+}
+
+__global__ void k_coo_sum(const double *V, const int32_t *perm, const unsigned char *valid, const int32_t *segstart, int64_t nuniq,
+                          int64_t n, double *nz) {
+  for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < nuniq; u += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t a = segstart[u], b = u + 1 < nuniq ? segstart[u + 1] : n;
+    double acc = 0.0;
+    for (int64_t s = a; s < b; ++s) {
+      const int32_t p = perm[s];
+      if (valid[p]) acc = __dadd_rn(acc, V[p]);  // A_nz[k] += v, input order
+    }
+    nz[u] = acc;
+  }
+}
+
+__global__ void k_narrow64(const int64_t *in, int32_t *out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int32_t)in[i];
+}
+
+static void free_coo_cache(MatPart &m) {
+  cudaFree(m.d_coo_perm);
+  cudaFree(m.d_coo_seg);
+  cudaFree(m.d_coo_valid);
+  m.d_coo_perm = m.d_coo_seg = nullptr;
+  m.d_coo_valid = nullptr;
+  m.n_coo = 0;
+}
+
+/* sparse_matrix(T, I, J, V, m, n; reuse=true) on the device for local part k.
+ * I: 1-based OWN row ids, J: 1-based LOCAL column ids (ids < 1 are skipped like the reference), idx_bits 32 or 64.
+ * The pattern cache (the reference's K) is kept for pa_mat_update_coo_values. */
+extern "C" int pa_mat_set_coo(pa_mat *A, int32_t k, int64_t n, int32_t idx_bits, const void *I, const void *J, const double *V) {
+  PA_CHECK(A && !A->committed && k >= 0 && k < A->ctx->nlocal, PA_ESTATE, "pa_mat_set_coo: bad matrix/part");
+  PA_CHECK((idx_bits == 32 || idx_bits == 64) && n >= 0 && n < (1ll << 31) && (n == 0 || (I && J && V)), PA_EINVAL, "pa_mat_set_coo: bad arguments");
+  pa_ctx *c = A->ctx;
+  const PlanPart &rp = A->rows->parts[k], &cp = A->cols->parts[k];
+  PA_CHECK(cp.prefix, PA_EINVAL, "pa_mat_set_coo: needs the own-first column layout (use the host path otherwise)");
+  PA_CUDA(cudaSetDevice(c->device));
+  MatPart &m = A->parts[k];
+  cudaFree(m.d_rowptr); cudaFree(m.d_colval); cudaFree(m.d_nzval);
+  m.d_rowptr = nullptr; m.d_colval = nullptr; m.d_nzval = nullptr;
+  free_coo_cache(m);
+  const int64_t nrows = rp.n_own, ncols = cp.n_local;
+  if (nrows == 0 || ncols == 0) n = 0;  // m*n == 0: nothing is stored (src/sparse_utils.jl:326-329)
+  std::vector<int64_t> hI(n), hJ(n);
+  for (int64_t p = 0; p < n; ++p) {
+    hI[p] = idx_bits == 64 ? ((const int64_t *)I)[p] : ((const int32_t *)I)[p];
+    hJ[p] = idx_bits == 64 ? ((const int64_t *)J)[p] : ((const int32_t *)J)[p];
+  }
+  const int64_t nn = std::max<int64_t>(n, 1);
+  int64_t *dI = nullptr, *dJ = nullptr, *d_rowcount = nullptr, *d_rp64 = nullptr;
+  double *dV = nullptr;
+  uint64_t *key = nullptr, *key2 = nullptr;
+  int32_t *pos = nullptr, *head = nullptr, *incl = nullptr;
+  PA_CUDA(cudaMalloc((void **)&dI, nn * 8)); PA_CUDA(cudaMalloc((void **)&dJ, nn * 8)); PA_CUDA(cudaMalloc((void **)&dV, nn * 8));
+  PA_CUDA(cudaMalloc((void **)&key, nn * 8)); PA_CUDA(cudaMalloc((void **)&key2, nn * 8));
+  PA_CUDA(cudaMalloc((void **)&pos, nn * 4)); PA_CUDA(cudaMalloc((void **)&m.d_coo_perm, nn * 4));
+  PA_CUDA(cudaMalloc((void **)&head, nn * 4)); PA_CUDA(cudaMalloc((void **)&incl, nn * 4));
+  PA_CUDA(cudaMalloc((void **)&m.d_coo_valid, nn));
+  PA_CUDA(cudaMalloc((void **)&d_rowcount, (nrows + 1) * 8)); PA_CUDA(cudaMalloc((void **)&d_rp64, (nrows + 1) * 8));
+  PA_CUDA(cudaMemsetAsync(d_rowcount, 0, (nrows + 1) * 8, c->stream));
+  int64_t nuniq = 0;
+  if (n) {
+    PA_CUDA(cudaMemcpyAsync(dI, hI.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
+    PA_CUDA(cudaMemcpyAsync(dJ, hJ.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
+    PA_CUDA(cudaMemcpyAsync(dV, V, n * 8, cudaMemcpyHostToDevice, c->stream));
+    const int g = 148 * 8;
+    k_coo_keys<<<g, 256, 0, c->stream>>>(dI, dJ, n, nrows, ncols, key, pos, m.d_coo_valid, c->d_err);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, key, key2, pos, m.d_coo_perm, (int)n, 0, 64, c->stream);
+    void *tmp = nullptr;
+    PA_CUDA(cudaMalloc(&tmp, tb ? tb : 1));
+    PA_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, key, key2, pos, m.d_coo_perm, (int)n, 0, 64, c->stream));  // stable
+    k_coo_heads<<<g, 256, 0, c->stream>>>(key2, n, head);
+    size_t tb2 = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, tb2, head, incl, (int)n, c->stream);
+    void *tmp2 = nullptr;
+    PA_CUDA(cudaMalloc(&tmp2, tb2 ? tb2 : 1));
+    PA_CUDA(cub::DeviceScan::InclusiveSum(tmp2, tb2, head, incl, (int)n, c->stream));
+    int32_t last = 0;
+    PA_CUDA(cudaMemcpyAsync(&last, incl + n - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    PA_CUDA(cudaStreamSynchronize(c->stream));
+    nuniq = last;
+    PA_CUDA(cudaMalloc((void **)&m.d_colval, (nuniq + 16) * 4));
+    PA_CUDA(cudaMalloc((void **)&m.d_nzval, (nuniq + 16) * 8));
+    PA_CUDA(cudaMalloc((void **)&m.d_coo_seg, (nuniq + 1) * 4));
+    k_coo_unique<<<g, 256, 0, c->stream>>>(key2, head, incl, n, m.d_colval, m.d_coo_seg, d_rowcount);
+    k_coo_sum<<<g, 256, 0, c->stream>>>(dV, m.d_coo_perm, m.d_coo_valid, m.d_coo_seg, nuniq, n, m.d_nzval);
+    cudaFree(tmp);  // (stream-ordered frees would be nicer; these are setup-time)
+    cudaFree(tmp2);
+    c->launches += 6;
+  } else {
+    PA_CUDA(cudaMalloc((void **)&m.d_colval, 16 * 4));
+    PA_CUDA(cudaMalloc((void **)&m.d_nzval, 16 * 8));
+  }
+  // rowptr = exclusive scan of the per-row unique counts
+  size_t tb3 = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb3, d_rowcount, d_rp64, (int)(nrows + 1), c->stream);
+  void *tmp3 = nullptr;
+  PA_CUDA(cudaMalloc(&tmp3, tb3 ? tb3 : 1));
+  PA_CUDA(cub::DeviceScan::ExclusiveSum(tmp3, tb3, d_rowcount, d_rp64, (int)(nrows + 1), c->stream));
+  PA_CUDA(cudaMalloc(&m.d_rowptr, (nrows + 1) * sizeof(int32_t)));
+  k_narrow64<<<148, 256, 0, c->stream>>>(d_rp64, (int32_t *)m.d_rowptr, nrows + 1);
+  PA_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(tmp3);
+  cudaFree(dI); cudaFree(dJ); cudaFree(dV); cudaFree(key); cudaFree(key2); cudaFree(pos); cudaFree(head); cudaFree(incl);
+  cudaFree(d_rowcount); cudaFree(d_rp64);
+  int herr = 0;
+  PA_CUDA(cudaMemcpy(&herr, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (herr == 4) {
+    cudaMemset(c->d_err, 0, sizeof(int));
+    pa_set_error("pa_mat_set_coo: a row or column id exceeds the local matrix size");
+    return PA_EINVAL;
+  }
+  m.nrows = nrows;
+  m.ncols = ncols;
+  m.nnz = nuniq;
+  m.ptr64 = false;
+  m.n_coo = n;
+  m.rows_per_cta = nuniq <= 8 * nrows ? 256 : (nuniq <= 16 * nrows ? 128 : (nuniq <= 32 * nrows ? 64 : 32));
+  m.tile_nnz.clear();
+  m.ghost_scanned = false;
+  m.set = true;
+  return PA_OK;
+}
+
+/* sparse_matrix!(A, V, K): refresh the values of a matrix built by pa_mat_set_coo with a new V of the same COO pattern
+ * (psparse!, src/p_sparse_matrix.jl:1291-1305).  May be called on a committed matrix. */
+extern "C" int pa_mat_update_coo_values(pa_mat *A, int32_t k, const double *V, int64_t n) {
+  PA_CHECK(A && k >= 0 && k < A->ctx->nlocal && A->parts[k].set, PA_ESTATE, "pa_mat_update_coo_values: bad matrix/part");
+  MatPart &m = A->parts[k];
+  PA_CHECK(m.d_coo_perm && n == m.n_coo && (n == 0 || V), PA_EINVAL, "pa_mat_update_coo_values: matrix was not built from COO or length differs");
+  pa_ctx *c = A->ctx;
+  PA_CUDA(cudaSetDevice(c->device));
+  if (!n) return PA_OK;
+  double *dV = nullptr;
+  PA_CUDA(cudaMalloc((void **)&dV, n * 8));
+  PA_CUDA(cudaMemcpyAsync(dV, V, n * 8, cudaMemcpyHostToDevice, c->stream));
+  k_coo_sum<<<148 * 8, 256, 0, c->stream>>>(dV, m.d_coo_perm, m.d_coo_valid, m.d_coo_seg, m.nnz, n, m.d_nzval);
+  c->launches++;
+  PA_CUDA(cudaGetLastError());
+  PA_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(dV);
+  return PA_OK;
+}

@@ -126,7 +126,11 @@ struct MatPart {
   bool ghost_scanned = false, ghost_tail_ok = true, tma_ok = true;
   int64_t n_grows = 0;
   int32_t *d_grows = nullptr;
-  double *d_dotpart = nullptr;  // per-CTA partials of the fused dot epilogue  // max nnz of a ROWS-row tile, by ROWS (TMA stage sizing)
+  double *d_dotpart = nullptr;  // per-CTA partials of the fused dot epilogue
+  // COO pattern cache (the reference's K of sparse_matrix(...; reuse=true)): sorted permutation + segment starts
+  int32_t *d_coo_perm = nullptr, *d_coo_seg = nullptr;
+  unsigned char *d_coo_valid = nullptr;
+  int64_t n_coo = 0;  // max nnz of a ROWS-row tile, by ROWS (TMA stage sizing)
 };
 
 struct pa_mat {

@@ -678,6 +678,9 @@ extern "C" int pa_mat_create(pa_plan *rows, pa_plan *cols, pa_mat **out) {
 }
 
 static void free_part(MatPart &m) {
+  cudaFree(m.d_coo_perm);
+  cudaFree(m.d_coo_seg);
+  cudaFree(m.d_coo_valid);
   cudaFree(m.d_dotpart);
   cudaFree(m.d_grows);
   cudaFree(m.d_rowptr);

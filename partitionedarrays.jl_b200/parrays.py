@@ -410,6 +410,18 @@ class PSparseMatrix:
         check(_capi.lib().pa_mat_set_csc_split(self.h, k, nrows, index_base, cp1.dtype.itemsize * 8, rv1.dtype.itemsize * 8,
                                                ptr(cp1), ptr(rv1), ptr(f64(nz1)), ptr(cp2), ptr(rv2), ptr(f64(nz2))))
 
+    def set_coo(self, k: int, I_own, J_local, V):
+        """Device-side sparse_matrix(I,J,V; reuse=true): 1-based own row ids / local column ids, ids < 1 skipped."""
+        Ia, Ja = i64(I_own), i64(J_local)
+        check(_capi.lib().pa_mat_set_coo(self.h, k, len(Ia), 64, ptr(Ia), ptr(Ja), ptr(f64(V))))
+
+    def update_coo_values_(self, V: List):
+        """psparse!(A, V, cache): refresh the values of the same COO pattern (src/p_sparse_matrix.jl:1291-1305)."""
+        for k, v in enumerate(V):
+            v = f64(v)
+            check(_capi.lib().pa_mat_update_coo_values(self.h, k, ptr(v), len(v)))
+        return self
+
     def commit(self):
         check(_capi.lib().pa_mat_commit(self.h))
         return self
@@ -488,7 +500,7 @@ def _csr_to_csc(rp, cv, nz, ncols):
 
 
 def psparse(I: List, J: List, V: List, rows: PRange, cols: PRange, assembled: bool = True, split_format: bool = True,
-            local_format: str = "csr") -> PSparseMatrix:
+            local_format: str = "csr", compress: str = "host") -> PSparseMatrix:
     """psparse([T,] I,J,V,row_partition,col_partition; assembled=true) (src/p_sparse_matrix.jl:1150-1286).
     local_format: "csr" = SparseMatrixCSR{1,Float64,Int32} local matrices; "csc" = the reference's default
     SparseMatrixCSC{Float64,Int} (converted to CSR at upload, summation order of spmv_csc! preserved).
@@ -534,6 +546,12 @@ def psparse(I: List, J: List, V: List, rows: PRange, cols: PRange, assembled: bo
         lj[Jk < 1] = 0
         if np.any((li == 0) & (Ik >= 1)):
             raise ValueError("psparse(assembled=true): a row id is not local to its part")
+        if compress == "device":
+            # COO -> CSR on the GPU (sort + in-order duplicate sums), pattern cache kept for update_coo_values_ (psparse!)
+            if not (ind_r.own_is_prefix and ind_c.own_is_prefix):
+                raise ValueError("device compression needs own-first layouts")
+            A.set_coo(k, li, lj, V[k])
+            continue
         rp, cv, nz = _coo_to_csr(li, lj, V[k], ind_r.n_local, ind_c.n_local)
         # keep own rows only, in own order (ghost rows of an assembled matrix are empty)
         o2l = ind_r.own_to_local.astype(np.int64)
