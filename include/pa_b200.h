@@ -197,6 +197,11 @@ int pa_mat_fill_stored(pa_mat *A, double a);
  * PA_SPMV_INLINE_PEER_LOADS|PA_SPMV_SKIP_GHOST_REFRESH). */
 int pa_spmv(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, uint32_t flags);
 
+/* mul!(c, transpose(A), b, alpha, beta) (src/p_sparse_matrix.jl:2144-2162): b on axes(A,1) (own entries read), c on
+ * axes(A,2): c_own = beta*c_own + alpha*A_oo^T b_own + the ghost contributions alpha*A_oh^T b_own shipped to their owners
+ * by assemble!; c's ghost entries are zero on return.  The local transposes are built once on the device. */
+int pa_spmv_transpose(pa_mat *A, pa_vec *b, pa_vec *c, double alpha, double beta);
+
 typedef struct {
   int32_t iters;
   int32_t converged;

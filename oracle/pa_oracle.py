@@ -814,3 +814,26 @@ def hash_uniform(gids_1based: np.ndarray, seed: int) -> np.ndarray:
         z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
         z = z ^ (z >> np.uint64(31))
     return (z >> np.uint64(11)).astype(np.float64) * (2.0 ** -52) - 1.0
+
+
+def pmul_transpose(A: PSparse, b_vals: List[np.ndarray], c_vals: List[np.ndarray], alpha: float = 1.0, beta: float = 0.0):
+    """mul!(c, transpose(A), b, alpha, beta) (src/p_sparse_matrix.jl:2144-2162): ghost entries of c receive
+    alpha*A_oh' b_own, assemble!(c) adds them at the owners after c_own = beta*c_own + alpha*A_oo' b_own.
+    Column sums run over ascending row index (transposed CSR with sorted rows)."""
+    import scipy.sparse as sp
+
+    plan = assembly_plan(A.col_partition)
+    for p in range(len(b_vals)):
+        rows, cols = A.row_partition[p], A.col_partition[p]
+        L = A.local[p]
+        At = sp.csr_matrix((L.nzval, L.colval - 1, L.rowptr.astype(np.int64) - 1), shape=(L.m, L.n)).T.tocsr()
+        At.sort_indices()
+        T = CSR(At.shape[0], At.shape[1], At.indptr.astype(np.int64) + 1, At.indices.astype(np.int32) + 1, At.data)
+        bo = np.zeros(L.m)
+        bo[rows.own_to_local - 1] = own_values(b_vals[p], rows)
+        acc = spmv_csr(T, bo)  # length n_local cols, sequential ascending-row order
+        c = c_vals[p]
+        gl, ol = cols.ghost_to_local - 1, cols.own_to_local - 1
+        c[gl] = alpha * acc[gl]
+        c[ol] = alpha * acc[ol] + beta * c[ol]
+    assemble(c_vals, A.col_partition, plan)

@@ -76,6 +76,7 @@ SIGNATURES = {
     "pa_mat_download_csr": [_P, _I32, _P, _P, _P],
     "pa_mat_fill_stored": [_P, _D],
     "pa_spmv": [_P, _P, _P, _D, _D, _U32],
+    "pa_spmv_transpose": [_P, _P, _P, _D, _D],
     "pa_cg": [_P, _P, _P, _I32, _D, _U32, _P, _P],
     "pa_gs_create": [_P, _P],
     "pa_gs_set_box": [_P, _I32, _I32, _P],

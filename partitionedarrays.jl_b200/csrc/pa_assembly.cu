@@ -185,3 +185,123 @@ extern "C" int pa_mat_update_coo_values(pa_mat *A, int32_t k, const double *V, i
   cudaFree(dV);
   return PA_OK;
 }
+
+// ------------------------------------------------------------------ transpose product
+// mul!(c, transpose(A), b, alpha, beta) (src/p_sparse_matrix.jl:2144-2162): the ghost entries of c receive
+// alpha * A_oh^T b_own, assemble!(c) ships them to their owners, and the own entries get
+// beta*c_own + alpha * A_oo^T b_own before the received contributions are added.
+// Device: the local matrix is transposed once (stable radix sort by column, so every transposed row lists its entries
+// by ascending original row — the summation order of a transposed-CSC/CSR product), the product is then ONE ordinary
+// streaming SpMV of A_local^T (rows = own|ghost columns of A) and the ghost -> owner step is pa_vec_assemble.
+__global__ void k_row_of_entry(const int32_t *rowptr32, const int64_t *rowptr64, int64_t nrows, int32_t *rowidx, int32_t *pos) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t a = rowptr32 ? (int64_t)rowptr32[r] : rowptr64[r], b = rowptr32 ? (int64_t)rowptr32[r + 1] : rowptr64[r + 1];
+    for (int64_t p = a; p < b; ++p) {
+      rowidx[p] = (int32_t)r;
+      pos[p] = (int32_t)p;
+    }
+  }
+}
+__global__ void k_count_cols(const int32_t *colval, int64_t nnz, int64_t *count) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd((unsigned long long *)(count + colval[p]), 1ull);
+}
+__global__ void k_gather_transposed(const int32_t *perm, const int32_t *rowidx, const double *nzval, int64_t nnz, int32_t *tcol, double *tval) {
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nnz; s += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t p = perm[s];
+    tcol[s] = rowidx[p];
+    tval[s] = nzval[p];
+  }
+}
+
+static int build_transpose(pa_mat *A) {
+  if (A->T) return PA_OK;
+  pa_ctx *c = A->ctx;
+  pa_mat *T = new pa_mat();
+  T->ctx = c;
+  T->rows = A->cols;  // rows of A^T = local columns of A (own | ghost)
+  T->cols = A->rows;
+  T->parts.resize(c->nlocal);
+  for (int k = 0; k < c->nlocal; ++k) {
+    const MatPart &m = A->parts[k];
+    MatPart &t = T->parts[k];
+    const int64_t tn = A->cols->parts[k].n_local, nnz = m.nnz;
+    PA_CHECK(nnz < (1ll << 31), PA_EINVAL, "transpose product: local matrix too large (nnz >= 2^31)");
+    PA_CHECK(A->cols->parts[k].prefix && A->rows->parts[k].prefix, PA_EINVAL, "transpose product needs own-first layouts");
+    t.nrows = tn;
+    t.ncols = m.nrows;
+    t.nnz = nnz;
+    t.ptr64 = false;
+    int64_t *d_count = nullptr, *d_tp64 = nullptr;
+    PA_CUDA(cudaMalloc((void **)&d_count, (tn + 1) * 8));
+    PA_CUDA(cudaMalloc((void **)&d_tp64, (tn + 1) * 8));
+    PA_CUDA(cudaMemsetAsync(d_count, 0, (tn + 1) * 8, c->stream));
+    PA_CUDA(cudaMalloc((void **)&t.d_colval, (nnz + 16) * 4));
+    PA_CUDA(cudaMalloc((void **)&t.d_nzval, (nnz + 16) * 8));
+    PA_CUDA(cudaMalloc(&t.d_rowptr, (tn + 1) * 4));
+    const int g = 148 * 8;
+    if (nnz) {
+      int32_t *rowidx = nullptr, *pos = nullptr, *perm = nullptr, *keys2 = nullptr;
+      PA_CUDA(cudaMalloc((void **)&rowidx, nnz * 4)); PA_CUDA(cudaMalloc((void **)&pos, nnz * 4));
+      PA_CUDA(cudaMalloc((void **)&perm, nnz * 4)); PA_CUDA(cudaMalloc((void **)&keys2, nnz * 4));
+      k_row_of_entry<<<g, 256, 0, c->stream>>>(m.ptr64 ? nullptr : (const int32_t *)m.d_rowptr, m.ptr64 ? (const int64_t *)m.d_rowptr : nullptr,
+                                                m.nrows, rowidx, pos);
+      k_count_cols<<<g, 256, 0, c->stream>>>(m.d_colval, nnz, d_count);
+      int bits = 1;
+      while ((1ll << bits) < tn) ++bits;
+      size_t tb = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tb, m.d_colval, keys2, pos, perm, (int)nnz, 0, bits, c->stream);
+      void *tmp = nullptr;
+      PA_CUDA(cudaMalloc(&tmp, tb ? tb : 1));
+      PA_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, m.d_colval, keys2, pos, perm, (int)nnz, 0, bits, c->stream));  // stable
+      k_gather_transposed<<<g, 256, 0, c->stream>>>(perm, rowidx, m.d_nzval, nnz, t.d_colval, t.d_nzval);
+      PA_CUDA(cudaStreamSynchronize(c->stream));
+      cudaFree(tmp); cudaFree(rowidx); cudaFree(pos); cudaFree(perm); cudaFree(keys2);
+      c->launches += 4;
+    }
+    size_t tb3 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb3, d_count, d_tp64, (int)(tn + 1), c->stream);
+    void *tmp3 = nullptr;
+    PA_CUDA(cudaMalloc(&tmp3, tb3 ? tb3 : 1));
+    PA_CUDA(cub::DeviceScan::ExclusiveSum(tmp3, tb3, d_count, d_tp64, (int)(tn + 1), c->stream));
+    k_narrow64<<<148, 256, 0, c->stream>>>(d_tp64, (int32_t *)t.d_rowptr, tn + 1);
+    PA_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(tmp3); cudaFree(d_count); cudaFree(d_tp64);
+    t.rows_per_cta = nnz <= 8 * tn ? 256 : (nnz <= 16 * tn ? 128 : (nnz <= 32 * tn ? 64 : 32));
+    t.set = true;
+  }
+  T->committed = true;
+  A->T = T;
+  return PA_OK;
+}
+
+__global__ void k_zero_tail(double *v, int64_t from, int64_t to) {
+  for (int64_t i = from + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < to; i += (int64_t)gridDim.x * blockDim.x) v[i] = 0.0;
+}
+
+/* mul!(c, transpose(A), b, alpha, beta): b on the row partition of A (own entries are read), c on the column partition
+ * of A (own entries updated, ghost entries are zero on return, like after assemble!). */
+extern "C" int pa_spmv_transpose(pa_mat *A, pa_vec *b, pa_vec *cvec, double alpha, double beta) {
+  PA_CHECK(A && b && cvec && A->committed, PA_ESTATE, "pa_spmv_transpose: matrix missing or not committed");
+  pa_ctx *c = A->ctx;
+  PA_CHECK(b->plan->ctx == c && cvec->plan->ctx == c && b->offset != cvec->offset, PA_EINVAL, "pa_spmv_transpose: bad operands");
+  for (int k = 0; k < c->nlocal; ++k) {
+    const PlanPart &rp = A->rows->parts[k], &cp = A->cols->parts[k], &bp = b->plan->parts[k], &yp = cvec->plan->parts[k];
+    PA_CHECK(bp.n_own == rp.n_own && bp.prefix, PA_EINVAL, "pa_spmv_transpose: b does not match axes(A,1) on part %d", c->part_ids[k] + 1);
+    PA_CHECK(yp.n_own == cp.n_own && yp.n_local == cp.n_local && yp.prefix, PA_EINVAL,
+             "pa_spmv_transpose: c does not match axes(A,2) (own and ghost ids) on part %d", c->part_ids[k] + 1);
+  }
+  PA_CUDA(cudaSetDevice(c->device));
+  PA_TRY(build_transpose(A));
+  PA_TRY(pa_before_write(c));
+  for (int k = 0; k < c->nlocal; ++k) {  // fill!(ghost_values(c), 0)
+    const PlanPart &yp = cvec->plan->parts[k];
+    if (!yp.n_ghost) continue;
+    k_zero_tail<<<(unsigned)std::min<int64_t>((yp.n_ghost + 255) / 256, 1184), 256, 0, c->stream>>>(cvec->d[k], yp.n_own, yp.n_local);
+    c->launches++;
+  }
+  PA_CUDA(cudaGetLastError());
+  // c_local = beta*c_local + alpha * A_local^T b_own (ghost rows start from zero)
+  PA_TRY(pa_spmv_local(A->T, b, cvec, alpha, beta, 0, nullptr, nullptr));
+  return pa_vec_assemble(cvec);
+}

@@ -138,6 +138,7 @@ struct pa_mat {
   pa_plan *rows = nullptr, *cols = nullptr;
   std::vector<MatPart> parts;
   bool committed = false;
+  pa_mat *T = nullptr;  // lazily built local transposes (transpose mul!)
 };
 
 // coefficient of a vector update: immediate, or sign * num/den read from device scalars (the CG

@@ -694,6 +694,10 @@ extern "C" int pa_mat_destroy(pa_mat *A) {
   cudaSetDevice(A->ctx->device);
   cudaStreamSynchronize(A->ctx->stream);
   for (auto &m : A->parts) free_part(m);
+  if (A->T) {
+    for (auto &m : A->T->parts) free_part(m);
+    delete A->T;
+  }
   delete A;
   return PA_OK;
 }

@@ -459,6 +459,12 @@ def mul_(c: PVector, A: PSparseMatrix, b: PVector, alpha: float = 1.0, beta: flo
     return c
 
 
+def mul_transpose_(c: PVector, A: PSparseMatrix, b: PVector, alpha: float = 1.0, beta: float = 0.0) -> PVector:
+    """mul!(c, transpose(A), b[, alpha, beta]) (src/p_sparse_matrix.jl:2144-2162); c lives on axes(A,2), b on axes(A,1)."""
+    check(_capi.lib().pa_spmv_transpose(A.h, b.h, c.h, float(alpha), float(beta)))
+    return c
+
+
 def mul_no_lat_(c: PVector, A: PSparseMatrix, b: PVector) -> PVector:
     """HPCG mul_no_lat! (HPCG/src/hpcg_utils.jl:6-17)."""
     return mul_(c, A, b)
