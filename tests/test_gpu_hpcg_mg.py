@@ -20,12 +20,15 @@ def _vec(pa, rows, vals):
     return pa.PVector(rows).set_local_values(vals)
 
 
+@pytest.mark.parametrize("lanes", [None, 0, 8, 16, 32])  # every variant of the sweep kernel (lanes per row; 0 = any row length)
 @pytest.mark.parametrize("npd,nloc,hint", [((2, 2, 1), (8, 6, 4), True), ((1, 2, 2), (4, 4, 6), False), ((1, 1, 1), (10, 9, 8), True)])
-def test_symmetric_gauss_seidel_is_bit_exact(pa, npd, nloc, hint):
+def test_symmetric_gauss_seidel_is_bit_exact(pa, npd, nloc, hint, lanes):
     """smooth! (smoothers.jl:98-125): wavefront sweeps == the reference's sequential per-part sweeps, bit for bit."""
     lev = hpcg_mg.Level(*nloc, npd)
     P = len(lev.part)
     b = pa.CUDAArray(P, arena_bytes=32 << 20)
+    if lanes is not None:
+        b.set_knob("gs_lanes", lanes)
     gn = tuple(a * c for a, c in zip(npd, nloc))
     A, rhs = pa.stencil_matrix(27, gn, npd, b)
     gs = pa.GaussSeidel(A, kind=27 if hint else None)  # hint=False exercises the generic (host) level schedule
