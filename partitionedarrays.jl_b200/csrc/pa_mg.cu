@@ -50,6 +50,8 @@ struct pa_mg {
   std::vector<std::vector<std::array<int64_t, 3>>> dims;  // [level][local part] local box dims
 };
 
+static int gs_default_lanes(pa_ctx *c, const GsPart &p);
+
 template <typename PtrT>
 struct GsArgs {
   const PtrT *rowptr;
@@ -90,6 +92,25 @@ __device__ __forceinline__ void gs_publish(ulonglong2 *slot, double *x, double s
   *x = s;  // the plain vector: read by later rows as an OLD value never, by the next kernels always
 }
 
+// The matrix is read once per sweep and is two orders of magnitude larger than x: marked evict-first in L2 so
+// that the L2 keeps x and the published values, which neighbouring rows (up to two grid planes apart in the
+// wavefront order) come back for.  Without the hint the 512^3 sweep misses L2 on most x gathers.
+__device__ __forceinline__ uint64_t gs_stream_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ double gs_ld_stream(const double *p, uint64_t pol) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int32_t gs_ld_stream(const int32_t *p, uint64_t pol) {
+  int32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
 // any row length: one warp per row, 32 entries per trip
 template <typename PtrT>
 __global__ void __launch_bounds__(GS_THREADS) k_gs_flow(const GsArgs<PtrT> a) {
@@ -97,6 +118,7 @@ __global__ void __launch_bounds__(GS_THREADS) k_gs_flow(const GsArgs<PtrT> a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t W = (int64_t)gridDim.x * (GS_THREADS / 32);
   const int64_t w = (int64_t)blockIdx.x * (GS_THREADS / 32) + warp;
+  const uint64_t pol = gs_stream_policy();
   for (int64_t pos = w; pos < a.npad; pos += W) {
     const int64_t row = a.backward ? a.rows[a.npad - 1 - pos] : a.rows[pos];
     if (row < 0) continue;
@@ -109,8 +131,8 @@ __global__ void __launch_bounds__(GS_THREADS) k_gs_flow(const GsArgs<PtrT> a) {
     for (int64_t p0 = ps; p0 < pe; p0 += 32) {
       const int64_t p = p0 + lane;
       const bool valid = p < pe;
-      const int32_t col = valid ? a.colval[p] : -1;
-      const double v = valid ? a.nzval[p] : 0.0;
+      const int32_t col = valid ? gs_ld_stream(a.colval + p, pol) : -1;
+      const double v = valid ? gs_ld_stream(a.nzval + p, pol) : 0.0;
       const bool use = valid && (!a.zero_guess || col < row);
       // NEW value needed: an own row that precedes this one in the sweep order
       const bool fresh = use && col < a.n && (a.backward ? col > row : col < row);
@@ -150,7 +172,9 @@ __global__ void __launch_bounds__(GS_THREADS, 6) k_gs_flow_pipe(const GsArgs<Ptr
   constexpr int NJ = 32 / G;   // entries per lane
   constexpr int RPW = 32 / G;  // rows per warp
   constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
-  __shared__ double prod[GS_THREADS / 32][RPW][32];
+  // +2: the leaders of a warp's rows read their products with 16-byte loads at the same time; 34 doubles apart
+  // they fall into different banks
+  __shared__ __align__(16) double prod[GS_THREADS / 32][RPW][34];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane / G, hl = lane % G;
   const int64_t W = (int64_t)gridDim.x * (GS_THREADS / 32) * RPW;
@@ -158,6 +182,7 @@ __global__ void __launch_bounds__(GS_THREADS, 6) k_gs_flow_pipe(const GsArgs<Ptr
   const int64_t np = a.npad;
   const int64_t niter = (np + W - 1) / W;
   const unsigned epoch = (unsigned)a.epoch;
+  const uint64_t pol = gs_stream_policy();
   auto row_at = [&](int64_t pos) -> int32_t { return pos < np ? a.rows[a.backward ? np - 1 - pos : pos] : -1; };
   auto extent = [&](int32_t r, int64_t &ps, int &cnt) {
     ps = 0;
@@ -178,8 +203,8 @@ __global__ void __launch_bounds__(GS_THREADS, 6) k_gs_flow_pipe(const GsArgs<Ptr
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
     const int k = hl + j * G;
-    colC[j] = k < cntC ? a.colval[psC + k] : -1;
-    vC[j] = k < cntC ? a.nzval[psC + k] : 0.0;
+    colC[j] = k < cntC ? gs_ld_stream(a.colval + psC + k, pol) : -1;
+    vC[j] = k < cntC ? gs_ld_stream(a.nzval + psC + k, pol) : 0.0;
   }
   if (hl == 0 && rC >= 0) {
     bC = a.b[rC];
@@ -196,8 +221,8 @@ __global__ void __launch_bounds__(GS_THREADS, 6) k_gs_flow_pipe(const GsArgs<Ptr
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int k = hl + j * G;
-      colB[j] = k < cntB ? a.colval[psB + k] : -1;
-      vB[j] = k < cntB ? a.nzval[psB + k] : 0.0;
+      colB[j] = k < cntB ? gs_ld_stream(a.colval + psB + k, pol) : -1;
+      vB[j] = k < cntB ? gs_ld_stream(a.nzval + psB + k, pol) : 0.0;
     }
     if (hl == 0 && rB >= 0) {
       bB = a.b[rB];
@@ -218,24 +243,27 @@ __global__ void __launch_bounds__(GS_THREADS, 6) k_gs_flow_pipe(const GsArgs<Ptr
 #pragma unroll
     for (int j = 0; j < NJ; ++j)
       if (fresh[j]) xv[j] = gs_wait_value(a.xe + colC[j], epoch, a.err);
-    unsigned usemask = 0;
     double d = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      prod[warp][sub][hl + j * G] = __dmul_rn(vC[j], xv[j]);
-      const unsigned ub = (__ballot_sync(0xffffffffu, use[j]) >> (sub * G)) & GM;
+      // unused entries contribute +0.0: s - (+0.0) == s bit for bit, so the leader's chain needs no predicates
+      prod[warp][sub][hl + j * G] = use[j] ? __dmul_rn(vC[j], xv[j]) : 0.0;
       const unsigned db = (__ballot_sync(0xffffffffu, colC[j] >= 0 && colC[j] == row) >> (sub * G)) & GM;
       const double dj = __shfl_sync(0xffffffffu, vC[j], db ? sub * G + __ffs(db) - 1 : lane);
       if (db) d = dj;
-      usemask |= ub << ((j * G) & 31);
     }
     __syncwarp();
     if (hl == 0 && row >= 0) {
       double s = bC;
+      const double2 *pp = reinterpret_cast<const double2 *>(&prod[warp][sub][0]);
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const double pk = prod[warp][sub][k];
-        if ((usemask >> k) & 1u) s = __dsub_rn(s, pk);  // s -= a*x[col], in CSR order
+      for (int k = 0; k < 14; ++k) {  // s -= a*x[col], in CSR order
+        const double2 pk = pp[k];
+        s = __dsub_rn(__dsub_rn(s, pk.x), pk.y);
+      }
+      if (cntC > 28) {
+        const double2 p14 = pp[14], p15 = pp[15];
+        s = __dsub_rn(__dsub_rn(__dsub_rn(__dsub_rn(s, p14.x), p14.y), p15.x), p15.y);
       }
       if (!a.zero_guess) s = __dadd_rn(s, __dmul_rn(d, xoC));  // s += d*x[row]
       s = __ddiv_rn(s, d);
@@ -372,15 +400,16 @@ extern "C" int pa_gs_commit(pa_gs *g) {
     p.maxlen = cnt[p.nlev];
     std::vector<int32_t> shift(p.nlev);
     int64_t at = 0, padded = 0;
+    const int64_t al = 4;
     for (int l = 0; l < p.nlev; ++l) {
-      padded = (padded + 3) & ~3ll;
+      padded = (padded + al - 1) & ~(al - 1);
       PA_CHECK(padded - at < (1ll << 31) && padded + cnt[l] < (1ll << 31), PA_EINVAL, "pa_gs_commit: too many rows");
       shift[l] = (int32_t)(padded - at);
       at += cnt[l];
       padded += cnt[l];
     }
     PA_CHECK(at == p.n, PA_ESTATE, "pa_gs_commit: level histogram does not add up");
-    p.npad = (padded + 3) & ~3ll;
+    p.npad = (padded + al - 1) & ~(al - 1);
     int32_t *d_shift = nullptr;
     PA_CUDA(cudaMalloc((void **)&d_shift, p.nlev * sizeof(int32_t)));
     PA_CUDA(cudaMemcpyAsync(d_shift, shift.data(), p.nlev * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
@@ -408,6 +437,14 @@ extern "C" int pa_gs_destroy(pa_gs *g) {
   return PA_OK;
 }
 
+// lanes per row: 16 (two rows per warp) once the levels are wide enough to be throughput bound, 32 where the
+// sweep is bound by the level-to-level hop; 0 = the unpipelined warp-per-row kernel (any row length).
+// Measured on B200 (27-pt, symmetric sweep): 16.8M rows 11.7 ms (16) vs 13.5 ms (32), 2.1M rows 5.0 vs 3.7 ms.
+// (One THREAD per row was tried for the widest levels and is 2.7x slower: 205 ms vs 75 ms at 134M rows.)
+static int gs_default_lanes(pa_ctx *c, const GsPart &p) {
+  return (int)pa_knob(c, "gs_lanes", p.n >= (4ll << 20) ? 16 : 32);
+}
+
 // one sweep over the own rows of every local part (ghost entries of x are inputs only)
 static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero_guess) {
   pa_ctx *c = g->A->ctx;
@@ -432,10 +469,7 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
       a.epoch = p.epoch;
       a.backward = backward;
       a.zero_guess = zero_guess;
-      // lanes per row: 16 (two rows per warp) pays once the levels are wide enough to be throughput bound,
-      // 32 where the sweep is bound by the level-to-level hop; 0 = the unpipelined kernel (any row length).
-      // Measured on B200 (27-pt, symmetric sweep): 16.8M rows 11.7 ms vs 13.5 ms, 2.1M rows 5.0 ms vs 3.7 ms.
-      int lanes = (int)pa_knob(c, "gs_lanes", p.n >= (4ll << 20) ? 16 : 32);
+      int lanes = gs_default_lanes(c, p);
       if (p.maxlen > 32) lanes = 0;
       void (*kern)(const GsArgs<PtrT>) = lanes == 8 ? k_gs_flow_pipe<PtrT, 8> : lanes == 16 ? k_gs_flow_pipe<PtrT, 16>
                                          : lanes == 32 ? k_gs_flow_pipe<PtrT, 32> : k_gs_flow<PtrT>;
