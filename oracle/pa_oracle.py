@@ -565,37 +565,17 @@ def split_format_locally(A: CSR, rows: LocalIndices, cols: LocalIndices) -> Tupl
     return oo, og
 
 
-def psparse(I, J, V, row_partition, col_partition, assembled: bool = False) -> PSparse:
+def psparse(I, J, V, row_partition, col_partition, assembled: bool = False, local_format: str = "csc") -> PSparse:
     """psparse (src/p_sparse_matrix.jl:1150-1286) restated at the semantic level.
 
-    assembled=False: triplets whose row is owned elsewhere are shipped to the row owner
-    (the ``assemble`` step, :1590-1756) — as the oracle sees every part it simply moves
-    them; ghost columns are discovered with find_owner + union_ghost (:1226-1236).
+    assembled=False: the reference's default, restated step by step in psparse_disassembled.
     assembled=True: every triplet already sits on its row owner (:1249-1270)."""
     nparts = len(row_partition)
     I = [np.asarray(i, dtype=np.int64) for i in I]
     J = [np.asarray(j, dtype=np.int64) for j in J]
     V = [np.asarray(v, dtype=np.float64) for v in V]
     if not assembled:
-        tab = global_to_owner_table(row_partition)
-        bins = [([], [], []) for _ in range(nparts)]
-        # own triplets first (in place), then received ones in neighbour(part) order
-        for p in range(nparts):
-            ok = (I[p] >= 1) & (J[p] >= 1)
-            own = ok & (tab[np.where(ok, I[p], 1)] == p + 1)
-            bins[p][0].append(I[p][own]); bins[p][1].append(J[p][own]); bins[p][2].append(V[p][own])
-        for p in range(nparts):
-            ok = (I[p] >= 1) & (J[p] >= 1)
-            o = tab[np.where(ok, I[p], 1)]
-            for q in range(nparts):
-                if q == p:
-                    continue
-                m = ok & (o == q + 1)
-                if m.any():
-                    bins[q][0].append(I[p][m]); bins[q][1].append(J[p][m]); bins[q][2].append(V[p][m])
-        I = [np.concatenate(b[0]) if b[0] else np.zeros(0, np.int64) for b in bins]
-        J = [np.concatenate(b[1]) if b[1] else np.zeros(0, np.int64) for b in bins]
-        V = [np.concatenate(b[2]) if b[2] else np.zeros(0, np.float64) for b in bins]
+        return psparse_disassembled(I, J, V, row_partition, col_partition, local_format)
     Jown = find_owner(col_partition, J)
     cols = [union_ghost(c, j, o) for c, j, o in zip(col_partition, J, Jown)]
     rows = row_partition
@@ -610,6 +590,123 @@ def psparse(I, J, V, row_partition, col_partition, assembled: bool = False) -> P
         a, b = split_format_locally(A, rows[p], cols[p])
         oo.append(a); og.append(b)
     return PSparse(rows, cols, local, oo, og, True)
+
+
+def _compress_coo(li, lj, V, m, n, fmt):
+    """compresscoo (src/sparse_utils.jl:313-350) seen as a list of stored entries: unique (i,j) in STORAGE order of
+    the local matrix type -- "csr": row-major (SparseMatrixCSR), "csc": column-major (SparseMatrixCSC, the default
+    of psparse) -- values of duplicates added in input order; triplets with an id < 1 become a stored (1,1,0.0)
+    (FilteredCooVector, :370-390)."""
+    li = np.asarray(li, dtype=np.int64).copy()
+    lj = np.asarray(lj, dtype=np.int64).copy()
+    V = np.asarray(V, dtype=np.float64).copy()
+    if m * n == 0:
+        li, lj, V = li[:0], lj[:0], V[:0]
+    bad = (li < 1) | (lj < 1)
+    li[bad], lj[bad], V[bad] = 1, 1, 0.0
+    order = np.lexsort((lj, li)) if fmt == "csr" else np.lexsort((li, lj))  # stable: ties stay in input order
+    li, lj, V = li[order], lj[order], V[order]
+    if len(li) == 0:
+        return li, lj, V
+    new = np.ones(len(li), dtype=bool)
+    new[1:] = (li[1:] != li[:-1]) | (lj[1:] != lj[:-1])
+    nz = np.zeros(int(new.sum()))
+    np.add.at(nz, np.cumsum(new) - 1, V)  # sequential, in order
+    return li[new], lj[new], nz
+
+
+def psparse_disassembled(I, J, V, row_partition, col_partition, local_format: str = "csc") -> PSparse:
+    """psparse(I,J,V,rows,cols) with its defaults (disassembled input, assemble=true, split_format=true), step by
+    step as the reference does it, because both the association of the sums and the numbering of the ghost columns
+    (hence the order of the terms of every row of the ghost block) follow from these steps:
+      1. src/p_sparse_matrix.jl:1186-1201  rows_sa/cols_sa = union_ghost(rows/cols, I/J, owners), local ids,
+         sub-assembled local matrix = compress(I,J,V) per part (duplicates of ONE part combined, in input order);
+      2. :1207-1209 (split_format, :823-899)  four blocks, entries kept in storage order;
+      3. :1600-1645 (setup_cache_snd)  entries in ghost rows, ghost_own block first then ghost_ghost, each in storage
+         order, bucketed by the owner of the row (neighbours = sorted ghost-row owners);
+      4. :1651-1684 (setup_own_triplets)  own_own list = findnz(own_own) ++ received entries with an own column,
+         own_ghost list = findnz(own_ghost) ++ the other received entries, received in neighbour (ascending part) order;
+      5. :1739 cols_fa = union_ghost(cols without ghosts, columns of the own_ghost list in that order);
+      6. :1700-1703 compresscoo of both lists: value = own sum, then + each sender's sum, in neighbour order.
+    local_format = storage of the local matrices: "csc" (SparseMatrixCSC, default) or "csr" (SparseMatrixCSR{1})."""
+    nparts = len(row_partition)
+    I = [np.asarray(i, dtype=np.int64) for i in I]
+    J = [np.asarray(j, dtype=np.int64) for j in J]
+    V = [np.asarray(v, dtype=np.float64) for v in V]
+    rows_sa = [union_ghost(r, i, o) for r, i, o in zip(row_partition, I, find_owner(row_partition, I))]
+    cols_sa = [union_ghost(c, j, o) for c, j, o in zip(col_partition, J, find_owner(col_partition, J))]
+    for r, c in zip(rows_sa, cols_sa):
+        assert r.own_is_prefix() and c.own_is_prefix(), "restated for own-first local orders"
+    nbr_snd, nbr_rcv = assembly_neighbors(rows_sa)
+    own_lists, outbox = [], []
+    for p in range(nparts):
+        r, c = rows_sa[p], cols_sa[p]
+        li = r.global_to_local(I[p]).astype(np.int64)
+        lj = c.global_to_local(J[p]).astype(np.int64)
+        li[I[p] < 1] = 0
+        lj[J[p] < 1] = 0
+        ei, ej, ev = _compress_coo(li, lj, V[p], r.n_local, c.n_local, local_format)  # storage order
+        gi, gj = r.local_to_global[ei - 1], c.local_to_global[ej - 1]
+        row_own, col_own = ei <= r.n_own, ej <= c.n_own
+        own_lists.append({"oo": (gi[row_own & col_own], gj[row_own & col_own], ev[row_own & col_own]),
+                          "og": (gi[row_own & ~col_own], gj[row_own & ~col_own], ev[row_own & ~col_own])})
+        # ghost rows: ghost_own block entries first, then ghost_ghost
+        sel = np.concatenate([np.nonzero(~row_own & col_own)[0], np.nonzero(~row_own & ~col_own)[0]])
+        owner = r.local_to_owner[ei[sel] - 1]
+        outbox.append({int(q): (gi[sel][owner == q], gj[sel][owner == q], ev[sel][owner == q]) for q in nbr_snd[p]})
+    cols_fa, oo, og, local = [], [], [], []
+    for p in range(nparts):
+        r, c = row_partition[p], col_partition[p]
+        rcv = [outbox[int(s) - 1][p + 1] for s in nbr_rcv[p]]
+        ri = np.concatenate([x[0] for x in rcv]) if rcv else np.zeros(0, np.int64)
+        rj = np.concatenate([x[1] for x in rcv]) if rcv else np.zeros(0, np.int64)
+        rv = np.concatenate([x[2] for x in rcv]) if rcv else np.zeros(0)
+        jown = c.global_to_local(rj) > 0 if len(rj) else np.zeros(0, dtype=bool)
+        a, b = own_lists[p]["oo"], own_lists[p]["og"]
+        oo_i, oo_j, oo_v = np.concatenate([a[0], ri[jown]]), np.concatenate([a[1], rj[jown]]), np.concatenate([a[2], rv[jown]])
+        og_i, og_j, og_v = np.concatenate([b[0], ri[~jown]]), np.concatenate([b[1], rj[~jown]]), np.concatenate([b[2], rv[~jown]])
+        c_own = LocalIndices(c.n_global, c.part, c.own_to_global, c.local_to_owner[c.own_to_local - 1],
+                             box=c.box, grid=c.grid, parts_per_dir=c.parts_per_dir)  # remove_ghost
+        cfa = union_ghost(c_own, og_j, find_owner(col_partition, [og_j])[0])
+        cols_fa.append(cfa)
+        n_own_r = r.n_own
+        row_own_id = lambda g: r.global_to_local(g).astype(np.int64)  # own-first: own id == local id
+        ei, ej, ev = _compress_coo(row_own_id(oo_i), c_own.global_to_local(oo_j).astype(np.int64), oo_v, n_own_r, c_own.n_own, "csr")
+        oo.append(_entries_to_csr(ei, ej, ev, n_own_r, c_own.n_own))
+        gid = cfa.global_to_local(og_j).astype(np.int64) - cfa.n_own if len(og_j) else np.zeros(0, np.int64)
+        ei, ej, ev = _compress_coo(row_own_id(og_i), gid, og_v, n_own_r, cfa.n_ghost, "csr")
+        og.append(_entries_to_csr(ei, ej, ev, n_own_r, cfa.n_ghost))
+        # unsplit view (own rows x local cols) for the callers that want one matrix
+        rows_of = lambda M: np.repeat(np.arange(1, M.m + 1), np.diff(M.rowptr.astype(np.int64)))
+        li = np.concatenate([rows_of(oo[-1]), rows_of(og[-1])])
+        lj = np.concatenate([oo[-1].colval.astype(np.int64), og[-1].colval.astype(np.int64) + cfa.n_own])
+        lv = np.concatenate([oo[-1].nzval, og[-1].nzval])
+        local.append(sparse_matrix_csr(li, lj, lv, n_own_r, cfa.n_local, skip=False))
+    return PSparse(list(row_partition), cols_fa, local, oo, og, True)  # rows_fa = rows (:1737)
+
+
+def _entries_to_csr(ei, ej, ev, m, n) -> CSR:
+    """row-major unique entries -> SparseMatrixCSR{1} arrays."""
+    counts = np.bincount(ei - 1, minlength=m) if len(ei) else np.zeros(m, dtype=np.int64)
+    rowptr = np.ones(m + 1, dtype=np.int64)
+    rowptr[1:] = 1 + np.cumsum(counts)
+    return CSR(m, n, rowptr.astype(np.int32), np.asarray(ej, dtype=np.int32), np.asarray(ev, dtype=np.float64))
+
+
+def pvector_disassembled(I, V, row_partition) -> List[np.ndarray]:
+    """pvector(I,V,rows) with its defaults (src/p_vector.jl:887-926 + assemble :1331-1347): rows_sa =
+    union_ghost(rows, I), dense_vector per part (a[i] += v in input order, ids < 1 skipped, :853-863), assemble!
+    (owner += each neighbour's contribution, in neighbour order), result on `rows` (own values only)."""
+    I = [np.asarray(i, dtype=np.int64) for i in I]
+    rows_sa = [union_ghost(r, i, o) for r, i, o in zip(row_partition, I, find_owner(row_partition, I))]
+    vals = []
+    for r, i, v in zip(rows_sa, I, V):
+        a = np.zeros(r.n_local)
+        ok = i >= 1
+        np.add.at(a, r.global_to_local(i[ok]).astype(np.int64) - 1, np.asarray(v, dtype=np.float64)[ok])
+        vals.append(a)
+    assemble(vals, rows_sa, assembly_plan(rows_sa))
+    return [own_values(a, r).copy() for a, r in zip(vals, rows_sa)]
 
 
 def own_values(v: np.ndarray, ind: LocalIndices) -> np.ndarray:

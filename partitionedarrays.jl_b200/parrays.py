@@ -516,27 +516,7 @@ def psparse(I: List, J: List, V: List, rows: PRange, cols: PRange, assembled: bo
     The COO->CSR compression runs on the host at setup time (on-device compression is 'next')."""
     b = rows.backend
     if not assembled:
-        # Disassembled input (the reference's default, src/p_sparse_matrix.jl:1186-1222 + assemble :1590-1756): triplets whose
-        # row is owned by another part are shipped to the row owner at setup time (host metadata exchange), the owner keeps
-        # its own triplets first and appends the received ones in sender order; ids < 1 are dropped.  The COO->CSR compression
-        # below then combines duplicates in that order (the reference combines per sender first: same sum, other association).
-        outgoing = []
-        for ind_r, i, j, v in zip(rows.indices, I, J, V):
-            i, j, v = np.asarray(i, dtype=np.int64), np.asarray(j, dtype=np.int64), np.asarray(v, dtype=np.float64)
-            ok = (i >= 1) & (j >= 1)
-            i, j, v = i[ok], j[ok], v[ok]
-            owner = _find_owner(rows, ind_r, i)
-            outgoing.append((ind_r.part, {int(q): (i[owner == q], j[owner == q], v[owner == q]) for q in np.unique(owner)}))
-        everyone = dict(b.gather_all(outgoing))
-        I2, J2, V2 = [], [], []
-        for ind_r in rows.indices:
-            me = ind_r.part
-            pieces = [everyone[me].get(me)] + [everyone[q].get(me) for q in sorted(everyone) if q != me]
-            pieces = [p for p in pieces if p is not None]
-            I2.append(np.concatenate([p[0] for p in pieces]) if pieces else np.zeros(0, np.int64))
-            J2.append(np.concatenate([p[1] for p in pieces]) if pieces else np.zeros(0, np.int64))
-            V2.append(np.concatenate([p[2] for p in pieces]) if pieces else np.zeros(0, np.float64))
-        I, J, V = I2, J2, V2
+        return _psparse_disassembled(I, J, V, rows, cols, split_format, local_format, compress)
     new_cols = []
     for ind_c, j in zip(cols.indices, J):
         j = np.asarray(j, dtype=np.int64)
@@ -589,6 +569,136 @@ def psparse(I: List, J: List, V: List, rows: PRange, cols: PRange, assembled: bo
         else:
             A.set_csr(k, rp2.astype(np.int32), cv2, nz2)
     return A.commit()
+
+
+def _stored_entries(li, lj, v, m, n, fmt):
+    """The stored entries of sparse_matrix(I,J,V,m,n) in the storage order of the local matrix type ("csc":
+    column-major, "csr": row-major): duplicates added in input order, ids < 1 -> a stored (1,1,0.0)."""
+    li, lj, v = li.copy(), lj.copy(), v.copy()
+    if m * n == 0:
+        li, lj, v = li[:0], lj[:0], v[:0]
+    bad = (li < 1) | (lj < 1)
+    li[bad], lj[bad], v[bad] = 1, 1, 0.0
+    order = np.lexsort((lj, li)) if fmt == "csr" else np.lexsort((li, lj))
+    li, lj, v = li[order], lj[order], v[order]
+    if len(li) == 0:
+        return li, lj, v
+    new = np.ones(len(li), dtype=bool)
+    new[1:] = (li[1:] != li[:-1]) | (lj[1:] != lj[:-1])
+    nz = np.zeros(int(np.count_nonzero(new)))
+    np.add.at(nz, np.cumsum(new) - 1, v)
+    return li[new], lj[new], nz
+
+
+def _psparse_disassembled(I, J, V, rows: PRange, cols: PRange, split_format: bool, local_format: str, compress: str) -> PSparseMatrix:
+    """Disassembled input, the reference's default (src/p_sparse_matrix.jl:1186-1222, then split_format :823-899 and
+    assemble :1590-1756), reproduced stage by stage because the stages fix both how the sums associate and how the ghost
+    columns are numbered (= the order of the terms in every row of the ghost block):
+      each part compresses ITS triplets first (duplicates in input order) into a sub-assembled local matrix over
+      rows_sa/cols_sa = union_ghost(rows/cols, I/J); the stored entries of its ghost rows -- ghost_own block, then
+      ghost_ghost block, each in storage order -- go to the row owners; an owner appends what it receives, sender by
+      sender in ascending part order, to the stored entries of its own rows (own_own / own_ghost lists), numbers the
+      ghost columns by first appearance in the own_ghost list and compresses again: own sum + sender sums in order.
+    This is setup-time index work on the host (the triplets travel through the metadata channel); the final compression
+    runs on the device with compress="device"."""
+    b = rows.backend
+    if local_format not in ("csr", "csc"):
+        raise ValueError("local_format must be 'csr' or 'csc'")
+    own_lists, outgoing = [], []
+    for ind_r, ind_c, i, j, v in zip(rows.indices, cols.indices, I, J, V):
+        i, j, v = np.asarray(i, dtype=np.int64), np.asarray(j, dtype=np.int64), np.asarray(v, dtype=np.float64)
+        rsa = pr.union_ghost(ind_r, i, _find_owner(rows, ind_r, i))
+        csa = pr.union_ghost(ind_c, j, _find_owner(cols, ind_c, j))
+        if not (rsa.own_is_prefix and csa.own_is_prefix):
+            raise ValueError("psparse(disassembled): needs own-first local orders")
+        li, lj = rsa.global_to_local(i).astype(np.int64), csa.global_to_local(j).astype(np.int64)
+        li[i < 1] = 0
+        lj[j < 1] = 0
+        ei, ej, ev = _stored_entries(li, lj, v, rsa.n_local, csa.n_local, local_format)
+        row_own, col_own = ei <= rsa.n_own, ej <= csa.n_own
+        gj_ghost = lambda m: csa.ghost_to_global[ej[m] - csa.n_own - 1]
+        m_oo, m_og = row_own & col_own, row_own & ~col_own
+        own_lists.append(((ei[m_oo], ej[m_oo], ev[m_oo]), (ei[m_og], gj_ghost(m_og), ev[m_og])))
+        sel = np.concatenate([np.nonzero(~row_own & col_own)[0], np.nonzero(~row_own & ~col_own)[0]])
+        gi = rsa.ghost_to_global[ei[sel] - rsa.n_own - 1]
+        gj = csa.local_to_global[ej[sel] - 1] if len(sel) else np.zeros(0, np.int64)
+        owner = rsa.ghost_to_owner[ei[sel] - rsa.n_own - 1]
+        outgoing.append((ind_r.part, {int(q): (gi[owner == q], gj[owner == q], ev[sel][owner == q]) for q in np.unique(owner)}))
+    everyone = dict(b.gather_all(outgoing))
+    new_cols, lists = [], []
+    for (oo, og), ind_r, ind_c in zip(own_lists, rows.indices, cols.indices):
+        me = ind_r.part
+        rcv = [everyone[q][me] for q in sorted(everyone) if q != me and me in everyone[q]]
+        ri = np.concatenate([x[0] for x in rcv]) if rcv else np.zeros(0, np.int64)
+        rj = np.concatenate([x[1] for x in rcv]) if rcv else np.zeros(0, np.int64)
+        rv = np.concatenate([x[2] for x in rcv]) if rcv else np.zeros(0)
+        rli = ind_r.global_to_local(ri).astype(np.int64)   # own-first: own id == local id
+        rlj = ind_c.global_to_local(rj).astype(np.int64)
+        if np.any(rli < 1) or np.any(rli > ind_r.n_own):
+            raise ValueError("psparse(disassembled): received a row this part does not own")
+        jown = (rlj >= 1) & (rlj <= ind_c.n_own)
+        oo_all = (np.concatenate([oo[0], rli[jown]]), np.concatenate([oo[1], rlj[jown]]), np.concatenate([oo[2], rv[jown]]))
+        og_i, og_gj, og_v = np.concatenate([og[0], rli[~jown]]), np.concatenate([og[1], rj[~jown]]), np.concatenate([og[2], rv[~jown]])
+        if ind_c.block is not None and ind_c.own_is_prefix:  # remove_ghost
+            c_own = pr.LocalIndices(ind_c.n_global, me, block=ind_c.block, n_own=ind_c.n_own)
+        else:
+            if not ind_c.own_is_prefix:
+                raise ValueError("psparse(disassembled): needs own-first local orders")
+            c_own = pr.LocalIndices(ind_c.n_global, me, ind_c.own_to_global, np.full(ind_c.n_own, me, dtype=np.int32))
+        cfa = pr.union_ghost(c_own, og_gj, _find_owner(cols, ind_c, og_gj))
+        new_cols.append(cfa)
+        og_all = (og_i, cfa.global_to_local(og_gj).astype(np.int64) - cfa.n_own, og_v)
+        lists.append((oo_all, og_all))
+    colr = PRange(b, new_cols)
+    A = PSparseMatrix(rows, colr)
+    for k, ((oo, og), ind_r, ind_c) in enumerate(zip(lists, rows.indices, colr.indices)):
+        if not ind_r.own_is_prefix:
+            raise ValueError("psparse(disassembled): needs own-first local orders")
+        no_r, no_c, ng_c = ind_r.n_own, ind_c.n_own, ind_c.n_ghost
+        if compress == "device":
+            A.set_coo(k, np.concatenate([oo[0], og[0]]), np.concatenate([oo[1], og[1] + no_c]), np.concatenate([oo[2], og[2]]))
+            continue
+        boo, bog = _coo_to_csr(*oo, no_r, no_c), _coo_to_csr(*og, no_r, ng_c)
+        if split_format:
+            if local_format == "csc":
+                A.set_csc_split(k, no_r, _csr_to_csc(*boo, no_c), _csr_to_csc(*bog, ng_c))
+            else:
+                A.set_csr_split(k, boo, bog)
+        else:
+            rid = lambda blk: np.repeat(np.arange(1, no_r + 1), np.diff(blk[0].astype(np.int64)))
+            rp, cv, nz = _coo_to_csr(np.concatenate([rid(boo), rid(bog)]),
+                                     np.concatenate([boo[1].astype(np.int64), bog[1].astype(np.int64) + no_c]),
+                                     np.concatenate([boo[2], bog[2]]), no_r, no_c + ng_c)
+            if local_format == "csc":
+                if ind_r.n_local != no_r:
+                    raise ValueError("unsplit CSC upload needs a ghost-free row partition")
+                A.set_csc(k, no_r, *_csr_to_csc(rp, cv, nz, no_c + ng_c))
+            else:
+                A.set_csr(k, rp, cv, nz)
+    return A.commit()
+
+
+def pvector_from_triplets(I: List, V: List, rows: PRange) -> PVector:
+    """pvector(I,V,rows) with its defaults (src/p_vector.jl:887-926): disassembled contributions in global ids;
+    rows_sa = union_ghost(rows, I), dense_vector per part (a[i] += v in input order, ids < 1 skipped, :853-863), then
+    assemble(a, rows) (:1331-1347): assemble! on the device (owners add their neighbours' contributions in neighbour
+    order), result on `rows`."""
+    b = rows.backend
+    sa, vals = [], []
+    for ind, i, v in zip(rows.indices, I, V):
+        i, v = np.asarray(i, dtype=np.int64), np.asarray(v, dtype=np.float64)
+        rsa = pr.union_ghost(ind, i, _find_owner(rows, ind, i))
+        a = np.zeros(rsa.n_local)
+        ok = i >= 1
+        np.add.at(a, rsa.global_to_local(i[ok]).astype(np.int64) - 1, v[ok])
+        sa.append(rsa)
+        vals.append(a)
+    w = PVector(PRange(b, sa)).set_local_values(vals)
+    w.assemble_()
+    out = PVector(rows)
+    out.copy_(w)  # w .= v2: own values (the layouts differ only in their ghosts)
+    w.free()
+    return out
 
 
 def _find_owner(cols: PRange, ind: pr.LocalIndices, gids: np.ndarray) -> np.ndarray:

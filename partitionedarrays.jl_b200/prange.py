@@ -166,9 +166,17 @@ class LocalIndices:
                 hit = sg[pos] == gids[rest]
                 out[np.nonzero(rest)[0][hit]] = self.n_own + order[pos[hit]] + 1
             return out.astype(np.int32)
-        if self._g2l is None:
-            self._g2l = {int(g): i + 1 for i, g in enumerate(self.local_to_global)}
-        return np.array([self._g2l.get(int(g), 0) for g in gids], dtype=np.int32)
+        if self._g2l is None:  # sorted table of the local gids (vectorised lookup: FEM-size id lists)
+            l2g = self.local_to_global
+            order = np.argsort(l2g, kind="stable")
+            self._g2l = (l2g[order], order)
+        sg, order = self._g2l
+        out = np.zeros(len(gids), dtype=np.int32)
+        if len(sg):
+            pos = np.clip(np.searchsorted(sg, gids), 0, len(sg) - 1)
+            hit = sg[pos] == gids
+            out[hit] = order[pos[hit]] + 1
+        return out
 
 
 def uniform_partition_part(rank: int, np_: Sequence[int], n: Sequence[int], ghost=None, periodic=None) -> LocalIndices:
