@@ -27,6 +27,17 @@ class Level:
     def __init__(self, nx, ny, nz, npd):
         self.n = (nx, ny, nz)
         self.A, self.r = o.hpcg_build_p_matrix(nx, ny, nz, *npd)
+        self._setup_local()
+
+    @classmethod
+    def from_psparse(cls, A):
+        """A smoother level for any assembled oracle PSparseMatrix (7-pt gallery operator, FEM stencil, ...)."""
+        self = cls.__new__(cls)
+        self.n, self.A, self.r = None, A, None
+        self._setup_local()
+        return self
+
+    def _setup_local(self):
         self.part = self.A.col_partition
         self.plan = o.assembly_plan(self.part)
         self.x = [np.zeros(i.n_local) for i in self.part]

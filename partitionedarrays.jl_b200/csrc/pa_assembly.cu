@@ -123,8 +123,8 @@ extern "C" int pa_mat_set_coo(pa_mat *A, int32_t k, int64_t n, int32_t idx_bits,
     PA_CUDA(cudaMemcpyAsync(&last, incl + n - 1, 4, cudaMemcpyDeviceToHost, c->stream));
     PA_CUDA(cudaStreamSynchronize(c->stream));
     nuniq = last;
-    PA_CUDA(cudaMalloc((void **)&m.d_colval, (nuniq + 16) * 4));
-    PA_CUDA(cudaMalloc((void **)&m.d_nzval, (nuniq + 16) * 8));
+    PA_CUDA(cudaMalloc((void **)&m.d_colval, (nuniq + PA_MAT_PAD) * 4));
+    PA_CUDA(cudaMalloc((void **)&m.d_nzval, (nuniq + PA_MAT_PAD) * 8));
     PA_CUDA(cudaMalloc((void **)&m.d_coo_seg, (nuniq + 1) * 4));
     k_coo_unique<<<g, 256, 0, c->stream>>>(key2, head, incl, n, m.d_colval, m.d_coo_seg, d_rowcount);
     k_coo_sum<<<g, 256, 0, c->stream>>>(dV, m.d_coo_perm, m.d_coo_valid, m.d_coo_seg, nuniq, n, m.d_nzval);
@@ -236,8 +236,8 @@ static int build_transpose(pa_mat *A) {
     PA_CUDA(cudaMalloc((void **)&d_count, (tn + 1) * 8));
     PA_CUDA(cudaMalloc((void **)&d_tp64, (tn + 1) * 8));
     PA_CUDA(cudaMemsetAsync(d_count, 0, (tn + 1) * 8, c->stream));
-    PA_CUDA(cudaMalloc((void **)&t.d_colval, (nnz + 16) * 4));
-    PA_CUDA(cudaMalloc((void **)&t.d_nzval, (nnz + 16) * 8));
+    PA_CUDA(cudaMalloc((void **)&t.d_colval, (nnz + PA_MAT_PAD) * 4));
+    PA_CUDA(cudaMalloc((void **)&t.d_nzval, (nnz + PA_MAT_PAD) * 8));
     PA_CUDA(cudaMalloc(&t.d_rowptr, (tn + 1) * 4));
     const int g = 148 * 8;
     if (nnz) {

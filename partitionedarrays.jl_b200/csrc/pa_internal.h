@@ -14,6 +14,8 @@
 #define PA_RED_BLOCKS 1184  // 148 SMs x 8 resident CTAs: grid of every BLAS-1 reduction
 #define PA_RED_THREADS 256
 #define PA_DOT_PARTS 4096  // >= persistent SpMV grid (SMs x resident CTAs)
+#define PA_MAT_PAD 48      // entries of tail padding behind colval/nzval: TMA copies are 16-byte granular, the batch
+                           // Gauss-Seidel kernel reads 32 entry slots per row without predicates
 
 void pa_set_error(const char *fmt, ...);
 int pa_cuda_fail(cudaError_t e, const char *what, const char *file, int line);

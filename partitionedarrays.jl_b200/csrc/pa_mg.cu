@@ -15,6 +15,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <cstdio>
 #include <array>
 
 #include "pa_internal.h"
@@ -26,11 +27,19 @@ struct GsPart {
   int64_t n = 0;
   int nlev = 0;
   int32_t *d_rows = nullptr;  // own rows sorted by wavefront level (ascending); every level starts at a multiple
-                              // of 4 (-1 = padding) so that the rows a warp takes together never depend on each other
-  int64_t npad = 0;           // length of d_rows (multiple of 4)
+                              // of 8 (-1 = padding) so that the rows a warp takes together never depend on each other
+  int64_t npad = 0;           // length of d_rows (multiple of 8)
   int maxlen = 0;             // longest stored row
   ulonglong2 *d_xe = nullptr; // [n] value of the row's last update + the sweep epoch it happened in (gs_publish)
   int epoch = 0;
+  // batch kernel (k_gs_level): the same order with every level padded to a multiple of GSB_ROWS (one CTA batch),
+  // level of every batch, batches per level, per-level completion counters
+  int32_t *d_rows_b = nullptr;
+  int64_t npad_b = 0;
+  int32_t *d_batch_lev = nullptr;
+  uint32_t *d_lev_nb = nullptr;
+  unsigned long long *d_done = nullptr;
+  unsigned long long sweeps = 0;  // batch sweeps run so far (the counters are never reset)
   bool geom = false;
   int64_t dims[3] = {0, 0, 0}, w[3] = {0, 0, 0};
 };
@@ -63,7 +72,7 @@ struct GsArgs {
   ulonglong2 *xe;
   int *err;
   int64_t n, npad;
-  int epoch, backward, zero_guess;
+  int epoch, backward, zero_guess, prefetch;
 };
 
 // Publishing a row: the new value travels WITH its "done in this sweep" mark, so a waiting reader needs one
@@ -168,7 +177,7 @@ __global__ void __launch_bounds__(GS_THREADS) k_gs_flow(const GsArgs<PtrT> a) {
 // (x_old and the entries can be fetched early: nobody writes x[row] before this row does, and a row's
 // coefficients are constant.)  Same arithmetic, same order as k_gs_flow.
 template <typename PtrT, int G>
-__global__ void __launch_bounds__(GS_THREADS, 6) k_gs_flow_pipe(const GsArgs<PtrT> a) {
+__global__ void __launch_bounds__(GS_THREADS, (G >= 16 ? 6 : (G == 8 ? 3 : 2))) k_gs_flow_pipe(const GsArgs<PtrT> a) {
   constexpr int NJ = 32 / G;   // entries per lane
   constexpr int RPW = 32 / G;  // rows per warp
   constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
@@ -282,6 +291,249 @@ __global__ void __launch_bounds__(GS_THREADS, 6) k_gs_flow_pipe(const GsArgs<Ptr
   }
 }
 
+// ------------------------------------------------------------------ the batch sweep kernel (rows of <= 32 entries)
+// An alternative schedule of the same sweep, selected with the knob gs_kernel=1 (NOT the default: see the numbers
+// below).  k_gs_flow_pipe spends ~300 issue slots per row (the ordered subtraction runs on one lane of a warp that
+// holds a few rows).  Here a CTA takes a BATCH of GSB_ROWS = 256 rows of one wavefront level, 32 per warp (the batch
+// list pads every level to a multiple of 256, so the rows of a batch never depend on each other), and the
+// dependency is tracked per LEVEL instead of per row: a batch of level L gathers its NEW x values when the counter
+// of level L-1 (L+1 in the backward sweep) says that all batches of that level have stored their rows -- which, by
+// induction, covers every earlier level.  One thread per CTA polls the counter and releases (fence + increment)
+// after the CTA barrier.  Per batch and warp:
+//   before the gate  the 32 rows' entries are streamed from the matrix into registers, 8 lanes per row and 4 rows
+//                    per step (coalesced 64-byte pieces of nzval / 32-byte pieces of colval), and the OLD x values
+//                    (rows of later levels, ghosts) are requested;
+//   behind the gate  the NEW x values are gathered (simply what x holds now: rows of later levels have not started),
+//                    the products are parked in shared memory, one line per row, and every lane walks ITS OWN row's
+//                    line: s = b - p0 - p1 - ... in CSR order, + d*x_old, / d, store; CTA barrier, release.
+// The ordered chain costs 2-3 issue slots per row instead of ~80 and the whole sweep ~25 per row; arithmetic and
+// order per row are those of k_gs_flow (bit-identical results, tests/test_gpu_hpcg_mg.py).
+// Measured on B200 (27-pt, symmetric sweep, 512^3 / 256^3 / 128^3 / 64^3 rows; the dataflow kernel: 60 / 11 / 2.2 /
+// 0.9 ms):  this kernel 88 / 16 / 7.2 / 3.3 ms; with the OLD values gathered behind the gate too 70 / 16 / 7.4 / 3.5;
+// one warp per 32-row batch with per-level counters 93 / 33 / 12 / 4.5; with per-row (value, epoch) pairs 106 / 45 /
+// 20 / 9.  Phase clocks of one CTA (gs_trace knob): gate >= 2000 cycles, NEW gather 1250 + products 1650 (LSU
+// wavefronts and 32-byte sectors for 8-byte values), chain 900, barrier + fence + increment 1450: one level costs
+// ~3 us however few rows it has, and 3578 levels x 1.5 rounds (148 batch slots, levels of up to 256 batches) add up
+// to more than the per-row dataflow needs, whose hop is ~1 us because only the LAST missing value of a row sits on
+// the critical path.
+#define GSB_THREADS 256
+#define GSB_ROWS 256
+#define GSB_WARP_DOUBLES(nj) (32 * (8 * (nj) + 2) + 32)  // shared memory per warp, in doubles
+
+template <typename PtrT>
+struct GsLevelArgs {
+  GsArgs<PtrT> g;                   // rows/npad = the batch list
+  const int32_t *batch_lev;         // [npad/GSB_ROWS] wavefront level of every batch
+  const uint32_t *lev_nb;           // [nlev] batches per level
+  unsigned long long *done;         // [nlev] batches finished, summed over all batch sweeps so far
+  unsigned long long sweep;         // 1-based count of batch sweeps on this part (target = sweep * lev_nb)
+  int nlev;
+  int trace;                        // > 0: CTA trace-1 prints its phase clocks (debugging aid)
+  int sync_mode;                    // 0 = release + acquire fences; 1 / 2 = timing experiments only (drop the acquire / both fences)
+};
+
+__device__ __forceinline__ double gs_ld_old(const double *p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void gs_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ unsigned long long gs_ld_relaxed(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void gs_fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// Polling is a relaxed load (an acquire load costs an L1 invalidation per poll); the acquire fence follows once.
+__device__ __noinline__ void gs_wait_level(const unsigned long long *cnt, unsigned long long target, int *err) {
+  long long t0 = 0;
+  while (gs_ld_relaxed(cnt) < target) {
+    if (!t0) {
+      t0 = clock64();
+    } else if (clock64() - t0 > GS_SPIN_LIMIT) {
+      *err = 3;
+      break;
+    }
+  }
+}
+
+template <typename PtrT, int NJ, bool BACKWARD, bool ZERO>
+__global__ void __launch_bounds__(GSB_THREADS, 1) k_gs_level(const GsLevelArgs<PtrT> la) {
+  const GsArgs<PtrT> &a = la.g;
+  constexpr int KMAX = 8 * NJ;      // entry slots per row
+  constexpr int STRIDE = KMAX + 2;  // doubles per row line: 16-byte aligned and conflict-free for the 16-byte chain reads
+  constexpr int NT = 8;             // steps per warp and batch (4 rows each)
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(16) double gsw_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *prod = gsw_smem + (size_t)warp * GSB_WARP_DOUBLES(NJ);  // [32][STRIDE] products of the warp's rows
+  double *dg = prod + 32 * STRIDE;                              // [32] their diagonal coefficients
+  const int sub = lane >> 3, hl = lane & 7;
+  const int64_t nb = a.npad / GSB_ROWS;
+  const int64_t W = gridDim.x;
+  const uint64_t pol = gs_stream_policy();
+
+  // batch bt of the sweep = batch bt of the list (forward) or nb-1-bt (backward: the list is walked from its end)
+  auto row_at = [&](int64_t bt) -> int32_t {  // this thread's row of batch bt (-1 = padding or past the end)
+    if (bt >= nb) return -1;
+    const int64_t lb = BACKWARD ? nb - 1 - bt : bt;
+    return a.rows[lb * GSB_ROWS + threadIdx.x];
+  };
+  auto meta = [&](int32_t r, int64_t &ps, int &cnt, double &bv, double &xo) {
+    ps = 0; cnt = 0; bv = 0.0; xo = 0.0;
+    if (r >= 0) {
+      ps = (int64_t)a.rowptr[r];
+      cnt = (int)((int64_t)a.rowptr[r + 1] - ps);
+      bv = a.b[r];
+      if (!ZERO) xo = gs_ld_old(a.x + r);  // nobody writes x[row] before this row does
+    }
+  };
+  auto prefetch = [&](int64_t ps, int cnt) {
+    if (a.prefetch && cnt > 0) {
+      const double *vp = a.nzval + ps;
+      const int32_t *cp = a.colval + ps;
+      gs_prefetch_l2(vp);
+      gs_prefetch_l2(cp);
+      if (cnt > 16) gs_prefetch_l2(vp + 16);
+      gs_prefetch_l2(vp + cnt - 1);
+      gs_prefetch_l2(cp + cnt - 1);
+    }
+  };
+
+  dg[lane] = 0.0;
+  const int64_t first = blockIdx.x;
+  int32_t r0 = row_at(first), r1 = row_at(first + W), r2 = row_at(first + 2 * W);
+  int64_t ps0, ps1;
+  int cnt0, cnt1;
+  double b0, b1, xo0, xo1;
+  meta(r0, ps0, cnt0, b0, xo0);
+  meta(r1, ps1, cnt1, b1, xo1);
+  __syncwarp();
+  for (int64_t bt = first; bt < nb; bt += W) {
+    // ---- keep the next batches in flight
+    const int32_t r3 = row_at(bt + 3 * W);
+    int64_t ps2;
+    int cnt2;
+    double b2, xo2;
+    meta(r2, ps2, cnt2, b2, xo2);
+    prefetch(ps1, cnt1);
+    const int lev = la.batch_lev[BACKWARD ? nb - 1 - bt : bt];
+    const int glev = BACKWARD ? lev + 1 : lev - 1;  // the level whose completion opens this one
+    const bool tr = la.trace > 0 && (int)blockIdx.x == la.trace - 1 && threadIdx.x == 0;
+    long long tk[7];
+    if (tr) tk[0] = clock64();
+    // ---- before the gate: the batch's matrix entries, 4 rows per step, and everything that does not depend on the
+    // previous level: the OLD x values (rows of later levels, ghosts) are requested here, so that only the NEW
+    // values are gathered on the critical path behind the gate
+    const int kend = (__reduce_max_sync(FULL, cnt0) + 1) & ~1;  // chain length of the warp's rows (even)
+    int32_t rowT[NT], code[NT][NJ];
+    double v[NT][NJ], xv[NT][NJ];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {  // the rows' extents travel by shuffle
+      const int rr = t * 4 + sub;
+      rowT[t] = __shfl_sync(FULL, r0, rr);
+      const int cntT = __shfl_sync(FULL, cnt0, rr);
+      const int64_t psT = __shfl_sync(FULL, ps0, rr);
+      const int32_t *cp = a.colval + (psT + hl);  // this lane's first entry of the row; the others are 8, 16, 24 further
+      const double *vp = a.nzval + (psT + hl);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        // no predicate: slots past the row end read the entries behind it (PA_MAT_PAD entries of padding follow the
+        // last row) and are discarded below.  (A predicated load makes ptxas put a select right behind the load,
+        // which waits for it.)
+        const int32_t c = gs_ld_stream(cp + 8 * j, pol);
+        v[t][j] = gs_ld_stream(vp + 8 * j, pol);
+        code[t][j] = hl + 8 * j < cntT ? c : -1;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int32_t c = code[t][j], row = rowT[t];
+        const bool valid = c >= 0;
+        // NEW value needed: an own row that precedes this one in the sweep order
+        const bool isnew = valid && (BACKWARD ? (c > row && c < (int32_t)a.n) : (c < row));
+        // slot code: >= 0 column of a NEW value, -1 unused, -2 OLD value, -3 OLD value + diagonal, -4 diagonal of the
+        // zero-guess sweep (not subtracted)
+        int32_t cd;
+        if (!valid) cd = -1;
+        else if (isnew) cd = c;
+        else if (ZERO) cd = c == row ? -4 : -1;
+        else cd = c == row ? -3 : -2;
+        xv[t][j] = gs_ld_old(a.x + (cd == -2 || cd == -3 ? c : 0));  // slots without an OLD value read x[0]: harmless
+        code[t][j] = cd;
+      }
+    }
+    if (tr) tk[1] = clock64();
+    // ---- the gate
+    if (glev >= 0 && glev < la.nlev) {
+      if (threadIdx.x == 0) {
+        gs_wait_level(la.done + glev, la.sweep * (unsigned long long)la.lev_nb[glev], a.err);
+        if (la.sync_mode == 0) gs_fence_acq_rel();  // acquire: relaxed poll + fence; the barrier extends it to the CTA
+      }
+      __syncthreads();
+    }
+    if (tr) tk[2] = clock64();
+    // ---- behind the gate: the NEW values (what x holds now: rows of later levels have not started), then the products
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        if (code[t][j] >= 0) xv[t][j] = gs_ld_old(a.x + code[t][j]);  // through L2: x changes during the sweep
+    }
+    if (tr) tk[3] = clock64();
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int rr = t * 4 + sub;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int32_t cd = code[t][j];
+        // unused entries contribute +0.0: s - (+0.0) == s bit for bit
+        prod[rr * STRIDE + hl + 8 * j] = (cd >= 0 || cd == -2 || cd == -3) ? __dmul_rn(v[t][j], xv[t][j]) : 0.0;
+        if (cd == -3 || cd == -4) dg[rr] = v[t][j];
+      }
+    }
+    __syncwarp();
+    if (tr) tk[4] = clock64();
+    // ---- every lane finishes its own row
+    {
+      double s = b0;
+      const double2 *pp = reinterpret_cast<const double2 *>(prod + lane * STRIDE);
+#pragma unroll 4
+      for (int k = 0; k < kend; k += 2) {  // s -= a*x[col], in CSR order
+        const double2 pk = pp[k >> 1];
+        s = __dsub_rn(__dsub_rn(s, pk.x), pk.y);
+      }
+      const double d = dg[lane];
+      dg[lane] = 0.0;
+      if (!ZERO) s = __dadd_rn(s, __dmul_rn(d, xo0));  // s += d*x[row]
+      s = __ddiv_rn(s, d);
+      if (r0 >= 0) a.x[r0] = s;
+    }
+    // ---- publish: CTA barrier, then one thread releases (fence + relaxed increment): the release is cumulative over
+    // the stores the barrier ordered before it.  (__threadfence() by every thread = MEMBAR.SC + L1 invalidation in
+    // all 8 warps was measured at ~3 us per level.)
+    if (tr) tk[5] = clock64();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (la.sync_mode <= 1) gs_fence_acq_rel();
+      asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(la.done + lev) : "memory");
+    }
+    if (tr) {
+      tk[6] = clock64();
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      printf("gs-trace bt %lld lev %d: loads-issued %lld gate %lld xloads-issued %lld products %lld chain %lld publish %lld | globaltimer %llu\n",
+             (long long)bt, lev, tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], gt);
+    }
+    // ---- rotate the pipeline
+    r0 = r1; ps0 = ps1; cnt0 = cnt1; b0 = b1; xo0 = xo1;
+    r1 = r2; ps1 = ps2; cnt1 = cnt2; b1 = b2; xo1 = xo2;
+    r2 = r3;
+  }
+}
+
 __global__ void k_level_hist(const int32_t *lev, int64_t n, int *count) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) atomicAdd(count + lev[i], 1);
 }
@@ -312,6 +564,10 @@ __global__ void k_iota(int32_t *rows, int64_t n) {
 static void gs_free_part(GsPart &g) {
   cudaFree(g.d_rows);
   cudaFree(g.d_xe);
+  cudaFree(g.d_rows_b);
+  cudaFree(g.d_batch_lev);
+  cudaFree(g.d_lev_nb);
+  cudaFree(g.d_done);
   g = GsPart();
 }
 
@@ -387,7 +643,7 @@ extern "C" int pa_gs_commit(pa_gs *g) {
     void *d_tmp = nullptr;
     PA_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
     PA_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_lev, d_lev2, d_rows0, d_rows1, (int)p.n, 0, bits, c->stream));
-    // start every level at a multiple of 4 in the order (see GsPart::d_rows)
+    // level histogram and the longest row
     int *d_cnt = nullptr;
     PA_CUDA(cudaMalloc((void **)&d_cnt, (p.nlev + 1) * sizeof(int)));
     PA_CUDA(cudaMemsetAsync(d_cnt, 0, (p.nlev + 1) * sizeof(int), c->stream));
@@ -398,28 +654,57 @@ extern "C" int pa_gs_commit(pa_gs *g) {
     PA_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, (p.nlev + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     PA_CUDA(cudaStreamSynchronize(c->stream));
     p.maxlen = cnt[p.nlev];
-    std::vector<int32_t> shift(p.nlev);
-    int64_t at = 0, padded = 0;
-    const int64_t al = 4;
-    for (int l = 0; l < p.nlev; ++l) {
-      padded = (padded + al - 1) & ~(al - 1);
-      PA_CHECK(padded - at < (1ll << 31) && padded + cnt[l] < (1ll << 31), PA_EINVAL, "pa_gs_commit: too many rows");
-      shift[l] = (int32_t)(padded - at);
-      at += cnt[l];
-      padded += cnt[l];
+    // the level-sorted row list with every level starting at a multiple of `al` (-1 = padding)
+    auto padded_list = [&](int64_t al, int32_t **d_list, int64_t *npad) -> int {
+      std::vector<int32_t> shift(p.nlev);
+      int64_t at = 0, padded = 0;
+      for (int l = 0; l < p.nlev; ++l) {
+        padded = (padded + al - 1) / al * al;
+        PA_CHECK(padded - at < (1ll << 31) && padded + cnt[l] < (1ll << 31), PA_EINVAL, "pa_gs_commit: too many rows");
+        shift[l] = (int32_t)(padded - at);
+        at += cnt[l];
+        padded += cnt[l];
+      }
+      PA_CHECK(at == p.n, PA_ESTATE, "pa_gs_commit: level histogram does not add up");
+      *npad = (padded + al - 1) / al * al;
+      int32_t *d_shift = nullptr;
+      PA_CUDA(cudaMalloc((void **)&d_shift, p.nlev * sizeof(int32_t)));
+      PA_CUDA(cudaMemcpyAsync(d_shift, shift.data(), p.nlev * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+      PA_CUDA(cudaMalloc((void **)d_list, *npad * sizeof(int32_t)));
+      PA_CUDA(cudaMemsetAsync(*d_list, 0xff, *npad * sizeof(int32_t), c->stream));
+      k_pad_levels<<<148 * 8, 256, 0, c->stream>>>(d_lev2, d_rows1, d_shift, p.n, *d_list);
+      PA_CUDA(cudaStreamSynchronize(c->stream));
+      cudaFree(d_shift);
+      return PA_OK;
+    };
+    PA_TRY(padded_list(8, &p.d_rows, &p.npad));
+    // batch kernel tables (only when that kernel is selected: it is not the default): level l occupies
+    // ceil(cnt_l / GSB_ROWS) consecutive batches
+    if (p.maxlen <= 32 && m.nnz > 0 && pa_knob(c, "gs_kernel", 0) == 1) {
+      const int64_t al = GSB_ROWS;
+      PA_TRY(padded_list(al, &p.d_rows_b, &p.npad_b));
+      std::vector<int32_t> batch_lev((size_t)(p.npad_b / al));
+      std::vector<uint32_t> lev_nb(p.nlev);
+      size_t bt = 0;
+      for (int l = 0; l < p.nlev; ++l) {
+        lev_nb[l] = (uint32_t)((cnt[l] + al - 1) / al);
+        PA_CHECK(lev_nb[l] > 0, PA_ESTATE, "pa_gs_commit: empty wavefront level %d", l);
+        for (uint32_t q = 0; q < lev_nb[l]; ++q) batch_lev[bt++] = l;
+      }
+      PA_CHECK(bt == batch_lev.size(), PA_ESTATE, "pa_gs_commit: batch table does not add up");
+      PA_CUDA(cudaMalloc((void **)&p.d_batch_lev, batch_lev.size() * sizeof(int32_t)));
+      PA_CUDA(cudaMalloc((void **)&p.d_lev_nb, lev_nb.size() * sizeof(uint32_t)));
+      PA_CUDA(cudaMalloc((void **)&p.d_done, (size_t)p.nlev * sizeof(unsigned long long)));
+      PA_CUDA(cudaMemcpyAsync(p.d_batch_lev, batch_lev.data(), batch_lev.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+      PA_CUDA(cudaMemcpyAsync(p.d_lev_nb, lev_nb.data(), lev_nb.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+      PA_CUDA(cudaMemsetAsync(p.d_done, 0, (size_t)p.nlev * sizeof(unsigned long long), c->stream));
+      PA_CUDA(cudaStreamSynchronize(c->stream));
+      p.sweeps = 0;
     }
-    PA_CHECK(at == p.n, PA_ESTATE, "pa_gs_commit: level histogram does not add up");
-    p.npad = (padded + al - 1) & ~(al - 1);
-    int32_t *d_shift = nullptr;
-    PA_CUDA(cudaMalloc((void **)&d_shift, p.nlev * sizeof(int32_t)));
-    PA_CUDA(cudaMemcpyAsync(d_shift, shift.data(), p.nlev * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    PA_CUDA(cudaMalloc((void **)&p.d_rows, p.npad * sizeof(int32_t)));
-    PA_CUDA(cudaMemsetAsync(p.d_rows, 0xff, p.npad * sizeof(int32_t), c->stream));
-    k_pad_levels<<<148 * 8, 256, 0, c->stream>>>(d_lev2, d_rows1, d_shift, p.n, p.d_rows);
     PA_CUDA(cudaMalloc((void **)&p.d_xe, p.n * sizeof(ulonglong2)));
     PA_CUDA(cudaMemsetAsync(p.d_xe, 0, p.n * sizeof(ulonglong2), c->stream));
     PA_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(d_tmp); cudaFree(d_lev); cudaFree(d_lev2); cudaFree(d_rows0); cudaFree(d_rows1); cudaFree(d_cnt); cudaFree(d_shift);
+    cudaFree(d_tmp); cudaFree(d_lev); cudaFree(d_lev2); cudaFree(d_rows0); cudaFree(d_rows1); cudaFree(d_cnt);
     p.epoch = 0;
     c->launches += 5;
   }
@@ -437,12 +722,17 @@ extern "C" int pa_gs_destroy(pa_gs *g) {
   return PA_OK;
 }
 
-// lanes per row: 16 (two rows per warp) once the levels are wide enough to be throughput bound, 32 where the
-// sweep is bound by the level-to-level hop; 0 = the unpipelined warp-per-row kernel (any row length).
-// Measured on B200 (27-pt, symmetric sweep): 16.8M rows 11.7 ms (16) vs 13.5 ms (32), 2.1M rows 5.0 vs 3.7 ms.
+// lanes per row of the dataflow kernel: 8 (four rows per warp) on the widest grids, 16 (two rows per warp) once the
+// levels are wide enough to be throughput bound, 32 where the sweep is bound by the level-to-level hop; 0 = the
+// unpipelined warp-per-row kernel (any row length).
+// Measured on B200 (27-pt, symmetric sweep, ms):   rows      4 lanes   8 lanes   16 lanes   32 lanes
+//                                                  134.2M     73.6      60.1      73.3        -
+//                                                   16.8M     21.8      12.5      11.3       13.5
+//                                                    2.1M     10.4       5.8       5.0        2.2 (3.7 before the pipeline)
+//                                                    262k      5.0       2.7        -         0.9
 // (One THREAD per row was tried for the widest levels and is 2.7x slower: 205 ms vs 75 ms at 134M rows.)
 static int gs_default_lanes(pa_ctx *c, const GsPart &p) {
-  return (int)pa_knob(c, "gs_lanes", p.n >= (4ll << 20) ? 16 : 32);
+  return (int)pa_knob(c, "gs_lanes", p.n >= (64ll << 20) ? 8 : (p.n >= (4ll << 20) ? 16 : 32));
 }
 
 // one sweep over the own rows of every local part (ghost entries of x are inputs only)
@@ -469,16 +759,52 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
       a.epoch = p.epoch;
       a.backward = backward;
       a.zero_guess = zero_guess;
+      a.prefetch = (int)pa_knob(c, "gs_prefetch", 1);
+      int nsm = 148;
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+      // batch kernel (32 rows of one level per warp) where the levels are wide; the warp-per-row dataflow kernel where
+      // the sweep is bound by the level-to-level hop (coarse grids) or rows are longer than 32 entries
+      if (p.d_rows_b && pa_knob(c, "gs_kernel", 0) == 1) {
+        const int nj = p.maxlen <= 8 ? 1 : (p.maxlen <= 16 ? 2 : 4);
+        void (*wk)(const GsLevelArgs<PtrT>) = nullptr;
+        PA_CHECK(!(zero_guess && backward), PA_ESTATE, "gs_sweep: the zero-guess sweep is a forward sweep");
+        if (zero_guess)
+          wk = nj == 1 ? k_gs_level<PtrT, 1, false, true> : nj == 2 ? k_gs_level<PtrT, 2, false, true> : k_gs_level<PtrT, 4, false, true>;
+        else if (!backward)
+          wk = nj == 1 ? k_gs_level<PtrT, 1, false, false> : nj == 2 ? k_gs_level<PtrT, 2, false, false> : k_gs_level<PtrT, 4, false, false>;
+        else
+          wk = nj == 1 ? k_gs_level<PtrT, 1, true, false> : nj == 2 ? k_gs_level<PtrT, 2, true, false> : k_gs_level<PtrT, 4, true, false>;
+        GsLevelArgs<PtrT> la;
+        la.g = a;
+        la.g.rows = p.d_rows_b;
+        la.g.npad = p.npad_b;
+        la.batch_lev = p.d_batch_lev;
+        la.lev_nb = p.d_lev_nb;
+        la.done = p.d_done;
+        la.sweep = ++p.sweeps;
+        la.nlev = p.nlev;
+        la.sync_mode = (int)pa_knob(c, "gs_sync", 0);
+        la.trace = (int)pa_knob(c, "gs_trace", 0);
+        const size_t smem = (size_t)(GSB_THREADS / 32) * GSB_WARP_DOUBLES(nj) * sizeof(double);
+        PA_CUDA(cudaFuncSetAttribute(wk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wk, GSB_THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
+        const int64_t cap = pa_knob(c, "gs_ctas", 0);
+        if (cap > 0 && cap < per_sm) per_sm = (int)cap;
+        // all CTAs co-resident: a waiting batch only waits for batches held by running CTAs
+        const int64_t grid = std::min<int64_t>(p.npad_b / GSB_ROWS, (int64_t)nsm * per_sm);
+        wk<<<(unsigned)grid, GSB_THREADS, smem, c->stream>>>(la);
+        return PA_OK;
+      }
       int lanes = gs_default_lanes(c, p);
       if (p.maxlen > 32) lanes = 0;
-      void (*kern)(const GsArgs<PtrT>) = lanes == 8 ? k_gs_flow_pipe<PtrT, 8> : lanes == 16 ? k_gs_flow_pipe<PtrT, 16>
-                                         : lanes == 32 ? k_gs_flow_pipe<PtrT, 32> : k_gs_flow<PtrT>;
-      const int rpw = lanes == 8 ? 4 : lanes == 16 ? 2 : 1;
+      void (*kern)(const GsArgs<PtrT>) = lanes == 4 ? k_gs_flow_pipe<PtrT, 4> : lanes == 8 ? k_gs_flow_pipe<PtrT, 8>
+                                         : lanes == 16 ? k_gs_flow_pipe<PtrT, 16> : lanes == 32 ? k_gs_flow_pipe<PtrT, 32> : k_gs_flow<PtrT>;
+      const int rpw = lanes == 4 ? 8 : lanes == 8 ? 4 : lanes == 16 ? 2 : 1;
       int ctas_per_sm = 0;
       PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, GS_THREADS, 0));
       if (ctas_per_sm < 1) ctas_per_sm = 1;
-      int nsm = 148;
-      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
       // all CTAs of the grid must be co-resident: a waiting warp only waits for rows held by running warps
       const int64_t per_cta = (int64_t)(GS_THREADS / 32) * rpw;
       const int64_t want = (p.npad + per_cta - 1) / per_cta;

@@ -727,8 +727,8 @@ static int upload_csr(pa_ctx *c, MatPart &m, int64_t nrows, int64_t ncols, const
     PA_CUDA(cudaStreamSynchronize(c->stream));
   }
   if (m.nnz) {
-    PA_CUDA(cudaMalloc((void **)&m.d_colval, (m.nnz + 16) * sizeof(int32_t)));
-    PA_CUDA(cudaMalloc((void **)&m.d_nzval, (m.nnz + 16) * sizeof(double)));
+    PA_CUDA(cudaMalloc((void **)&m.d_colval, (m.nnz + PA_MAT_PAD) * sizeof(int32_t)));
+    PA_CUDA(cudaMalloc((void **)&m.d_nzval, (m.nnz + PA_MAT_PAD) * sizeof(double)));
     PA_CUDA(cudaMemcpyAsync(m.d_colval, cv.data(), m.nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     PA_CUDA(cudaMemcpyAsync(m.d_nzval, nz.data(), m.nnz * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   }
@@ -1051,8 +1051,8 @@ extern "C" int pa_mat_set_stencil(pa_mat *A, int32_t k, int32_t kind, const int6
   m.nnz = nnz;
   m.ptr64 = nnz >= (1ll << 31);
   m.rows_per_cta = choose_rows(n, nnz);
-  PA_CUDA(cudaMalloc((void **)&m.d_colval, (nnz + 16) * sizeof(int32_t)));
-  PA_CUDA(cudaMalloc((void **)&m.d_nzval, (nnz + 16) * sizeof(double)));
+  PA_CUDA(cudaMalloc((void **)&m.d_colval, (nnz + PA_MAT_PAD) * sizeof(int32_t)));
+  PA_CUDA(cudaMalloc((void **)&m.d_nzval, (nnz + PA_MAT_PAD) * sizeof(double)));
   double *d_rhs = nullptr;
   if (rhs) {
     PA_TRY(pa_before_write(c));

@@ -20,14 +20,23 @@ def _vec(pa, rows, vals):
     return pa.PVector(rows).set_local_values(vals)
 
 
-@pytest.mark.parametrize("lanes", [None, 0, 8, 16, 32])  # every variant of the sweep kernel (lanes per row; 0 = any row length)
-@pytest.mark.parametrize("npd,nloc,hint", [((2, 2, 1), (8, 6, 4), True), ((1, 2, 2), (4, 4, 6), False), ((1, 1, 1), (10, 9, 8), True)])
+# every variant of the sweep kernel: default choice, warp-per-row dataflow kernel with 0 (any row length) / 4 / 8 / 16 / 32 lanes per
+# row, and the batch kernel (32 rows of one level per warp) with and without the L2 prefetch
+@pytest.mark.parametrize("lanes", [None, 0, 4, 8, 16, 32, "batch", "batch-noprefetch"])
+@pytest.mark.parametrize("npd,nloc,hint", [((2, 2, 1), (8, 6, 4), True), ((1, 2, 2), (4, 4, 6), False), ((1, 1, 1), (10, 9, 8), True),
+                                           ((2, 1, 1), (40, 32, 24), True)])
 def test_symmetric_gauss_seidel_is_bit_exact(pa, npd, nloc, hint, lanes):
     """smooth! (smoothers.jl:98-125): wavefront sweeps == the reference's sequential per-part sweeps, bit for bit."""
+    if nloc[0] >= 40 and lanes not in (None, 16, "batch", "batch-noprefetch"):
+        pytest.skip("the large case runs the default, the 16-lane and the batch kernels")
     lev = hpcg_mg.Level(*nloc, npd)
     P = len(lev.part)
     b = pa.CUDAArray(P, arena_bytes=32 << 20)
-    if lanes is not None:
+    if isinstance(lanes, str):
+        b.set_knob("gs_kernel", 1)
+        b.set_knob("gs_prefetch", 0 if lanes.endswith("noprefetch") else 1)
+    elif lanes is not None:
+        b.set_knob("gs_kernel", 0)
         b.set_knob("gs_lanes", lanes)
     gn = tuple(a * c for a, c in zip(npd, nloc))
     A, rhs = pa.stencil_matrix(27, gn, npd, b)
@@ -96,4 +105,50 @@ def test_hpcg_preconditioned_cg_matches_reference_constant(pa):
     for k, ind in enumerate(L.part):
         np.testing.assert_allclose(got[k][: ind.n_own], xo[k][: ind.n_own], rtol=1e-10, atol=1e-12)
     P.free()
+    b.close()
+
+
+def _smooth_and_compare(pa, lev, A, gs, seed):
+    rng = np.random.default_rng(seed)
+    bvals = [rng.standard_normal(i.n_local) for i in lev.part]
+    for zero_guess in (True, False):
+        x0 = [np.zeros(i.n_local) if zero_guess else rng.standard_normal(i.n_local) for i in lev.part]
+        xo = [v.copy() for v in x0]
+        x, bv = _vec(pa, A.cols, x0), _vec(pa, A.cols, bvals)
+        for _ in range(2):
+            hpcg_mg.smooth(lev, xo, bvals, zero_guess)
+            gs.smooth_(x, bv, zero_guess)
+        got = x.local_values()
+        for k, ind in enumerate(lev.part):
+            assert np.array_equal(got[k][: ind.n_own], xo[k][: ind.n_own]), (zero_guess, k)
+        x.free(); bv.free()
+
+
+@pytest.mark.parametrize("kernel", [0, 1])  # 0 = warp-per-row dataflow kernel, 1 = batch kernel (1 / 2 entry slots per lane)
+@pytest.mark.parametrize("case", ["fdm7-box", "fdm7-generic", "fem9"])
+def test_gauss_seidel_on_short_rows_is_bit_exact(pa, case, kernel):
+    """Rows of <= 8 entries (7-pt gallery operator, closed-form and host-computed levels) and <= 16 entries (the Q1 FEM
+    operator of test/fem_example.jl, levels from the sparsity pattern): same sweeps as the reference, bit for bit."""
+    from oracle import fem_q1
+
+    if case.startswith("fdm7"):
+        gn, npd = (14, 12, 10), (2, 1, 2)
+        b = pa.CUDAArray(4, arena_bytes=16 << 20)
+        b.set_knob("gs_kernel", kernel)
+        A, _ = pa.stencil_matrix(7, gn, npd, b)
+        I, J, V, rows, cols = o.laplacian_fdm(gn, npd)
+        Ao = o.psparse(I, J, V, rows, cols, assembled=True, local_format="csr")
+        gs = pa.GaussSeidel(A, kind=7 if case.endswith("box") else None)
+    else:
+        prob = fem_q1.Q1Problem((2, 2), (13, 9), (2.0, 2.0 * 9 / 13))
+        b = pa.CUDAArray(4, arena_bytes=16 << 20)
+        b.set_knob("gs_kernel", kernel)
+        rows = pa.variable_partition(b, prob.n_own_dofs, prob.n_global_dofs)
+        A = pa.psparse(prob.I, prob.J, prob.V, rows, rows, assembled=False, local_format="csr")
+        orows = o.variable_partition(prob.n_own_dofs, prob.n_global_dofs)
+        Ao = o.psparse(prob.I, prob.J, prob.V, orows, orows, assembled=False, local_format="csr")
+        gs = pa.GaussSeidel(A)
+    lev = hpcg_mg.Level.from_psparse(Ao)
+    _smooth_and_compare(pa, lev, A, gs, 5)
+    gs.free()
     b.close()
