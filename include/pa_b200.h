@@ -123,6 +123,40 @@ int pa_vec_sum(const pa_vec *x, double *out);
  * returned state is the reference's task; pa_ctx_sync is its wait(). */
 int pa_vec_consistent(pa_vec *v);
 int pa_vec_assemble(pa_vec *v);
+/* assemble!(op, v) (src/p_vector.jl:699-708): values[lid] = op(values[lid], ghost copy) in neighbour order (:605-609);
+ * op = PA_OP_SUM (+), PA_OP_INSERT (insert(a,b) = b, :755), PA_OP_MAX, PA_OP_MIN. */
+#define PA_OP_SUM 0
+#define PA_OP_MAX 1
+#define PA_OP_MIN 2
+#define PA_OP_ABSSUM 3 /* reductions only: sum |x|   = norm(x,1)   */
+#define PA_OP_ABSMAX 4 /* reductions only: max |x|                  */
+#define PA_OP_ABSPOW 5 /* reductions only: sum |x|^p = norm(x,p)^p  */
+#define PA_OP_INSERT 6 /* assemble only                             */
+int pa_vec_assemble_op(pa_vec *v, int32_t op);
+/* reduce(op, a::PVector) / maximum / minimum / norm(a,p) (src/p_vector.jl:1178-1183, :1201-1206): out[k] =
+ * reduce(op, own_values(a)[k]; init = neutral_element(op)) (:1170-1175) for every local part k -- one single-pass
+ * kernel per part; the (tiny) reduction over parts is the caller's second step (reduce(op,b), :1182).  p is the
+ * exponent of PA_OP_ABSPOW.  Synchronises. */
+int pa_vec_reduce_parts(const pa_vec *x, int32_t op, double p, double *out);
+
+/* ------------------------------------------------------------------ exchange!(rcv, snd, graph) ----------
+ * ExchangeGraph (src/primitives.jl:728-741) + the vector-payload exchange (exchange!/exchange_impl! :992-1042;
+ * src/debug_array.jl:250-255, src/mpi_array.jl:525-614) for 8-byte elements (Float64 / Int64 payloads).
+ * snd_ids / rcv_ids: 1-based part ids (graph.snd[p], graph.rcv[p]); snd_ptrs / rcv_ptrs: the 1-based JaggedArray ptrs
+ * of the send / receive buffers (n+1 entries; what allocate_exchange_impl computes, :921-947).
+ * rcv_src_offsets (nullable): for every source i the 0-based position of the segment addressed to this part inside the
+ * SOURCE's send buffer; derived internally when the source is held by this process, required otherwise.
+ * The send buffers live in the symmetric arena: a receiver reads its segment straight from the sender's HBM. */
+typedef struct pa_xchg pa_xchg;
+int pa_xchg_create(pa_ctx *ctx, pa_xchg **out);
+int pa_xchg_set_part(pa_xchg *x, int32_t k, int32_t n_snd, const int32_t *snd_ids, const int64_t *snd_ptrs, int32_t n_rcv,
+                     const int32_t *rcv_ids, const int64_t *rcv_ptrs, const int64_t *rcv_src_offsets);
+/* sym_snd_len: longest send buffer over ALL parts of the job (0 = over the local parts; only when every part is local) */
+int pa_xchg_commit(pa_xchg *x, int64_t sym_snd_len);
+int pa_xchg_destroy(pa_xchg *x);
+int pa_xchg_upload_snd(pa_xchg *x, int32_t k, const void *data, int64_t n);
+int pa_xchg_exchange(pa_xchg *x);
+int pa_xchg_download_rcv(pa_xchg *x, int32_t k, void *data, int64_t n);
 /* v[lid] = hash(gid, seed) in [-1,1) for a box partition (own box lo..hi, 0-based, hi exclusive,
  * of a gn grid; column-major ids); ghost entries are set to 0.  Test/bench input generator. */
 int pa_vec_fill_hash_box(pa_vec *v, int32_t k, const int64_t *gn, const int64_t *lo, const int64_t *hi,

@@ -19,6 +19,7 @@ PA_SPMV_SKIP_GHOST_REFRESH = 2
 PA_CG_REFERENCE_OPS = 4
 PA_SPMV_INLINE_PEER_LOADS = 8
 PA_SPMV_OVERLAP = 16
+PA_OP_SUM, PA_OP_MAX, PA_OP_MIN, PA_OP_ABSSUM, PA_OP_ABSMAX, PA_OP_ABSPOW, PA_OP_INSERT = range(7)
 
 
 class PAError(RuntimeError):
@@ -61,6 +62,15 @@ SIGNATURES = {
     "pa_vec_sum": [_P, _P],
     "pa_vec_consistent": [_P],
     "pa_vec_assemble": [_P],
+    "pa_vec_assemble_op": [_P, _I32],
+    "pa_vec_reduce_parts": [_P, _I32, _D, _P],
+    "pa_xchg_create": [_P, _P],
+    "pa_xchg_set_part": [_P, _I32, _I32, _P, _P, _I32, _P, _P, _P],
+    "pa_xchg_commit": [_P, _I64],
+    "pa_xchg_destroy": [_P],
+    "pa_xchg_upload_snd": [_P, _I32, _P, _I64],
+    "pa_xchg_exchange": [_P],
+    "pa_xchg_download_rcv": [_P, _I32, _P, _I64],
     "pa_vec_fill_hash_box": [_P, _I32, _P, _P, _P, _U64],
     "pa_mat_create": [_P, _P, _P],
     "pa_mat_destroy": [_P],

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libpa_b200.so")
-SOURCES = ["pa_runtime.cu", "pa_vector.cu", "pa_spmv.cu", "pa_cg.cu", "pa_mg.cu", "pa_assembly.cu"]
+SOURCES = ["pa_runtime.cu", "pa_vector.cu", "pa_spmv.cu", "pa_cg.cu", "pa_mg.cu", "pa_assembly.cu", "pa_prims.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -158,6 +158,7 @@ int pa_collective_begin(pa_plan *plan);   // publish my data + wait for the neig
 int pa_collective_end(pa_plan *plan);     // tell the neighbours I am done reading theirs
 int pa_before_write(pa_ctx *ctx);         // wait until nobody is still reading my vectors
 PeerPtrs pa_peer_ptrs(const pa_vec *v, int k);
+int pa_arena_alloc(pa_ctx *ctx, uint64_t bytes, uint64_t *off);  // symmetric offset (same sequence of calls on every process)
 int pa_reduce_finish(pa_ctx *ctx, double *d_out);  // sum local partials (+ NCCL all-reduce) into *d_out
 int pa_read_scalars(pa_ctx *ctx, int first, int count, double *out);  // synchronises
 int pa_check_device_error(pa_ctx *ctx);

@@ -399,7 +399,8 @@ static int signal_all(pa_plan *plan, bool done) {
   for (int k = 0; k < c->nlocal; ++k) {
     const PlanPart &pp = plan->parts[k];
     int n = (int)pp.nbrs.size();
-    if (!n) continue;
+    // a part without neighbours in THIS collective still counts it: the epochs of all parts advance in lockstep
+    if (!n && done) continue;
     FlagPtrs dst;
     for (int i = 0; i < n; ++i) {
       PA_CHECK(c->peer_base[pp.nbrs[i]], PA_ESTATE, "part %d's arena was never imported (pa_ctx_arena_import)", pp.nbrs[i] + 1);
@@ -456,7 +457,6 @@ int pa_collective_begin(pa_plan *plan) {
   if (c->nlocal == 1) {
     const PlanPart &pp = plan->parts[0];
     const int n = (int)pp.nbrs.size();
-    if (!n) return PA_OK;
     FlagPtrs dst, src;
     for (int i = 0; i < n; ++i) {
       PA_CHECK(c->peer_base[pp.nbrs[i]], PA_ESTATE, "part %d's arena was never imported (pa_ctx_arena_import)", pp.nbrs[i] + 1);

@@ -5,7 +5,7 @@
 #include "pa_internal.h"
 
 // ------------------------------------------------------------------ symmetric arena
-static int arena_alloc(pa_ctx *c, uint64_t bytes, uint64_t *off) {
+int pa_arena_alloc(pa_ctx *c, uint64_t bytes, uint64_t *off) {
   auto it = c->freelist.find(bytes);
   if (it != c->freelist.end() && !it->second.empty()) {
     *off = it->second.back();
@@ -25,7 +25,7 @@ extern "C" int pa_vec_create(pa_plan *plan, pa_vec **out) {
   pa_ctx *c = plan->ctx;
   pa_vec *v = new pa_vec();
   v->plan = plan;
-  int r = arena_alloc(c, plan->vec_bytes, &v->offset);
+  int r = pa_arena_alloc(c, plan->vec_bytes, &v->offset);
   if (r != PA_OK) {
     delete v;
     return r;
@@ -333,13 +333,18 @@ __global__ void k_consistent(double *v, const int32_t *__restrict__ lid, const i
     v[lid[j]] = __ldcg(peers.p[slot[j]] + rlid[j]);
 }
 
-// assemble!: each owned destination adds the neighbours' ghost copies in neighbour order
-// (values[lid] = values[lid] + buf[p], src/p_vector.jl:605-609), one thread per destination.
+// assemble!: each owned destination combines the neighbours' ghost copies in neighbour order
+// (values[lid] = f(values[lid], buf[p]), src/p_vector.jl:605-609), one thread per destination.
+// OP 0: +   1: insert(a,b) = b (src/p_vector.jl:755)   2: max   3: min
+template <int OP>
 __global__ void k_assemble(double *v, const int32_t *__restrict__ dst, const int32_t *__restrict__ ptr,
                            const int32_t *__restrict__ slot, const int32_t *__restrict__ rlid, int64_t ndst, PeerPtrs peers) {
   for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < ndst; d += (int64_t)gridDim.x * blockDim.x) {
     double acc = v[dst[d]];
-    for (int t = ptr[d]; t < ptr[d + 1]; ++t) acc = __dadd_rn(acc, __ldcg(peers.p[slot[t]] + rlid[t]));
+    for (int t = ptr[d]; t < ptr[d + 1]; ++t) {
+      const double b = __ldcg(peers.p[slot[t]] + rlid[t]);
+      acc = OP == 0 ? __dadd_rn(acc, b) : (OP == 1 ? b : (OP == 2 ? (b > acc ? b : acc) : (b < acc ? b : acc)));
+    }
     v[dst[d]] = acc;
   }
 }
@@ -377,8 +382,11 @@ extern "C" int pa_vec_consistent(pa_vec *v) {
   return pa_collective_end(v->plan);
 }
 
-extern "C" int pa_vec_assemble(pa_vec *v) {
+extern "C" int pa_vec_assemble(pa_vec *v) { return pa_vec_assemble_op(v, PA_OP_SUM); }
+
+extern "C" int pa_vec_assemble_op(pa_vec *v, int32_t op) {
   PA_CHECK(v, PA_EINVAL, "pa_vec_assemble: null vector");
+  PA_CHECK(op == PA_OP_SUM || op == PA_OP_INSERT || op == PA_OP_MAX || op == PA_OP_MIN, PA_EINVAL, "pa_vec_assemble_op: unknown operation %d", op);
   pa_ctx *c = v->plan->ctx;
   PA_CUDA(cudaSetDevice(c->device));
   PA_TRY(pa_before_write(c));
@@ -386,8 +394,9 @@ extern "C" int pa_vec_assemble(pa_vec *v) {
   for (int k = 0; k < c->nlocal; ++k) {
     const PlanPart &pp = v->plan->parts[k];
     if (!pp.n_asm_dst) continue;
-    k_assemble<<<small_grid(pp.n_asm_dst), 256, 0, c->stream>>>(v->d[k], pp.d_asm_dst, pp.d_asm_ptr, pp.d_asm_slot,
-                                                               pp.d_asm_rlid, pp.n_asm_dst, pa_peer_ptrs(v, k));
+    auto kern = op == PA_OP_SUM ? k_assemble<0> : (op == PA_OP_INSERT ? k_assemble<1> : (op == PA_OP_MAX ? k_assemble<2> : k_assemble<3>));
+    kern<<<small_grid(pp.n_asm_dst), 256, 0, c->stream>>>(v->d[k], pp.d_asm_dst, pp.d_asm_ptr, pp.d_asm_slot, pp.d_asm_rlid,
+                                                        pp.n_asm_dst, pa_peer_ptrs(v, k));
     c->launches++;
   }
   PA_CUDA(cudaGetLastError());

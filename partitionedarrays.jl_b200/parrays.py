@@ -263,9 +263,12 @@ class PVector:
         check(_capi.lib().pa_vec_consistent(self.h))
         return _Task(self)
 
-    def assemble_(self):
-        """assemble!(v) (src/p_vector.jl:695-708)."""
-        check(_capi.lib().pa_vec_assemble(self.h))
+    def assemble_(self, op: str = "+"):
+        """assemble!([op,] v) (src/p_vector.jl:695-708): op in '+', 'insert', 'max', 'min'."""
+        code = {"+": _capi.PA_OP_SUM, "insert": _capi.PA_OP_INSERT, "max": _capi.PA_OP_MAX, "min": _capi.PA_OP_MIN}.get(op)
+        if code is None:
+            raise ValueError(f"assemble!: unsupported operation {op!r}")
+        check(_capi.lib().pa_vec_assemble_op(self.h, code))
         return _Task(self)
 
     # --- reductions ---
@@ -274,10 +277,40 @@ class PVector:
         check(_capi.lib().pa_vec_dot(self.h, other.h, C.byref(out)))
         return out.value
 
-    def norm(self) -> float:
-        out = C.c_double()
-        check(_capi.lib().pa_vec_norm2(self.h, C.byref(out)))
-        return math.sqrt(out.value)
+    def norm(self, p: float = 2) -> float:
+        """norm(a, p) = (sum over parts of norm(own, p)^p)^(1/p) (src/p_vector.jl:1201-1206)."""
+        if p == 2:
+            out = C.c_double()
+            check(_capi.lib().pa_vec_norm2(self.h, C.byref(out)))
+            return math.sqrt(out.value)
+        if not (p >= 1 and math.isfinite(p)):
+            raise ValueError("norm(a, p): p must be a finite number >= 1")
+        return self.reduce("+", _op=_capi.PA_OP_ABSSUM if p == 1 else _capi.PA_OP_ABSPOW, _p=float(p)) ** (1.0 / p)
+
+    def reduce(self, op: str = "+", _op: Optional[int] = None, _p: float = 0.0) -> float:
+        """reduce(op, a) (src/p_vector.jl:1178-1183): per-part reduction of the own values on the device (neutral element
+        as init, :1170-1175), then the reduction over parts (over processes: a host all-gather of one number per part)."""
+        code = _op if _op is not None else {"+": _capi.PA_OP_SUM, "max": _capi.PA_OP_MAX, "min": _capi.PA_OP_MIN}.get(op)
+        if code is None:
+            raise ValueError(f"reduce: unsupported operation {op!r}")
+        nl = len(self.backend.parts)
+        part = np.zeros(nl, dtype=np.float64)
+        check(_capi.lib().pa_vec_reduce_parts(self.h, code, float(_p), ptr(part)))
+        allp = self.backend.gather_all([float(v) for v in part])
+        if op == "max":
+            return max(allp)
+        if op == "min":
+            return min(allp)
+        acc = 0.0
+        for v in allp:  # part order, like sum over the array of parts
+            acc += v
+        return acc
+
+    def maximum(self) -> float:
+        return self.reduce("max")
+
+    def minimum(self) -> float:
+        return self.reduce("min")
 
     def sum(self) -> float:
         out = C.c_double()
@@ -348,16 +381,90 @@ def dot(a: PVector, b: PVector) -> float:
     return a.dot(b)
 
 
-def norm(a: PVector) -> float:
-    return a.norm()
+def norm(a: PVector, p: float = 2) -> float:
+    return a.norm(p)
 
 
 def consistent_(v: PVector):
     return v.consistent_()
 
 
-def assemble_(v: PVector):
-    return v.assemble_()
+def assemble_(v: PVector, op: str = "+"):
+    return v.assemble_(op)
+
+
+class ExchangeGraph:
+    """ExchangeGraph(snd[, rcv]) (src/primitives.jl:728-741, 776-789): ``snd[k]`` = 1-based ids of the parts local part k
+    sends to.  Without ``rcv`` the receive sides are found like default_find_rcv_ids (:826-859): the transpose of the
+    adjacency, sources sorted ascending (one host all-gather of the send lists)."""
+
+    def __init__(self, backend: CUDAArray, snd: Sequence[Sequence[int]], rcv: Optional[Sequence[Sequence[int]]] = None):
+        self.backend = backend
+        self.snd = [[int(q) for q in s] for s in snd]
+        if len(self.snd) != len(backend.parts):
+            raise ValueError("ExchangeGraph: one send list per local part")
+        if rcv is None:
+            all_snd = backend.gather_all(self.snd)
+            rcv = [sorted(p + 1 for p, s in enumerate(all_snd) if me in set(s)) for me in backend.parts]
+        self.rcv = [[int(q) for q in r] for r in rcv]
+
+
+def _ptrs1(lengths) -> np.ndarray:
+    out = np.ones(len(lengths) + 1, dtype=np.int64)
+    np.cumsum(lengths, out=out[1:])
+    out[1:] += 1
+    return out
+
+
+def exchange(snd: Sequence[Sequence], graph: ExchangeGraph) -> List[List[np.ndarray]]:
+    """rcv = fetch(exchange(snd, graph)) (src/primitives.jl:876-925, 992-1042): ``snd[k][j]`` (a scalar or a vector of
+    Float64 / Int64) goes to part ``graph.snd[k][j]``; ``rcv[k][i]`` is what part ``graph.rcv[k][i]`` sent here.  The
+    payload moves on the device: each receiver reads its segments from the senders' HBM (pa_xchg_*)."""
+    b = graph.backend
+    L = _capi.lib()
+    nl = len(b.parts)
+    segs = [[np.atleast_1d(np.asarray(v)) for v in s] for s in snd]
+    # 8-byte elements on the device: Float64 when any part sends floats, Int64 otherwise (all processes must agree)
+    kinds = sorted({("f" if a.dtype.kind == "f" else "i") for s in segs for a in s})
+    dtype = np.float64 if any("f" in k for k in b.gather_all([kinds])) else np.int64
+    for k in range(nl):
+        if len(segs[k]) != len(graph.snd[k]):
+            raise ValueError("exchange: one send item per destination")
+    snd_len = [[len(a) for a in s] for s in segs]
+    # allocate_exchange (src/primitives.jl:921-947): the receive lengths are the senders' send lengths
+    all_snd_ids, all_snd_len = b.gather_all(graph.snd), b.gather_all(snd_len)
+    h = C.c_void_p()
+    check(L.pa_xchg_create(b.h, C.byref(h)))
+    rcv_len = []
+    try:
+        for k, me in enumerate(b.parts):
+            rl, off = [], []
+            for src in graph.rcv[k]:
+                ids = all_snd_ids[src - 1]
+                if me not in ids:
+                    raise ValueError(f"exchange: graph not consistent (part {me} receives from {src}, which does not send to it)")
+                j = ids.index(me)
+                rl.append(all_snd_len[src - 1][j])
+                off.append(int(sum(all_snd_len[src - 1][:j])))
+            rcv_len.append(rl)
+            si, ri = i32(graph.snd[k]), i32(graph.rcv[k])
+            sp, rp, so = _ptrs1(snd_len[k]), _ptrs1(rl), i64(off)
+            check(L.pa_xchg_set_part(h, k, len(si), ptr(si), ptr(sp), len(ri), ptr(ri), ptr(rp), ptr(so)))
+        sym = max([sum(l) for l in all_snd_len] + [0])
+        check(L.pa_xchg_commit(h, sym))
+        for k in range(nl):
+            flat = np.ascontiguousarray(np.concatenate([a.astype(dtype) for a in segs[k]]) if segs[k] else np.zeros(0, dtype=dtype))
+            check(L.pa_xchg_upload_snd(h, k, ptr(flat), len(flat)))
+        check(L.pa_xchg_exchange(h))
+        out = []
+        for k in range(nl):
+            flat = np.zeros(sum(rcv_len[k]), dtype=dtype)
+            check(L.pa_xchg_download_rcv(h, k, ptr(flat), len(flat)))
+            cuts = np.cumsum([0] + rcv_len[k])
+            out.append([flat[cuts[i] : cuts[i + 1]].copy() for i in range(len(rcv_len[k]))])
+    finally:
+        L.pa_xchg_destroy(h)
+    return out
 
 
 class PSparseMatrix:
