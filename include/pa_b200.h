@@ -217,6 +217,7 @@ int pa_mat_fill_stored(pa_mat *A, double a);
 #define PA_CG_REFERENCE_OPS 4u        /* op-for-op sequence of ref_cg.jl (copy,dot,axpby,spmv,dot,...) */
 #define PA_SPMV_INLINE_PEER_LOADS 8u  /* one kernel: ghost columns dereference the owner's arena inside the SpMV */
 #define PA_SPMV_OVERLAP 16u           /* consistent!(x) on a side stream || own-block product, then ghost-block product */
+#define PA_SPMV_FUSED_EXCHANGE 32u    /* ONE kernel: the SpMV's producer warps pull the ghost values while the first tiles stream */
 
 /* mul!(y,A,x) (src/p_sparse_matrix.jl:2090-2103) when alpha=1,beta=0; mul!(y,A,x,alpha,beta)
  * (:2105-2142) otherwise; HPCG mul_no_lat! (HPCG/src/hpcg_utils.jl:6-17) is the same call.
@@ -226,6 +227,9 @@ int pa_mat_fill_stored(pa_mat *A, double a);
  *                              columns (the HPCG mul_no_lat! schedule; fastest measured on B200)
  *   PA_SPMV_OVERLAP            the reference mul! latency hiding: the gather runs on a side stream while the
  *                              own-block product A_oo*x_own streams from HBM; then A_oh*x_ghost is added in order
+ *   PA_SPMV_FUSED_EXCHANGE     one kernel: the producer warp of every CTA pulls its share of the ghost values into x's
+ *                              ghost slots (NVLink peer loads) while the first matrix tiles are in flight; only rows that
+ *                              touch a ghost column wait for the gather (needs regular rows; else falls back to default)
  *   PA_SPMV_INLINE_PEER_LOADS  one kernel: ghost columns dereference the owner's arena inside the SpMV
  * x's ghost slots are consistent on return, like after the reference's mul! (except with
  * PA_SPMV_INLINE_PEER_LOADS|PA_SPMV_SKIP_GHOST_REFRESH). */

@@ -121,6 +121,41 @@ struct DeviceTask; ctx::Ptr{Cvoid}; end
 Base.wait(t::DeviceTask) = @pacall ccall((:pa_ctx_sync, LIB), Cint, (Ptr{Cvoid},), t.ctx)
 consistent!(v::DeviceVector, b::CUDABackend) = (@pacall ccall((:pa_vec_consistent, LIB), Cint, (Ptr{Cvoid},), v.h); DeviceTask(b.h))  # :747-755
 assemble!(v::DeviceVector, b::CUDABackend) = (@pacall ccall((:pa_vec_assemble, LIB), Cint, (Ptr{Cvoid},), v.h); DeviceTask(b.h))      # :695-708
+# assemble!(op, v) (:699-708); insert(a,b) = b (:755)
+const PA_OP = Dict{Any,Int32}(+ => 0, max => 1, min => 2, PartitionedArrays.insert => 6)
+assemble!(op, v::DeviceVector, b::CUDABackend) = (@pacall ccall((:pa_vec_assemble_op, LIB), Cint, (Ptr{Cvoid}, Int32), v.h, PA_OP[op]); DeviceTask(b.h))
+"reduce(op, a) (src/p_vector.jl:1178-1183): the per-part reduction runs on the device; the reduction over parts is the backend's `reduce`"
+function reduce_own(op, v::DeviceVector)
+    r = Ref{Float64}(); @pacall ccall((:pa_vec_reduce_parts, LIB), Cint, (Ptr{Cvoid}, Int32, Float64, Ptr{Float64}), v.h, PA_OP[op], 0.0, r); r[]
+end
+"norm(a,p) (:1201-1206): sum over parts of norm(own,p)^p, then ^(1/p)  (op 3 = sum|x|, op 5 = sum|x|^p)"
+function norm_p_own(v::DeviceVector, p::Real)
+    r = Ref{Float64}(); @pacall ccall((:pa_vec_reduce_parts, LIB), Cint, (Ptr{Cvoid}, Int32, Float64, Ptr{Float64}), v.h, p == 1 ? Int32(3) : Int32(5), Float64(p), r); r[]
+end
+
+# ---------------------------------------------------------------- exchange!(rcv, snd, graph) with device-resident buffers
+# exchange_impl!(rcv, snd, graph, setup, ::Type{<:AbstractVector}) (src/primitives.jl:1020-1042; src/mpi_array.jl:525-614):
+# snd/rcv are JaggedArrays of 8-byte elements; the receiver pulls its segments from the senders' HBM.
+mutable struct DeviceExchange
+    h::Ptr{Cvoid}
+end
+function DeviceExchange(b::CUDABackend, graph::ExchangeGraph, snd_ptrs::Vector{Int64}, rcv_ptrs::Vector{Int64}, rcv_src_offsets::Vector{Int64}, sym_snd_len)
+    h = Ref{Ptr{Cvoid}}()
+    @pacall ccall((:pa_xchg_create, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), b.h, h)
+    map(graph.snd, graph.rcv) do s, r   # one part per process: a single item
+        @pacall ccall((:pa_xchg_set_part, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Ptr{Int64}, Int32, Ptr{Int32}, Ptr{Int64}, Ptr{Int64}),
+                      h[], 0, length(s), Int32.(s), snd_ptrs, length(r), Int32.(r), rcv_ptrs, rcv_src_offsets)
+    end
+    @pacall ccall((:pa_xchg_commit, LIB), Cint, (Ptr{Cvoid}, Int64), h[], sym_snd_len)
+    x = DeviceExchange(h[])
+    finalizer(y -> ccall((:pa_xchg_destroy, LIB), Cint, (Ptr{Cvoid},), y.h), x)
+end
+function exchange!(rcv::Vector{T}, snd::Vector{T}, x::DeviceExchange, b::CUDABackend) where T<:Union{Float64,Int64}
+    @pacall ccall((:pa_xchg_upload_snd, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int64), x.h, 0, snd, length(snd))
+    @pacall ccall((:pa_xchg_exchange, LIB), Cint, (Ptr{Cvoid},), x.h)
+    @pacall ccall((:pa_xchg_download_rcv, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int64), x.h, 0, rcv, length(rcv))   # = fetch(t)
+    rcv
+end
 
 # ---------------------------------------------------------------- PSparseMatrix payload on the GPU
 mutable struct DeviceMatrix

@@ -19,6 +19,7 @@ PA_SPMV_SKIP_GHOST_REFRESH = 2
 PA_CG_REFERENCE_OPS = 4
 PA_SPMV_INLINE_PEER_LOADS = 8
 PA_SPMV_OVERLAP = 16
+PA_SPMV_FUSED_EXCHANGE = 32
 PA_OP_SUM, PA_OP_MAX, PA_OP_MIN, PA_OP_ABSSUM, PA_OP_ABSMAX, PA_OP_ABSPOW, PA_OP_INSERT = range(7)
 
 

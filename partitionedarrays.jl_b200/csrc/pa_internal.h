@@ -129,6 +129,8 @@ struct MatPart {
   int64_t n_grows = 0;
   int32_t *d_grows = nullptr;
   double *d_dotpart = nullptr;  // per-CTA partials of the fused dot epilogue
+  unsigned long long *d_arrive = nullptr;  // fused consistent! (SpMV MODE 4): CTAs counted in, over all launches
+  int64_t arrive_grid = 0;
   // COO pattern cache (the reference's K of sparse_matrix(...; reuse=true)): sorted permutation + segment starts
   int32_t *d_coo_perm = nullptr, *d_coo_seg = nullptr;
   unsigned char *d_coo_valid = nullptr;

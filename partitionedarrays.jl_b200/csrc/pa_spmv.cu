@@ -35,6 +35,11 @@ struct SpmvArgs {
   // fused dot epilogue (CG: u.c with c = A*u): sum_i y_i * dotw_i, one partial per CTA
   const double *dotw;
   double *dot_part;
+  // fused consistent! (MODE 4): the kernel itself pulls the ghost values from the owners' HBM into x's ghost slots
+  double *xw;                                  // x, writable
+  const int32_t *cons_lid, *cons_slot, *cons_rlid;  // the consistent! table of x's plan (ghost slot <- owner slot, lid)
+  int64_t n_cons;
+  unsigned long long *arrive;                  // CTAs whose share of the gather is stored, summed over all launches
 };
 
 // The matrix stream is read exactly once: keep it out of L1 and mark it evict-first in L2 so the
@@ -183,13 +188,35 @@ __device__ __forceinline__ void keep_live(const double (&x)[N]) {
   if (N >= 32) keep_live16(x + 16);
 }
 
+// MODE 4: wait until every CTA of this launch has stored its share of the ghost values (out of line: rare path).
+// The first thread of a CTA that gets here polls the global counter (relaxed loads, then ONE acquire fence: an
+// acquire load would invalidate the SM's L1 on every poll) and leaves a CTA-wide flag behind for the others.
+__device__ __noinline__ void spmv_wait_gather(const unsigned long long *arrive, unsigned long long target, int *cta_ready) {
+  int seen;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(seen) : "r"((uint32_t)__cvta_generic_to_shared(cta_ready)) : "memory");
+  if (seen) return;
+  unsigned long long got;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(got) : "l"(arrive) : "memory");
+    if (got >= target || clock64() - t0 > 20000000000LL) break;  // (~10 s: never hang the GPU)
+  }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  asm volatile("st.release.cta.shared.s32 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(cta_ready)) : "memory");
+}
+
 // minBlocksPerSM is stated explicitly: with maxThreads alone ptxas squeezes the kernel into 32 registers
 // (full-occupancy target) by sinking every load next to its use, which serialises the x gathers.
 // MODE 0: every column is a local x entry (1 part, or ghosts already refreshed)
 // MODE 1: ghost columns are loaded from the owner's arena inside this kernel (inline NVLink loads)
 // MODE 2: own block only (A_oo * x_own); the ghost block is added afterwards by k_spmv_ghost_rows
+// MODE 4: consistent!(x) fused into this kernel: while the first matrix tiles are in flight (TMA), the producer warp
+//         of every CTA pulls its share of the ghost values from the owners' HBM (NVLink peer loads) into x's ghost
+//         slots, fences and counts itself in; rows that touch a ghost column wait (once per thread) until all CTAs
+//         are counted in and read the slots through L2.  Own-block products never wait: on a banded operator only
+//         the first tiles of the persistent grid can meet the gather still in flight.
 template <typename PtrT, int MODE, int BATCH>
-__global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MODE == 1 ? 3 : 4)))) k_spmv_tma(const SpmvArgs<PtrT> a, const TmaCfg cfg) {
+__global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MODE == 1 || MODE == 4 ? 3 : 4)))) k_spmv_tma(const SpmvArgs<PtrT> a, const TmaCfg cfg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int ROWS = cfg.rows, CAP = cfg.cap, S = cfg.stages;
   // layout: val[S][CAP+2] | col[S][CAP+8] | p0[S] (int64) | full[S] | empty[S]
@@ -199,41 +226,79 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
   uint64_t *full = reinterpret_cast<uint64_t *>(p0_s + S);
   uint64_t *empty = full + S;
   const int tid = threadIdx.x;
+  __shared__ unsigned long long gather_target;
+  __shared__ int gather_seen;  // MODE 4: some thread of this CTA has seen the gather complete
   if (tid == 0) {
+    gather_seen = 0;
     for (int s = 0; s < S; ++s) {
       mbar_init(full + s, 1);
       mbar_init(empty + s, ROWS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (MODE == 4) {
+      // arrivals of earlier launches are complete (kernel boundary) and this CTA has not arrived yet, so fewer than
+      // gridDim.x arrivals of THIS launch can be in the count: the launch ends at the next multiple of gridDim.x
+      unsigned long long a0;
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a0) : "l"(a.arrive) : "memory");
+      gather_target = (a0 / gridDim.x + 1ull) * gridDim.x;
+    }
   }
   __syncthreads();
   const int64_t first = blockIdx.x, stride = gridDim.x;
   const int64_t nloc = first < cfg.ntiles ? (cfg.ntiles - first + stride - 1) / stride : 0;
   if (tid >= ROWS) {
     // ---------------- producer warp: one elected lane drives the TMA ring
-    if (tid == ROWS) {
-      const uint64_t pol = stream_policy();
-      for (int64_t j = 0; j < nloc; ++j) {
-        const int s = (int)(j % S);
-        if (j >= S) mbar_wait(empty + s, (uint32_t)(((j / S) - 1) & 1));
-        const int64_t t = first + j * stride;
-        const int64_t r0 = t * ROWS, r1 = min(r0 + (int64_t)ROWS, a.nrows);
-        const int64_t p0 = (int64_t)a.rowptr[r0], p1 = (int64_t)a.rowptr[r1];
-        p0_s[s] = p0;
-        const int64_t pv = p0 & ~(int64_t)1, pc = p0 & ~(int64_t)3;
-        const uint32_t bv = (uint32_t)(((p1 - pv + 1) & ~(int64_t)1) * 8), bc = (uint32_t)(((p1 - pc + 3) & ~(int64_t)3) * 4);
-        const bool any = p1 > p0;
-        mbar_expect_tx(full + s, any ? bv + bc : 0u);
-        if (any) {
-          tma_load_1d(val_s + (size_t)s * (CAP + 2), a.nzval + pv, bv, full + s, pol);
-          tma_load_1d(col_s + (size_t)s * (CAP + 8), a.colval + pc, bc, full + s, pol);
+    auto issue = [&](int64_t j, uint64_t pol) {
+      const int s = (int)(j % S);
+      if (j >= S) mbar_wait(empty + s, (uint32_t)(((j / S) - 1) & 1));
+      const int64_t t = first + j * stride;
+      const int64_t r0 = t * ROWS, r1 = min(r0 + (int64_t)ROWS, a.nrows);
+      const int64_t p0 = (int64_t)a.rowptr[r0], p1 = (int64_t)a.rowptr[r1];
+      p0_s[s] = p0;
+      const int64_t pv = p0 & ~(int64_t)1, pc = p0 & ~(int64_t)3;
+      const uint32_t bv = (uint32_t)(((p1 - pv + 1) & ~(int64_t)1) * 8), bc = (uint32_t)(((p1 - pc + 3) & ~(int64_t)3) * 4);
+      const bool any = p1 > p0;
+      mbar_expect_tx(full + s, any ? bv + bc : 0u);
+      if (any) {
+        tma_load_1d(val_s + (size_t)s * (CAP + 2), a.nzval + pv, bv, full + s, pol);
+        tma_load_1d(col_s + (size_t)s * (CAP + 8), a.colval + pc, bc, full + s, pol);
+      }
+    };
+    const uint64_t pol = stream_policy();
+    int64_t j0 = 0;
+    if (MODE == 4) {
+      // fill the ring first (asynchronous), then the whole warp does this CTA's share of consistent!(x)
+      const int64_t nfill = min((int64_t)S, nloc);
+      if (tid == ROWS)
+        for (; j0 < nfill; ++j0) issue(j0, pol);
+      __syncwarp();
+      const int lane = tid - ROWS;
+      const int64_t gstride = (int64_t)gridDim.x * 32;
+      for (int64_t q = (int64_t)blockIdx.x * 32 + lane; q < a.n_cons; q += 4 * gstride) {  // 4 NVLink loads in flight per lane
+        double g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t qu = q + u * gstride;
+          g[u] = qu < a.n_cons ? __ldcg(a.peers.p[a.cons_slot[qu]] + a.cons_rlid[qu]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t qu = q + u * gstride;
+          if (qu < a.n_cons) a.xw[a.cons_lid[qu]] = g[u];
         }
       }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicAdd(a.arrive, 1ull);
+      j0 = nfill;  // (only lane 0 advanced its copy)
     }
+    if (tid == ROWS)
+      for (int64_t j = j0; j < nloc; ++j) issue(j, pol);
     return;
   }
   // ---------------- consumers: one thread per row
   double dsum = 0.0;
+  bool ghosts_ready = false;  // MODE 4: this thread has seen the gather complete
   int64_t rs_n = 0, re_n = 0;
   if (nloc > 0) {
     const int64_t row = first * ROWS + tid;
@@ -275,7 +340,7 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
           v[u] = vs[kk];
         }
         bool ghost = false;
-        if (MODE == 1) {
+        if (MODE == 1 || MODE == 4) {
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) ghost |= c[u] >= a.n_own_cols;
         }
@@ -286,6 +351,13 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
         } else if (MODE == 0 || !ghost) {  // straight-line: all BATCH gathers are in flight together
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) xv[u] = __ldg(a.x + c[u]);
+        } else if (MODE == 4) {  // boundary rows: the ghost slots are filled by this very kernel
+          if (!ghosts_ready) {
+            spmv_wait_gather(a.arrive, gather_target, &gather_seen);
+            ghosts_ready = true;
+          }
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u) xv[u] = c[u] >= a.n_own_cols ? __ldcg(a.x + c[u]) : __ldg(a.x + c[u]);
         } else {  // boundary rows: ghost columns come from the owner's HBM over NVLink
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) {
@@ -367,10 +439,11 @@ static int max_tile_nnz(pa_ctx *c, MatPart &m, int rows, int64_t *out) {
 }
 
 template <typename PtrT>
-static int launch_spmv_tma(pa_ctx *c, const SpmvArgs<PtrT> &a, int mode, const TmaCfg &cfg, int ctas_per_sm, int64_t *grid_out) {
+static int launch_spmv_tma(pa_ctx *c, MatPart &m, const SpmvArgs<PtrT> &a, int mode, const TmaCfg &cfg, int ctas_per_sm, int64_t *grid_out) {
   const size_t smem = (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (cfg.cap + 8) * 4 + 8 + 16) + 128;
   const int batch = cfg.batch;
   auto kern = mode == 1 ? (batch >= 32 ? k_spmv_tma<PtrT, 1, 32> : batch >= 16 ? k_spmv_tma<PtrT, 1, 16> : k_spmv_tma<PtrT, 1, 8>)
+            : mode == 4 ? (batch >= 32 ? k_spmv_tma<PtrT, 4, 32> : batch >= 16 ? k_spmv_tma<PtrT, 4, 16> : k_spmv_tma<PtrT, 4, 8>)
             : mode == 2 ? (batch >= 32 ? k_spmv_tma<PtrT, 2, 32> : batch >= 16 ? k_spmv_tma<PtrT, 2, 16> : k_spmv_tma<PtrT, 2, 8>)
                         : (batch >= 32 ? k_spmv_tma<PtrT, 0, 32> : batch >= 16 ? k_spmv_tma<PtrT, 0, 16> : k_spmv_tma<PtrT, 0, 8>);
   PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -382,6 +455,10 @@ static int launch_spmv_tma(pa_ctx *c, const SpmvArgs<PtrT> &a, int mode, const T
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
   int64_t grid = std::min<int64_t>(cfg.ntiles, (int64_t)nsm * ctas_per_sm);
   PA_CHECK(!a.dotw || grid <= PA_DOT_PARTS, PA_ESTATE, "dot epilogue: grid larger than the partial buffer");
+  if (mode == 4 && m.arrive_grid != grid) {  // the arrival counter advances by `grid` per launch: restart it when the grid changes
+    PA_CUDA(cudaMemsetAsync(m.d_arrive, 0, sizeof(unsigned long long), c->stream));
+    m.arrive_grid = grid;
+  }
   kern<<<(unsigned)grid, cfg.rows + 32, smem, c->stream>>>(a, cfg);
   *grid_out = grid;
   return PA_OK;
@@ -492,7 +569,8 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, in
     const PlanPart &cp = A->cols->parts[k];
     const PlanPart &rp = A->rows->parts[k];
     int kmode = mode;
-    if ((mode == 1 || mode == 2) && cp.n_ghost == 0) kmode = 0;
+    const PlanPart &xp = x->plan->parts[k];
+    if ((mode == 1 || mode == 2 || mode == 4) && (cp.n_ghost == 0 || (mode == 4 && xp.n_cons == 0))) kmode = 0;
     if (mode == 3 && m.n_grows == 0) continue;
     int rows = (int)pa_knob(c, "spmv_rows", 0);
     if (rows != 256 && rows != 128 && rows != 64 && rows != 32) rows = m.rows_per_cta;
@@ -511,7 +589,8 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, in
       const size_t smem = (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (cfg.cap + 8) * 4 + 8 + 16) + 128;
       if (smem > 200 * 1024) use_tma = false;  // a tile does not fit: irregular rows -> chunked kernel
     }
-    PA_CHECK(use_tma || kmode != 2, PA_ESTATE, "own-block mode needs the TMA kernel");
+    PA_CHECK(use_tma || (kmode != 2 && kmode != 4), PA_ESTATE, "own-block / fused-exchange modes need the TMA kernel");
+    if (kmode == 4 && !m.d_arrive) PA_CUDA(cudaMalloc((void **)&m.d_arrive, sizeof(unsigned long long)));
     auto fill = [&](auto &a) {
       a.nrows = m.nrows;
       a.colval = m.d_colval;
@@ -527,6 +606,12 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, in
       a.peers = pa_peer_ptrs(x, k);
       a.dotw = dotw ? dotw->d[k] : nullptr;
       a.dot_part = m.d_dotpart;
+      a.xw = x->d[k];
+      a.cons_lid = xp.d_ghost_lid;
+      a.cons_slot = xp.d_ghost_slot;
+      a.cons_rlid = xp.d_ghost_rlid;
+      a.n_cons = xp.n_cons;
+      a.arrive = m.d_arrive;
     };
     if (dotw) {
       PA_CHECK(use_tma && mode != 2 && mode != 3 && rp.prefix && alpha == 1.0 && beta == 0.0, PA_ESTATE, "dot epilogue unavailable for this configuration");
@@ -539,7 +624,7 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, in
         const int64_t g = std::min<int64_t>((m.n_grows + 255) / 256, 148 * 8);
         k_spmv_ghost_rows<PtrT><<<(unsigned)g, 256, 0, c->stream>>>(a, m.d_grows, m.n_grows);
       } else if (use_tma) {
-        PA_TRY(launch_spmv_tma<PtrT>(c, a, kmode, cfg, ctas, &grid_used));
+        PA_TRY(launch_spmv_tma<PtrT>(c, m, a, kmode, cfg, ctas, &grid_used));
       } else if (kmode == 1) {
         launch_spmv_t<PtrT, true>(a, rows, c->stream);
       } else {
@@ -569,14 +654,14 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, in
   return PA_OK;
 }
 
-// can pa_spmv_dot fuse the dot into the SpMV for this matrix? (regular rows, own-first layout)
-static bool dot_fusable(pa_mat *A, pa_vec *x) {
+// does every local part run the TMA kernel? (regular rows: a tile fits a stage; own-first layout)
+static bool tma_usable(pa_mat *A, pa_vec *x) {
   pa_ctx *c = A->ctx;
-  if (pa_knob(c, "spmv_kernel", 3) != 3 || pa_knob(c, "no_dot_fusion", 0)) return false;
+  if (pa_knob(c, "spmv_kernel", 3) != 3) return false;
   for (int k = 0; k < c->nlocal; ++k) {
     MatPart &m = A->parts[k];
     if (!x->plan->parts[k].prefix || !A->rows->parts[k].prefix) return false;
-    if (m.nrows == 0) return false;
+    if (m.nrows == 0 || !m.tma_ok) return false;
     int rows = (int)pa_knob(c, "tma_rows", m.nnz > 12 * m.nrows ? 64 : 256);
     int64_t mt = 0;
     if (max_tile_nnz(c, m, rows, &mt) != PA_OK) return false;
@@ -585,6 +670,8 @@ static bool dot_fusable(pa_mat *A, pa_vec *x) {
   }
   return true;
 }
+// can pa_spmv_dot fuse the dot into the SpMV for this matrix?
+static bool dot_fusable(pa_mat *A, pa_vec *x) { return !pa_knob(A->ctx, "no_dot_fusion", 0) && tma_usable(A, x); }
 
 static int check_mul_args(pa_mat *A, pa_vec *x, pa_vec *y) {
   PA_CHECK(A && x && y, PA_EINVAL, "pa_spmv: null argument");
@@ -625,9 +712,10 @@ int pa_spmv_dot(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, uint
     tma_ok &= A->parts[k].tma_ok;
   }
   // default = the fastest measured on B200 (profiles/r01_multigpu_strategies.md): peer-load gather, then one local SpMV
-  int strategy = (flags & PA_SPMV_INLINE_PEER_LOADS) ? 1 : ((flags & PA_SPMV_OVERLAP) ? 2 : 0);
+  int strategy = (flags & PA_SPMV_INLINE_PEER_LOADS) ? 1 : ((flags & PA_SPMV_OVERLAP) ? 2 : ((flags & PA_SPMV_FUSED_EXCHANGE) ? 3 : 0));
   const int64_t forced = pa_knob(c, "spmv_strategy", -1);
-  if (forced >= 0 && forced <= 2) strategy = (int)forced;
+  if (forced >= 0 && forced <= 3) strategy = (int)forced;
+  if (strategy == 3 && !tma_usable(A, x)) strategy = 0;  // irregular rows / permuted layouts: explicit gather first
   if (!prefix) strategy = 0;                                         // permuted layouts: plain local kernel after consistent!
   if (strategy == 2 && (!tail_ok || !tma_ok || alpha != 1.0 || beta != 0.0 || pa_knob(c, "spmv_kernel", 3) != 3)) strategy = 0;
   if (!any_ghost) strategy = 0;
@@ -639,6 +727,8 @@ int pa_spmv_dot(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, uint
   if (strategy == 0) {
     PA_TRY(pa_launch_consistent(x));
     PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 0, dotw, d_out));
+  } else if (strategy == 3) {
+    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 4, dotw, d_out));  // consistent!(x) happens inside the SpMV kernel
   } else if (strategy == 1) {
     PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 1, dotw, d_out));
     if (!(flags & PA_SPMV_SKIP_GHOST_REFRESH)) PA_TRY(pa_launch_consistent(x));
@@ -682,6 +772,7 @@ static void free_part(MatPart &m) {
   cudaFree(m.d_coo_seg);
   cudaFree(m.d_coo_valid);
   cudaFree(m.d_dotpart);
+  cudaFree(m.d_arrive);
   cudaFree(m.d_grows);
   cudaFree(m.d_rowptr);
   cudaFree(m.d_colval);

@@ -102,7 +102,8 @@ def main():
         o.mul_no_lat(Ao, xo, plan, co)
         x = pa.fill_hash(pa.PVector(A.cols), 9)
         y = pa.pzeros(A.rows)
-        for flags in (pa.PA_SPMV_DEFAULT, pa.PA_SPMV_OVERLAP, pa.PA_SPMV_INLINE_PEER_LOADS, pa.PA_SPMV_INLINE_PEER_LOADS | pa.PA_SPMV_SKIP_GHOST_REFRESH):
+        for flags in (pa.PA_SPMV_DEFAULT, pa.PA_SPMV_FUSED_EXCHANGE, pa.PA_SPMV_OVERLAP, pa.PA_SPMV_INLINE_PEER_LOADS,
+                      pa.PA_SPMV_INLINE_PEER_LOADS | pa.PA_SPMV_SKIP_GHOST_REFRESH, pa.PA_SPMV_FUSED_EXCHANGE):
             y.fill_(-7.0)
             x2 = pa.fill_hash(pa.PVector(A.cols), 9)
             pa.mul_(y, A, x2, flags=flags)
@@ -136,12 +137,14 @@ def main():
                 for p, i in enumerate(part)]
         prob = c_oracle.CGProblem(mats, plan, bo, [np.zeros(i.n_local) for i in part])
         it_o, hist_o, _ = prob.cg(12, 0.0)
-        for flags in (0, pa.PA_CG_REFERENCE_OPS):
+        for flags, strategy in ((0, -1), (pa.PA_CG_REFERENCE_OPS, -1), (0, 3)):  # 3: consistent! fused into the SpMV kernel
+            backend.set_knob("spmv_strategy", strategy)
             xs = pa.pzeros(A.cols)
             res = pa.ref_cg_(xs, A, rhs, tolerance=0.0, maxiter=12, flags=flags)
             np.testing.assert_allclose(res.history, hist_o, rtol=1e-8, atol=1e-12 * hist_o[0])
             np.testing.assert_allclose(xs.local_values()[0][: ind.n_own], prob.x[rank][: ind.n_own], rtol=1e-8, atol=1e-10)
             xs.free()
+        backend.set_knob("spmv_strategy", -1)
         for obj in (x, y, v, rhs):
             obj.free()
         A.free()

@@ -187,8 +187,11 @@ def test_stencil_generator_and_mul_bit_exact(pa, kind, nloc, npd):
     o.mul_no_lat(Ao, xo, plan, co)
     want = o.collect(co, Ao.row_partition)
     y = pa.pzeros(A.rows)
-    for flags in (pa.PA_SPMV_DEFAULT, pa.PA_SPMV_OVERLAP, pa.PA_SPMV_INLINE_PEER_LOADS, pa.PA_SPMV_INLINE_PEER_LOADS | pa.PA_SPMV_SKIP_GHOST_REFRESH):
+    for flags in (pa.PA_SPMV_DEFAULT, pa.PA_SPMV_FUSED_EXCHANGE, pa.PA_SPMV_OVERLAP, pa.PA_SPMV_INLINE_PEER_LOADS,
+                  pa.PA_SPMV_INLINE_PEER_LOADS | pa.PA_SPMV_SKIP_GHOST_REFRESH, pa.PA_SPMV_FUSED_EXCHANGE):
         y.fill_(-1.0)
+        if flags != pa.PA_SPMV_INLINE_PEER_LOADS | pa.PA_SPMV_SKIP_GHOST_REFRESH:
+            pa.fill_hash(x, 3)  # ghosts back to zero: every schedule has to fetch them itself
         pa.mul_(y, A, x, flags=flags)
         assert np.array_equal(y.collect(), want), f"flags={flags}"
     for k in range(P):  # consistent! side effect: ghosts of x hold the owners' values
@@ -255,13 +258,15 @@ def test_cg_history_matches_oracle(pa, kind, nloc, npd):
     it_o, hist_o, _ = prob.cg(maxiter, 0.0)
     bk = seq(pa, len(part))
     A, rhs = pa.stencil_matrix(kind, gn, npd, bk)
-    for flags in (0, pa.PA_CG_REFERENCE_OPS):
+    for flags, strategy in ((0, -1), (pa.PA_CG_REFERENCE_OPS, -1), (0, 3)):  # 3: consistent! fused into the SpMV kernel
+        bk.set_knob("spmv_strategy", strategy)
         x = pa.pzeros(A.cols)
         res = pa.ref_cg_(x, A, rhs, tolerance=0.0, maxiter=maxiter, flags=flags)
         assert res.iters == it_o == maxiter
         np.testing.assert_allclose(res.history, hist_o, rtol=1e-8, atol=1e-12 * hist_o[0])
         np.testing.assert_allclose(np.concatenate(x.own_values()), np.concatenate([prob.x[p][: ind.n_own] for p, ind in enumerate(part)]),
                                    rtol=1e-8, atol=1e-10)
+    bk.set_knob("spmv_strategy", -1)
     # tolerance-driven stop: identical iteration count (tol >= 1e-10)
     prob2 = c_oracle.CGProblem(mats, plan, bo, [np.zeros(ind.n_local) for ind in part])
     it2, hist2, _ = prob2.cg(500, 1e-9)
@@ -375,7 +380,7 @@ def test_irregular_rows_and_fallback_kernel(pa, split):
     o.pmul(Ao, xo, plan, co)
     want = o.collect(co, Ao.row_partition)
     y = pa.pzeros(A.rows)
-    for flags in (pa.PA_SPMV_DEFAULT, pa.PA_SPMV_OVERLAP, pa.PA_SPMV_INLINE_PEER_LOADS):
+    for flags in (pa.PA_SPMV_DEFAULT, pa.PA_SPMV_OVERLAP, pa.PA_SPMV_INLINE_PEER_LOADS, pa.PA_SPMV_FUSED_EXCHANGE):
         for kernel in (3, 1):
             b.set_knob("spmv_kernel", kernel)
             x = pa.pvector_from_global(xg, A.cols)
