@@ -43,7 +43,8 @@ def parse():
     ap.add_argument("--cpu-rows", type=int, default=1 << 24, help="rows of the CPU sample")
     ap.add_argument("--no-hpcg27", action="store_true")
     ap.add_argument("--strong", action="store_true", help="strong scaling: the GLOBAL grid is n^3, split over the parts")
-    ap.add_argument("--mg", action="store_true", help="also time HPCG multigrid-preconditioned CG (27-pt 512^3, 4 levels)")
+    ap.add_argument("--mg", action="store_true", help="(default on) HPCG multigrid-preconditioned CG section (27-pt 512^3, 4 levels)")
+    ap.add_argument("--no-mg", action="store_true", help="skip the multigrid-preconditioned CG section")
     return ap.parse_args()
 
 
@@ -334,7 +335,7 @@ def run_ours(args):
         extra["hpcg27_512"] = {"spmv_ms": ms27, "spmv_gflops": 2 * nnz27 / ms27 / 1e6, "spmv_hbm_gbs": B27 / ms27 / 1e6,
                                "spmv_frac_of_peak": B27 / ms27 / 1e6 / peak, "cg_iters_per_sec": args.iters / (mscg27 * 1e-3),
                                "cg_gflops": (2 * nnz27 + 12 * n_rows) * args.iters / mscg27 / 1e6, "nnz": nnz27}
-        if args.mg:
+        if not args.no_mg:
             # HPCG proper: 4-level multigrid (symmetric Gauss-Seidel) preconditioned CG on the same operator
             for v in (x27, y27, u27, b27):
                 v.free()

@@ -275,6 +275,15 @@ int pa_mg_apply(pa_mg *mg, pa_vec *x, const pa_vec *b);
 int pa_cg_precond(pa_mat *A, pa_vec *x, const pa_vec *b, pa_mg *mg, int32_t maxiter, double tol, uint32_t flags,
                   pa_cg_result *result, double *history);
 
+/* spmv!(b,A,x) / spmtv!(b,A,x) on ONE local matrix in the storage and element types the reference tests
+ * (src/sparse_utils.jl:609-690; test/sparse_utils_tests.jl:14-45,113-118): host arrays in, b out.
+ *   kind 0 = spmv_csr!(b,x,ptr,idx,val) (:649-669): spmv! of a SparseMatrixCSR{Bi}, spmtv! of a SparseMatrixCSC
+ *   kind 1 = spmv_csc!(b,x,ptr,idx,val) (:671-690): spmv! of a SparseMatrixCSC,     spmtv! of a SparseMatrixCSR{Bi}
+ * ncomp = length(ptr)-1; index_base 0/1; idx_bits 32/64 (ptr and idx); val_bits 32/64 (val, x, b: Float32/Float64).
+ * Sequential per-entry multiply and add in the value type, contributions in the reference's order: same bits. */
+int pa_local_spmv(pa_ctx *ctx, int32_t kind, int32_t index_base, int32_t idx_bits, int32_t val_bits, int64_t ncomp, int64_t nb,
+                  const void *ptr, const void *idx, const void *val, const void *x, int64_t nx, void *b);
+
 /* Pinned host memory for the end-to-end path (cudaHostAlloc / cudaFreeHost). */
 int pa_host_alloc(void **ptr, size_t bytes);
 int pa_host_free(void *ptr);

@@ -98,6 +98,7 @@ SIGNATURES = {
     "pa_mg_destroy": [_P],
     "pa_mg_apply": [_P, _P, _P],
     "pa_cg_precond": [_P, _P, _P, _P, _I32, _D, _U32, _P, _P],
+    "pa_local_spmv": [_P, _I32, _I32, _I32, _I32, _I64, _I64, _P, _P, _P, _P, _I64, _P],
     "pa_host_alloc": [_P, C.c_size_t],
     "pa_host_free": [_P],
     # not in the public header: tuning knob used by bench/tests

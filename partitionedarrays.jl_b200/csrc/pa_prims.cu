@@ -306,3 +306,103 @@ extern "C" int pa_vec_reduce_parts(const pa_vec *x, int32_t op, double p, double
   PA_CUDA(cudaStreamSynchronize(c->stream));
   return pa_check_device_error(c);
 }
+
+// ------------------------------------------------------------------ spmv! / spmtv! on ONE local matrix
+// The reference's four local kernels (src/sparse_utils.jl:609-690) for every storage it tests
+// (test/sparse_utils_tests.jl:14-45,113-118: CSC / CSR{1} / CSR{0} x (Float64,Int) / (Float32,Int32)):
+//   kind 0 = spmv_csr!(b,x,ptr,idx,val)   b[i] = sum_p val[p]*x[idx[p]], p in storage order            (:649-669)
+//   kind 1 = spmv_csc!(b,x,ptr,idx,val)   b = 0; for j, p: b[idx[p]] += val[p]*x[j]                    (:671-690)
+// spmv!(CSR) = kind 0 on (rowptr,colval); spmtv!(CSR) = kind 1 on (rowptr,colval); spmv!(CSC) = kind 1 on (colptr,rowval);
+// spmtv!(CSC) = kind 0 on (colptr,rowval) (:617-647).  Kind 1 is executed as a gather: the entries are transposed on the host
+// with a stable counting sort, so that every b[i] receives its contributions in the order of the reference's scatter loop
+// (ascending j, then storage order) -- same bits.  Separate multiply and add in the value type, like Julia's bi += aij*xj.
+template <typename T>
+__device__ __forceinline__ T mul_add_seq(T acc, T a, T x);
+template <>
+__device__ __forceinline__ double mul_add_seq<double>(double acc, double a, double x) { return __dadd_rn(acc, __dmul_rn(a, x)); }
+template <>
+__device__ __forceinline__ float mul_add_seq<float>(float acc, float a, float x) { return __fadd_rn(acc, __fmul_rn(a, x)); }
+
+template <typename T>
+__global__ void k_local_spmv(const int64_t *__restrict__ ptr, const int64_t *__restrict__ idx, const T *__restrict__ val, const T *__restrict__ x,
+                             T *__restrict__ b, int64_t nb) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += (int64_t)gridDim.x * blockDim.x) {
+    T acc = (T)0;
+    for (int64_t p = ptr[i]; p < ptr[i + 1]; ++p) acc = mul_add_seq<T>(acc, val[p], x[idx[p]]);
+    b[i] = acc;
+  }
+}
+
+template <typename T>
+static int local_spmv_run(pa_ctx *c, const std::vector<int64_t> &ptr, const std::vector<int64_t> &idx, const T *val, const std::vector<int64_t> &vperm,
+                          const T *x, int64_t nx, T *b, int64_t nb) {
+  const int64_t nnz = (int64_t)idx.size();
+  std::vector<T> v(nnz);
+  for (int64_t p = 0; p < nnz; ++p) v[p] = val[vperm.empty() ? p : vperm[p]];
+  int64_t *d_ptr = nullptr, *d_idx = nullptr;
+  T *d_val = nullptr, *d_x = nullptr, *d_b = nullptr;
+  PA_CUDA(cudaMalloc((void **)&d_ptr, (nb + 1) * sizeof(int64_t)));
+  PA_CUDA(cudaMalloc((void **)&d_idx, std::max<int64_t>(nnz, 1) * sizeof(int64_t)));
+  PA_CUDA(cudaMalloc((void **)&d_val, std::max<int64_t>(nnz, 1) * sizeof(T)));
+  PA_CUDA(cudaMalloc((void **)&d_x, std::max<int64_t>(nx, 1) * sizeof(T)));
+  PA_CUDA(cudaMalloc((void **)&d_b, std::max<int64_t>(nb, 1) * sizeof(T)));
+  PA_CUDA(cudaMemcpyAsync(d_ptr, ptr.data(), (nb + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+  if (nnz) {
+    PA_CUDA(cudaMemcpyAsync(d_idx, idx.data(), nnz * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    PA_CUDA(cudaMemcpyAsync(d_val, v.data(), nnz * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  }
+  if (nx) PA_CUDA(cudaMemcpyAsync(d_x, x, nx * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  if (nb) {
+    k_local_spmv<T><<<(unsigned)std::min<int64_t>((nb + 255) / 256, 148 * 8), 256, 0, c->stream>>>(d_ptr, d_idx, d_val, d_x, d_b, nb);
+    c->launches++;
+    PA_CUDA(cudaGetLastError());
+    PA_CUDA(cudaMemcpyAsync(b, d_b, nb * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+  }
+  PA_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_ptr); cudaFree(d_idx); cudaFree(d_val); cudaFree(d_x); cudaFree(d_b);
+  return PA_OK;
+}
+
+extern "C" int pa_local_spmv(pa_ctx *c, int32_t kind, int32_t index_base, int32_t idx_bits, int32_t val_bits, int64_t ncomp, int64_t nb,
+                             const void *ptr, const void *idx, const void *val, const void *x, int64_t nx, void *b) {
+  PA_CHECK(c && ptr && b && (kind == 0 || kind == 1) && (index_base == 0 || index_base == 1) && (idx_bits == 32 || idx_bits == 64) &&
+               (val_bits == 32 || val_bits == 64) && ncomp >= 0 && nb >= 0 && nx >= 0,
+           PA_EINVAL, "pa_local_spmv: bad arguments");
+  // dimension asserts of spmv!/spmtv! (src/sparse_utils.jl:618-621): kind 0 writes one entry per compressed row
+  PA_CHECK(kind == 1 || nb == ncomp, PA_EINVAL, "pa_local_spmv: length(b) = %lld, the matrix has %lld rows", (long long)nb, (long long)ncomp);
+  PA_CHECK(kind == 0 || nx == ncomp, PA_EINVAL, "pa_local_spmv: length(x) = %lld, the matrix has %lld columns", (long long)nx, (long long)ncomp);
+  PA_CUDA(cudaSetDevice(c->device));
+  auto rd = [&](const void *p, int64_t i) { return idx_bits == 64 ? ((const int64_t *)p)[i] : (int64_t)((const int32_t *)p)[i]; };
+  std::vector<int64_t> p0(ncomp + 1);
+  for (int64_t i = 0; i <= ncomp; ++i) p0[i] = rd(ptr, i) - index_base;
+  PA_CHECK(p0[0] == 0, PA_EINVAL, "pa_local_spmv: ptr does not start at the index base");
+  for (int64_t i = 0; i < ncomp; ++i) PA_CHECK(p0[i + 1] >= p0[i], PA_EINVAL, "pa_local_spmv: ptr not monotone");
+  const int64_t nnz = p0[ncomp];
+  PA_CHECK(nnz == 0 || (idx && val && x), PA_EINVAL, "pa_local_spmv: null array");
+  std::vector<int64_t> i0(nnz);
+  const int64_t bound = kind == 0 ? nx : nb;
+  for (int64_t p = 0; p < nnz; ++p) {
+    i0[p] = rd(idx, p) - index_base;
+    PA_CHECK(i0[p] >= 0 && i0[p] < bound, PA_EINVAL, "pa_local_spmv: index %lld out of range", (long long)(i0[p] + index_base));
+  }
+  std::vector<int64_t> gptr, gidx, perm;
+  if (kind == 0) {
+    gptr = p0;
+    gidx = i0;
+  } else {  // stable transpose: entries of b[i] in ascending (j, p) = the order of the scatter loop
+    gptr.assign(nb + 1, 0);
+    for (int64_t p = 0; p < nnz; ++p) gptr[i0[p] + 1]++;
+    for (int64_t i = 0; i < nb; ++i) gptr[i + 1] += gptr[i];
+    gidx.resize(nnz);
+    perm.resize(nnz);
+    std::vector<int64_t> at(gptr.begin(), gptr.end() - 1);
+    for (int64_t j = 0; j < ncomp; ++j)
+      for (int64_t p = p0[j]; p < p0[j + 1]; ++p) {
+        const int64_t q = at[i0[p]]++;
+        gidx[q] = j;
+        perm[q] = p;
+      }
+  }
+  if (val_bits == 64) return local_spmv_run<double>(c, gptr, gidx, (const double *)val, perm, (const double *)x, nx, (double *)b, nb);
+  return local_spmv_run<float>(c, gptr, gidx, (const float *)val, perm, (const float *)x, nx, (float *)b, nb);
+}

@@ -560,6 +560,31 @@ class PSparseMatrix:
             pass
 
 
+def _local_spmv(backend: CUDAArray, kind: int, ptr_, idx, val, x, nb: int, index_base: int) -> np.ndarray:
+    ptr_, idx, val, x = (np.ascontiguousarray(a) for a in (ptr_, idx, val, x))
+    if ptr_.dtype != idx.dtype or ptr_.dtype not in (np.int32, np.int64):
+        raise TypeError("spmv!: ptr and idx must both be Int32 or Int64")
+    if val.dtype != x.dtype or val.dtype not in (np.float32, np.float64):
+        raise TypeError("spmv!: values and x must both be Float32 or Float64")
+    out = np.empty(nb, dtype=val.dtype)
+    check(_capi.lib().pa_local_spmv(backend.h, kind, index_base, ptr_.dtype.itemsize * 8, val.dtype.itemsize * 8, len(ptr_) - 1, nb,
+                                    ptr(ptr_), ptr(idx), ptr(val), ptr(x), len(x), ptr(out)))
+    return out
+
+
+def spmv_(backend: CUDAArray, fmt: str, ptr_, idx, val, x, m: int, n: int, index_base: int = 1) -> np.ndarray:
+    """b = spmv!(b, A, x) for one local m x n matrix (src/sparse_utils.jl:617-640): fmt 'csr' (ptr_=rowptr, idx=colval) or
+    'csc' (ptr_=colptr, idx=rowval); Float64/Float32 values, Int32/Int64 indices, index_base 1 (Julia) or 0 (CSR{0})."""
+    assert len(x) == n and len(ptr_) - 1 == (m if fmt == "csr" else n)
+    return _local_spmv(backend, 0 if fmt == "csr" else 1, ptr_, idx, val, x, m, index_base)
+
+
+def spmtv_(backend: CUDAArray, fmt: str, ptr_, idx, val, x, m: int, n: int, index_base: int = 1) -> np.ndarray:
+    """b = spmtv!(b, A, x) = transpose(A)*x for one local m x n matrix (src/sparse_utils.jl:626-647)."""
+    assert len(x) == m and len(ptr_) - 1 == (m if fmt == "csr" else n)
+    return _local_spmv(backend, 1 if fmt == "csr" else 0, ptr_, idx, val, x, n, index_base)
+
+
 def mul_(c: PVector, A: PSparseMatrix, b: PVector, alpha: float = 1.0, beta: float = 0.0, flags: int = 0) -> PVector:
     """mul!(c,A,b[,alpha,beta]) (src/p_sparse_matrix.jl:2090-2142)."""
     check(_capi.lib().pa_spmv(A.h, b.h, c.h, float(alpha), float(beta), flags))

@@ -102,3 +102,78 @@ def test_reduce_maximum_minimum_norm_p(pa):
     with pytest.raises(ValueError):
         x.norm(0.5)
     b.close()
+
+
+def _compress(I, J, V, m, n, fmt):
+    """compresscoo (src/sparse_utils.jl:313-350) on the host: entries sorted, duplicates summed in input order; 0-based."""
+    maj, mnr, nmaj = (I, J, m) if fmt == "csr" else (J, I, n)
+    order = sorted(range(len(I)), key=lambda t: (maj[t], mnr[t]))  # stable
+    ptr_, idx, val = [0] * (nmaj + 1), [], []
+    last = None
+    for t in order:
+        if last == (maj[t], mnr[t]):
+            val[-1] = val[-1] + V[t]
+        else:
+            idx.append(mnr[t] - 1)
+            val.append(V[t])
+            ptr_[maj[t]] += 1
+            last = (maj[t], mnr[t])
+    return np.cumsum([0] + ptr_[1:]).tolist(), idx, val
+
+
+@pytest.mark.parametrize("Tv,Ti", [(np.float64, np.int64), (np.float32, np.int32), (np.float64, np.int32)])
+@pytest.mark.parametrize("fmt,base", [("csc", 1), ("csr", 1), ("csr", 0)])
+def test_local_spmv_spmtv_golden_7x6(pa, fmt, base, Tv, Ti):
+    """test/sparse_utils_tests.jl:14-45,113-118: I=[1,2,5,4,1], J=[3,6,1,1,3], V=[4,5,3,2,5], 7x6, x=1:n; spmv! == mul!,
+    spmtv! == transpose mul!, for SparseMatrixCSC / SparseMatrixCSR{1} / SparseMatrixCSR{0} x (Float64,Int) / (Float32,Int32)."""
+    b = pa.CUDAArray(1, arena_bytes=1 << 20)
+    I, J, V, m, n = [1, 2, 5, 4, 1], [3, 6, 1, 1, 3], [4, 5, 3, 2, 5], 7, 6
+    p0, i0, v0 = _compress(I, J, [Tv(v) for v in V], m, n, fmt)
+    ptr_, idx, val = np.array(p0, dtype=Ti) + base, np.array(i0, dtype=Ti) + base, np.array(v0, dtype=Tv)
+    dense = np.zeros((m, n))
+    for i, j, v in zip(I, J, V):
+        dense[i - 1, j - 1] += v
+    x = np.arange(1, n + 1, dtype=Tv)
+    got = pa.spmv_(b, fmt, ptr_, idx, val, x, m, n, index_base=base)
+    assert got.dtype == Tv and got.tolist() == (dense @ x).tolist()  # small integers: exact in both precisions
+    xt = np.arange(1, m + 1, dtype=Tv)
+    got = pa.spmtv_(b, fmt, ptr_, idx, val, xt, m, n, index_base=base)
+    assert got.dtype == Tv and got.tolist() == (dense.T @ xt).tolist()
+    with pytest.raises(pa.PAError):
+        pa._capi.check(pa._capi.lib().pa_local_spmv(b.h, 0, base, ptr_.dtype.itemsize * 8, val.dtype.itemsize * 8, len(ptr_) - 1, 3,
+                                                    pa._capi.ptr(ptr_), pa._capi.ptr(idx), pa._capi.ptr(val), pa._capi.ptr(x), len(x),
+                                                    pa._capi.ptr(np.zeros(3, dtype=Tv))))  # length(b) != size(A,1)
+    b.close()
+
+
+@pytest.mark.parametrize("Tv", [np.float64, np.float32])
+def test_local_spmv_random_bit_exact_vs_sequential_loops(pa, Tv):
+    """Random rectangular matrices: same bits as the reference loops run in the same element type (spmv_csr!: bi += aij*xj
+    in storage order; spmv_csc!: b[row] += aij*xj column by column)."""
+    rng = np.random.default_rng(5)
+    b = pa.CUDAArray(1, arena_bytes=1 << 20)
+    m, n, nnz = 301, 257, 4000
+    I, J = rng.integers(1, m + 1, nnz).tolist(), rng.integers(1, n + 1, nnz).tolist()
+    V = rng.standard_normal(nnz).astype(Tv)
+    for fmt in ("csr", "csc"):
+        p0, i0, v0 = _compress(I, J, list(V), m, n, fmt)
+        ptr_, idx, val = np.array(p0, dtype=np.int32) + 1, np.array(i0, dtype=np.int32) + 1, np.array(v0, dtype=Tv)
+        for transpose in (False, True):
+            x = rng.standard_normal(m if transpose else n).astype(Tv)
+            gather = (fmt == "csr") != transpose  # spmv_csr! on the stored arrays, else spmv_csc!
+            nb = n if transpose else m
+            want = np.zeros(nb, dtype=Tv)
+            if gather:
+                for i in range(len(ptr_) - 1):
+                    acc = Tv(0)
+                    for p in range(ptr_[i] - 1, ptr_[i + 1] - 1):
+                        acc = Tv(acc + Tv(val[p] * x[idx[p] - 1]))
+                    want[i] = acc
+            else:
+                for j in range(len(ptr_) - 1):
+                    for p in range(ptr_[j] - 1, ptr_[j + 1] - 1):
+                        want[idx[p] - 1] = Tv(want[idx[p] - 1] + Tv(val[p] * x[j]))
+            f = pa.spmtv_ if transpose else pa.spmv_
+            got = f(b, fmt, ptr_, idx, val, x, m, n)
+            assert np.array_equal(got, want), (fmt, transpose)
+    b.close()
