@@ -21,6 +21,9 @@
 #include "pa_internal.h"
 
 #define GS_THREADS 256
+#ifndef GS_MINB8
+#define GS_MINB8 4  // resident CTAs per SM of the 8-lanes-per-row kernel: 64 registers (4 bytes of spill); 3 CTAs = 76 registers
+#endif
 #define GS_SPIN_LIMIT (20000000000LL)  // ~10 s of SM cycles, then give up and flag an error instead of hanging
 
 struct GsPart {
@@ -73,6 +76,7 @@ struct GsArgs {
   int *err;
   int64_t n, npad;
   int epoch, backward, zero_guess, prefetch;
+  int keep;  // mark x and the published pairs evict-last in L2 (they are re-read by the rows of the next 7 levels)
 };
 
 // Publishing a row: the new value travels WITH its "done in this sweep" mark, so a waiting reader needs one
@@ -80,11 +84,11 @@ struct GsArgs {
 // words, each carrying the sweep epoch in its upper half ({lo32, epoch}, {hi32, epoch}); an aligned 8-byte
 // store is single-copy atomic, so a reader that sees the current epoch in BOTH words has both halves of the
 // new value, however the 16-byte access is split on the way.
-__device__ __forceinline__ double gs_wait_value(const ulonglong2 *slot, unsigned epoch, int *err) {
+__device__ __forceinline__ double gs_wait_value(const ulonglong2 *slot, unsigned epoch, int *err, uint64_t keep) {
   unsigned long long w0, w1;
   long long t0 = 0;
   for (;;) {
-    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+    asm volatile("ld.relaxed.gpu.global.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(w0), "=l"(w1) : "l"(slot), "l"(keep) : "memory");
     if ((unsigned)(w0 >> 32) == epoch && (unsigned)(w1 >> 32) == epoch) break;
     if (!t0) {
       t0 = clock64();
@@ -95,10 +99,24 @@ __device__ __forceinline__ double gs_wait_value(const ulonglong2 *slot, unsigned
   }
   return __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
 }
-__device__ __forceinline__ void gs_publish(ulonglong2 *slot, double *x, double s, unsigned epoch) {
+__device__ __forceinline__ void gs_publish(ulonglong2 *slot, double *x, double s, unsigned epoch, uint64_t keep) {
   const unsigned long long bits = (unsigned long long)__double_as_longlong(s), e = (unsigned long long)epoch << 32;
-  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"((bits & 0xffffffffull) | e), "l"((bits >> 32) | e) : "memory");
+  asm volatile("st.relaxed.gpu.global.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;" ::"l"(slot), "l"((bits & 0xffffffffull) | e), "l"((bits >> 32) | e), "l"(keep)
+               : "memory");
   *x = s;  // the plain vector: read by later rows as an OLD value never, by the next kernels always
+}
+// x changes during the sweep: always through L2; the rows of the neighbouring levels come back for the same sectors
+__device__ __forceinline__ double gs_ld_x(const double *p, uint64_t keep) {
+  double v;
+  asm volatile("ld.global.cg.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(keep));
+  return v;
+}
+// L2 retention of x and the published (value, epoch) pairs: evict-last when asked for, else no preference
+__device__ __forceinline__ uint64_t gs_keep_policy(int keep) {
+  uint64_t pol;
+  if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
 }
 
 // The matrix is read once per sweep and is two orders of magnitude larger than x: marked evict-first in L2 so
@@ -127,7 +145,7 @@ __global__ void __launch_bounds__(GS_THREADS) k_gs_flow(const GsArgs<PtrT> a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t W = (int64_t)gridDim.x * (GS_THREADS / 32);
   const int64_t w = (int64_t)blockIdx.x * (GS_THREADS / 32) + warp;
-  const uint64_t pol = gs_stream_policy();
+  const uint64_t pol = gs_stream_policy(), keep = gs_keep_policy(a.keep);
   for (int64_t pos = w; pos < a.npad; pos += W) {
     const int64_t row = a.backward ? a.rows[a.npad - 1 - pos] : a.rows[pos];
     if (row < 0) continue;
@@ -146,8 +164,8 @@ __global__ void __launch_bounds__(GS_THREADS) k_gs_flow(const GsArgs<PtrT> a) {
       // NEW value needed: an own row that precedes this one in the sweep order
       const bool fresh = use && col < a.n && (a.backward ? col > row : col < row);
       double xv = 0.0;
-      if (fresh) xv = gs_wait_value(a.xe + col, (unsigned)a.epoch, a.err);
-      else if (use) xv = __ldcg(a.x + col);  // x changes during the sweep: always through L2
+      if (fresh) xv = gs_wait_value(a.xe + col, (unsigned)a.epoch, a.err, keep);
+      else if (use) xv = gs_ld_x(a.x + col, keep);
       prod[warp][lane] = __dmul_rn(v, xv);
       const unsigned usemask = __ballot_sync(0xffffffffu, use);
       const unsigned dmask = __ballot_sync(0xffffffffu, valid && col == row);
@@ -165,7 +183,7 @@ __global__ void __launch_bounds__(GS_THREADS) k_gs_flow(const GsArgs<PtrT> a) {
     if (lane == 0) {
       if (!a.zero_guess) s = __dadd_rn(s, __dmul_rn(d, xold));  // s += d*x[row]
       s = __ddiv_rn(s, d);
-      gs_publish(a.xe + row, a.x + row, s, (unsigned)a.epoch);
+      gs_publish(a.xe + row, a.x + row, s, (unsigned)a.epoch, keep);
     }
   }
 }
@@ -177,7 +195,7 @@ __global__ void __launch_bounds__(GS_THREADS) k_gs_flow(const GsArgs<PtrT> a) {
 // (x_old and the entries can be fetched early: nobody writes x[row] before this row does, and a row's
 // coefficients are constant.)  Same arithmetic, same order as k_gs_flow.
 template <typename PtrT, int G>
-__global__ void __launch_bounds__(GS_THREADS, (G >= 16 ? 6 : (G == 8 ? 3 : 2))) k_gs_flow_pipe(const GsArgs<PtrT> a) {
+__global__ void __launch_bounds__(GS_THREADS, (G >= 16 ? 6 : (G == 8 ? GS_MINB8 : 2))) k_gs_flow_pipe(const GsArgs<PtrT> a) {
   constexpr int NJ = 32 / G;   // entries per lane
   constexpr int RPW = 32 / G;  // rows per warp
   constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
@@ -191,7 +209,7 @@ __global__ void __launch_bounds__(GS_THREADS, (G >= 16 ? 6 : (G == 8 ? 3 : 2))) 
   const int64_t np = a.npad;
   const int64_t niter = (np + W - 1) / W;
   const unsigned epoch = (unsigned)a.epoch;
-  const uint64_t pol = gs_stream_policy();
+  const uint64_t pol = gs_stream_policy(), keep = gs_keep_policy(a.keep);
   auto row_at = [&](int64_t pos) -> int32_t { return pos < np ? a.rows[a.backward ? np - 1 - pos : pos] : -1; };
   auto extent = [&](int32_t r, int64_t &ps, int &cnt) {
     ps = 0;
@@ -217,7 +235,7 @@ __global__ void __launch_bounds__(GS_THREADS, (G >= 16 ? 6 : (G == 8 ? 3 : 2))) 
   }
   if (hl == 0 && rC >= 0) {
     bC = a.b[rC];
-    xoC = __ldcg(a.x + rC);
+    xoC = gs_ld_x(a.x + rC, keep);
   }
   for (int64_t it = 0; it < niter; ++it) {
     // ---- issue the loads of the next stages
@@ -235,7 +253,7 @@ __global__ void __launch_bounds__(GS_THREADS, (G >= 16 ? 6 : (G == 8 ? 3 : 2))) 
     }
     if (hl == 0 && rB >= 0) {
       bB = a.b[rB];
-      xoB = __ldcg(a.x + rB);
+      xoB = gs_ld_x(a.x + rB, keep);
     }
     // ---- the row of this iteration
     const int32_t row = rC;
@@ -247,11 +265,11 @@ __global__ void __launch_bounds__(GS_THREADS, (G >= 16 ? 6 : (G == 8 ? 3 : 2))) 
       use[j] = col >= 0 && (!a.zero_guess || col < row);
       // NEW value needed: an own row that precedes this one in the sweep order
       fresh[j] = use[j] && col < a.n && (a.backward ? col > row : col < row);
-      xv[j] = (use[j] && !fresh[j]) ? __ldcg(a.x + col) : 0.0;  // OLD values and ghosts: through L2
+      xv[j] = (use[j] && !fresh[j]) ? gs_ld_x(a.x + col, keep) : 0.0;  // OLD values and ghosts
     }
 #pragma unroll
     for (int j = 0; j < NJ; ++j)
-      if (fresh[j]) xv[j] = gs_wait_value(a.xe + colC[j], epoch, a.err);
+      if (fresh[j]) xv[j] = gs_wait_value(a.xe + colC[j], epoch, a.err, keep);
     double d = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
@@ -276,7 +294,7 @@ __global__ void __launch_bounds__(GS_THREADS, (G >= 16 ? 6 : (G == 8 ? 3 : 2))) 
       }
       if (!a.zero_guess) s = __dadd_rn(s, __dmul_rn(d, xoC));  // s += d*x[row]
       s = __ddiv_rn(s, d);
-      gs_publish(a.xe + row, a.x + row, s, epoch);
+      gs_publish(a.xe + row, a.x + row, s, epoch, keep);
     }
     __syncwarp();
     // ---- rotate the pipeline
@@ -726,7 +744,7 @@ extern "C" int pa_gs_destroy(pa_gs *g) {
 // levels are wide enough to be throughput bound, 32 where the sweep is bound by the level-to-level hop; 0 = the
 // unpipelined warp-per-row kernel (any row length).
 // Measured on B200 (27-pt, symmetric sweep, ms):   rows      4 lanes   8 lanes   16 lanes   32 lanes
-//                                                  134.2M     73.6      60.1      73.3        -
+//                                                  134.2M     73.6      58.0      73.3        -     (8 lanes: 60.1 at 3 CTAs/SM)
 //                                                   16.8M     21.8      12.5      11.3       13.5
 //                                                    2.1M     10.4       5.8       5.0        2.2 (3.7 before the pipeline)
 //                                                    262k      5.0       2.7        -         0.9
@@ -760,6 +778,7 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
       a.backward = backward;
       a.zero_guess = zero_guess;
       a.prefetch = (int)pa_knob(c, "gs_prefetch", 1);
+      a.keep = (int)pa_knob(c, "gs_keep", 1);
       int nsm = 148;
       cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
       // batch kernel (32 rows of one level per warp) where the levels are wide; the warp-per-row dataflow kernel where

@@ -400,7 +400,8 @@ static int signal_all(pa_plan *plan, bool done) {
     const PlanPart &pp = plan->parts[k];
     int n = (int)pp.nbrs.size();
     // a part without neighbours in THIS collective still counts it: the epochs of all parts advance in lockstep
-    if (!n && done) continue;
+    // (a job of one part has nobody to stay in step with: no launch at all)
+    if (!n && (done || c->nparts == 1)) continue;
     FlagPtrs dst;
     for (int i = 0; i < n; ++i) {
       PA_CHECK(c->peer_base[pp.nbrs[i]], PA_ESTATE, "part %d's arena was never imported (pa_ctx_arena_import)", pp.nbrs[i] + 1);
@@ -457,6 +458,7 @@ int pa_collective_begin(pa_plan *plan) {
   if (c->nlocal == 1) {
     const PlanPart &pp = plan->parts[0];
     const int n = (int)pp.nbrs.size();
+    if (!n && c->nparts == 1) return PA_OK;  // one part in the whole job: nothing to order
     FlagPtrs dst, src;
     for (int i = 0; i < n; ++i) {
       PA_CHECK(c->peer_base[pp.nbrs[i]], PA_ESTATE, "part %d's arena was never imported (pa_ctx_arena_import)", pp.nbrs[i] + 1);
