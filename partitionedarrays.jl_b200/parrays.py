@@ -416,6 +416,28 @@ def _ptrs1(lengths) -> np.ndarray:
     return out
 
 
+def exchange_layout(graph: ExchangeGraph, snd_len: Sequence[Sequence[int]]):
+    """allocate_exchange (src/primitives.jl:921-947) on the host: from the send lengths of every local part, the receive
+    lengths (= what each source sends here) and, for every source, where the segment addressed to this part starts inside
+    the SOURCE's send buffer (the address a receiver pulls from).  One all-gather of the send ids and lengths.
+    Returns (rcv_len, rcv_src_off, sym_snd_len) with one list per local part."""
+    b = graph.backend
+    all_snd_ids, all_snd_len = b.gather_all(graph.snd), b.gather_all([list(map(int, l)) for l in snd_len])
+    rcv_len, rcv_off = [], []
+    for k, me in enumerate(b.parts):
+        rl, off = [], []
+        for src in graph.rcv[k]:
+            ids = list(all_snd_ids[src - 1])
+            if me not in ids:
+                raise ValueError(f"exchange: graph not consistent (part {me} receives from {src}, which does not send to it)")
+            j = ids.index(me)
+            rl.append(int(all_snd_len[src - 1][j]))
+            off.append(int(sum(all_snd_len[src - 1][:j])))
+        rcv_len.append(rl)
+        rcv_off.append(off)
+    return rcv_len, rcv_off, max([sum(l) for l in all_snd_len] + [0])
+
+
 def exchange(snd: Sequence[Sequence], graph: ExchangeGraph) -> List[List[np.ndarray]]:
     """rcv = fetch(exchange(snd, graph)) (src/primitives.jl:876-925, 992-1042): ``snd[k][j]`` (a scalar or a vector of
     Float64 / Int64) goes to part ``graph.snd[k][j]``; ``rcv[k][i]`` is what part ``graph.rcv[k][i]`` sent here.  The
@@ -431,26 +453,14 @@ def exchange(snd: Sequence[Sequence], graph: ExchangeGraph) -> List[List[np.ndar
         if len(segs[k]) != len(graph.snd[k]):
             raise ValueError("exchange: one send item per destination")
     snd_len = [[len(a) for a in s] for s in segs]
-    # allocate_exchange (src/primitives.jl:921-947): the receive lengths are the senders' send lengths
-    all_snd_ids, all_snd_len = b.gather_all(graph.snd), b.gather_all(snd_len)
+    rcv_len, rcv_off, sym = exchange_layout(graph, snd_len)
     h = C.c_void_p()
     check(L.pa_xchg_create(b.h, C.byref(h)))
-    rcv_len = []
     try:
-        for k, me in enumerate(b.parts):
-            rl, off = [], []
-            for src in graph.rcv[k]:
-                ids = all_snd_ids[src - 1]
-                if me not in ids:
-                    raise ValueError(f"exchange: graph not consistent (part {me} receives from {src}, which does not send to it)")
-                j = ids.index(me)
-                rl.append(all_snd_len[src - 1][j])
-                off.append(int(sum(all_snd_len[src - 1][:j])))
-            rcv_len.append(rl)
+        for k in range(nl):
             si, ri = i32(graph.snd[k]), i32(graph.rcv[k])
-            sp, rp, so = _ptrs1(snd_len[k]), _ptrs1(rl), i64(off)
+            sp, rp, so = _ptrs1(snd_len[k]), _ptrs1(rcv_len[k]), i64(rcv_off[k])
             check(L.pa_xchg_set_part(h, k, len(si), ptr(si), ptr(sp), len(ri), ptr(ri), ptr(rp), ptr(so)))
-        sym = max([sum(l) for l in all_snd_len] + [0])
         check(L.pa_xchg_commit(h, sym))
         for k in range(nl):
             flat = np.ascontiguousarray(np.concatenate([a.astype(dtype) for a in segs[k]]) if segs[k] else np.zeros(0, dtype=dtype))

@@ -67,6 +67,23 @@ def main():
             oplan = o.assembly_plan(Ao.col_partition)
             assert plan.snd_lids.tolist() == oplan.local_indices_snd[rank].data.tolist()
             assert plan.rcv_lids.tolist() == oplan.local_indices_rcv[rank].data.tolist()
+        # exchange primitive, host side: receive ids and buffer layout over a real all-gather (one part per process)
+        class _Meta:
+            parts = [rank + 1]
+
+            @staticmethod
+            def gather_all(objs):
+                return gather_all(objs)
+
+        snd_all = [[q for q in range(1, world + 1) if q != p] for p in range(1, world + 1)]  # everybody sends to everybody else
+        len_all = [[3 * p + q for q in s] for p, s in enumerate(snd_all, 1)]
+        g = pa.ExchangeGraph(_Meta, [snd_all[rank]])
+        assert g.rcv == [o.find_rcv_ids(snd_all)[rank]]
+        rcv_len, rcv_off, sym = pa.exchange_layout(g, [len_all[rank]])
+        assert sym == max(sum(l) for l in len_all)
+        for i, src in enumerate(g.rcv[0]):
+            j = snd_all[src - 1].index(rank + 1)
+            assert rcv_len[0][i] == len_all[src - 1][j] and rcv_off[0][i] == sum(len_all[src - 1][:j])
         dist.barrier()
         if rank == 0:
             print("GLOO_WORKER_OK")
