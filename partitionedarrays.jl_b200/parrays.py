@@ -648,7 +648,7 @@ def _csr_to_csc(rp, cv, nz, ncols):
 
 
 def psparse(I: List, J: List, V: List, rows: PRange, cols: PRange, assembled: bool = True, split_format: bool = True,
-            local_format: str = "csr", compress: str = "host") -> PSparseMatrix:
+            local_format: str = "csr", compress: str = "host", ship: str = "host") -> PSparseMatrix:
     """psparse([T,] I,J,V,row_partition,col_partition; assembled=true) (src/p_sparse_matrix.jl:1150-1286).
     local_format: "csr" = SparseMatrixCSR{1,Float64,Int32} local matrices; "csc" = the reference's default
     SparseMatrixCSC{Float64,Int} (converted to CSR at upload, summation order of spmv_csc! preserved).
@@ -658,7 +658,7 @@ def psparse(I: List, J: List, V: List, rows: PRange, cols: PRange, assembled: bo
     The COO->CSR compression runs on the host at setup time (on-device compression is 'next')."""
     b = rows.backend
     if not assembled:
-        return _psparse_disassembled(I, J, V, rows, cols, split_format, local_format, compress)
+        return _psparse_disassembled(I, J, V, rows, cols, split_format, local_format, compress, ship)
     new_cols = []
     for ind_c, j in zip(cols.indices, J):
         j = np.asarray(j, dtype=np.int64)
@@ -732,7 +732,31 @@ def _stored_entries(li, lj, v, m, n, fmt):
     return li[new], lj[new], nz
 
 
-def _psparse_disassembled(I, J, V, rows: PRange, cols: PRange, split_format: bool, local_format: str, compress: str) -> PSparseMatrix:
+def _ship_ghost_rows(b: CUDAArray, outgoing, ship: str):
+    """The entries of ghost rows travel to the row owners (assemble, src/p_sparse_matrix.jl:1590-1756): ``outgoing[k]`` =
+    (my part id, {destination part: (gi, gj, v)}).  Returns per local part the received (gi, gj, v), sender by sender in
+    ascending part order.  ship='host': the metadata channel (an all-gather of everything, setup-time only);
+    ship='device': three exchange! calls (I, J as Int64, V as Float64) -- every owner pulls exactly its segments from the
+    senders' HBM (pa_xchg_*), nothing is broadcast."""
+    if ship == "host":
+        everyone = dict(b.gather_all(outgoing))
+        out = []
+        for me, _ in outgoing:
+            rcv = [everyone[q][me] for q in sorted(everyone) if q != me and me in everyone[q]]
+            out.append(tuple(np.concatenate([x[t] for x in rcv]) if rcv else np.zeros(0, np.float64 if t == 2 else np.int64) for t in range(3)))
+        return out
+    if ship != "device":
+        raise ValueError("ship must be 'host' or 'device'")
+    dests = [sorted(dst.keys()) for _, dst in outgoing]
+    graph = ExchangeGraph(b, dests)  # receive sides: sources in ascending order (default_find_rcv_ids)
+    parts = []
+    for t, dt in ((0, np.int64), (1, np.int64), (2, np.float64)):
+        rcv = exchange([[np.asarray(dst[q][t], dtype=dt) for q in d] for (_, dst), d in zip(outgoing, dests)], graph)
+        parts.append([np.concatenate(r).astype(dt) if r else np.zeros(0, dt) for r in rcv])
+    return [tuple(parts[t][k] for t in range(3)) for k in range(len(outgoing))]
+
+
+def _psparse_disassembled(I, J, V, rows: PRange, cols: PRange, split_format: bool, local_format: str, compress: str, ship: str = "host") -> PSparseMatrix:
     """Disassembled input, the reference's default (src/p_sparse_matrix.jl:1186-1222, then split_format :823-899 and
     assemble :1590-1756), reproduced stage by stage because the stages fix both how the sums associate and how the ghost
     columns are numbered (= the order of the terms in every row of the ghost block):
@@ -741,8 +765,8 @@ def _psparse_disassembled(I, J, V, rows: PRange, cols: PRange, split_format: boo
       ghost_ghost block, each in storage order -- go to the row owners; an owner appends what it receives, sender by
       sender in ascending part order, to the stored entries of its own rows (own_own / own_ghost lists), numbers the
       ghost columns by first appearance in the own_ghost list and compresses again: own sum + sender sums in order.
-    This is setup-time index work on the host (the triplets travel through the metadata channel); the final compression
-    runs on the device with compress="device"."""
+    This is setup-time index work on the host; the ghost-row entries travel through the metadata channel (ship="host") or
+    through the device exchange! (ship="device"); the final compression runs on the device with compress="device"."""
     b = rows.backend
     if local_format not in ("csr", "csc"):
         raise ValueError("local_format must be 'csr' or 'csc'")
@@ -766,14 +790,10 @@ def _psparse_disassembled(I, J, V, rows: PRange, cols: PRange, split_format: boo
         gj = csa.local_to_global[ej[sel] - 1] if len(sel) else np.zeros(0, np.int64)
         owner = rsa.ghost_to_owner[ei[sel] - rsa.n_own - 1]
         outgoing.append((ind_r.part, {int(q): (gi[owner == q], gj[owner == q], ev[sel][owner == q]) for q in np.unique(owner)}))
-    everyone = dict(b.gather_all(outgoing))
+    received = _ship_ghost_rows(b, outgoing, ship)
     new_cols, lists = [], []
-    for (oo, og), ind_r, ind_c in zip(own_lists, rows.indices, cols.indices):
+    for (oo, og), ind_r, ind_c, (ri, rj, rv) in zip(own_lists, rows.indices, cols.indices, received):
         me = ind_r.part
-        rcv = [everyone[q][me] for q in sorted(everyone) if q != me and me in everyone[q]]
-        ri = np.concatenate([x[0] for x in rcv]) if rcv else np.zeros(0, np.int64)
-        rj = np.concatenate([x[1] for x in rcv]) if rcv else np.zeros(0, np.int64)
-        rv = np.concatenate([x[2] for x in rcv]) if rcv else np.zeros(0)
         rli = ind_r.global_to_local(ri).astype(np.int64)   # own-first: own id == local id
         rlj = ind_c.global_to_local(rj).astype(np.int64)
         if np.any(rli < 1) or np.any(rli > ind_r.n_own):

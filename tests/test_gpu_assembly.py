@@ -12,13 +12,14 @@ J = [[2, 6, 1, 2, 1], [3, 9, 4, 2, 0], [5, 6, 6, 7], [9, 3, 8, 10, 5, 1]]
 V = [[1.0, 2.0, 30.0, 10.0, 1.0], [10.0, 2.0, 30.0, 2.0, 2.0], [10.0, 2.0, 30.0, 1.0], [10.0, 2.0, 30.0, 50.0, 2.0, 1.0]]
 
 
+@pytest.mark.parametrize("ship", ["host", "device"])  # ghost-row entries through the metadata channel / the device exchange!
 @pytest.mark.parametrize("fmt", ["csr", "csc"])
-def test_disassembled_psparse_mul_and_cg(fmt):
+def test_disassembled_psparse_mul_and_cg(fmt, ship):
     import pa_b200 as pa
 
     b = pa.CUDAArray(4, arena_bytes=16 << 20)
     rows = pa.uniform_partition(b, 4, 10)
-    A = pa.psparse(I, J, V, rows, rows, assembled=False, local_format=fmt)
+    A = pa.psparse(I, J, V, rows, rows, assembled=False, local_format=fmt, ship=ship)
     dense = np.zeros((10, 10))
     for Ip, Jp, Vp in zip(I, J, V):
         for i, j, v in zip(Ip, Jp, Vp):

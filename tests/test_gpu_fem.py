@@ -18,10 +18,10 @@ def pa():
     return pa_b200
 
 
-def _compare_with_oracle(pa, b, prob, fmt, compress):
+def _compare_with_oracle(pa, b, prob, fmt, compress, ship="host"):
     P = len(prob.I)
     rows = pa.variable_partition(b, prob.n_own_dofs, prob.n_global_dofs)
-    A = pa.psparse(prob.I, prob.J, prob.V, rows, rows, assembled=False, local_format=fmt, compress=compress)
+    A = pa.psparse(prob.I, prob.J, prob.V, rows, rows, assembled=False, local_format=fmt, compress=compress, ship=ship)
     orows = o.variable_partition(prob.n_own_dofs, prob.n_global_dofs)
     Ao = o.psparse(prob.I, prob.J, prob.V, orows, orows, assembled=False, local_format=fmt)
     for k in range(P):
@@ -65,6 +65,15 @@ def test_fem_example_matches_oracle_and_known_answer(pa, parts, cells, fmt, comp
     res = pa.ref_cg_(x, A, bc, tolerance=1e-10, maxiter=500)
     assert res.converged
     assert np.linalg.norm(x.collect() - prob.exact_solution()) < 1.0e-5
+    b.close()
+
+
+def test_fem_assembly_with_device_shipping_is_bit_identical(pa):
+    """Same assembly with the ghost-row entries pulled by their owners through exchange! on the device (psparse(...; ship=
+    "device")): identical CSR, ghost numbering and products as the oracle's stage-by-stage assembly."""
+    prob = fem_q1.Q1Problem((3, 2), (13, 9), (2.0, 2.0 * 9 / 13))
+    b = pa.CUDAArray(len(prob.I), arena_bytes=16 << 20)
+    _compare_with_oracle(pa, b, prob, "csr", "device", ship="device")
     b.close()
 
 

@@ -57,3 +57,36 @@ def test_exchange_layout_matches_oracle_exchange():
             assert False, "expected ValueError"
         except ValueError:
             pass
+
+
+def test_ghost_row_shipping_device_route_equals_host_route(monkeypatch):
+    """psparse(disassembled): the entries of ghost rows reach their owners either through the metadata channel or through
+    three exchange! calls; both routes must deliver the same arrays in the same (ascending sender) order.  The device
+    exchange is replaced by the oracle's exchange here (no GPU); the real one is checked in tests/test_gpu_primitives.py."""
+    import pa_b200 as pa
+    from pa_b200 import parrays
+
+    def fake_exchange(snd, graph):
+        dtype = np.float64 if any(np.asarray(a).dtype.kind == "f" for s in snd for a in s) else np.int64
+        jag = [o.jagged_from_lists([np.asarray(a, dtype=dtype) for a in s], dtype) for s in snd]
+        rcv = o.exchange(jag, graph.snd, graph.rcv)
+        return [[r.segment(i).copy() for i in range(len(graph.rcv[k]))] for k, r in enumerate(rcv)]
+
+    monkeypatch.setattr(parrays, "exchange", fake_exchange)
+    rng = np.random.default_rng(4)
+    P = 5
+    b = _HostBackend(P)
+    outgoing = []
+    for p in range(1, P + 1):
+        dests = sorted(rng.choice([q for q in range(1, P + 1) if q != p], size=rng.integers(0, P - 1), replace=False).tolist())
+        out = {}
+        for q in dests:
+            m = int(rng.integers(0, 6))
+            out[int(q)] = (rng.integers(1, 100, m), rng.integers(1, 100, m), rng.standard_normal(m))
+        outgoing.append((p, out))
+    host = parrays._ship_ghost_rows(b, outgoing, "host")
+    dev = parrays._ship_ghost_rows(b, outgoing, "device")
+    assert len(host) == len(dev) == P
+    for h, d in zip(host, dev):
+        for t in range(3):
+            assert h[t].dtype == d[t].dtype and np.array_equal(h[t], d[t])
