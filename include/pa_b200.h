@@ -222,7 +222,7 @@ int pa_mat_fill_stored(pa_mat *A, double a);
 /* mul!(y,A,x) (src/p_sparse_matrix.jl:2090-2103) when alpha=1,beta=0; mul!(y,A,x,alpha,beta)
  * (:2105-2142) otherwise; HPCG mul_no_lat! (HPCG/src/hpcg_utils.jl:6-17) is the same call.
  * Ghost values are always read straight from the owner's HBM over NVLink by a kernel of this call — no
- * message, no pack/unpack, no MPI/NCCL.  Three schedules (results are bit-identical):
+ * message, no pack/unpack, no MPI/NCCL.  Four schedules (results are bit-identical):
  *   default                    consistent!(x) as a peer-load gather kernel, then ONE local SpMV over own|ghost
  *                              columns (the HPCG mul_no_lat! schedule; fastest measured on B200)
  *   PA_SPMV_OVERLAP            the reference mul! latency hiding: the gather runs on a side stream while the
