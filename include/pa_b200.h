@@ -218,6 +218,7 @@ int pa_mat_fill_stored(pa_mat *A, double a);
 #define PA_SPMV_INLINE_PEER_LOADS 8u  /* one kernel: ghost columns dereference the owner's arena inside the SpMV */
 #define PA_SPMV_OVERLAP 16u           /* consistent!(x) on a side stream || own-block product, then ghost-block product */
 #define PA_SPMV_FUSED_EXCHANGE 32u    /* ONE kernel: the SpMV's producer warps pull the ghost values while the first tiles stream */
+#define PA_CG_TIMING 64u              /* pa_cg*: record per-operation device times (see pa_cg_timings); runs the loop eagerly */
 
 /* mul!(y,A,x) (src/p_sparse_matrix.jl:2090-2103) when alpha=1,beta=0; mul!(y,A,x,alpha,beta)
  * (:2105-2142) otherwise; HPCG mul_no_lat! (HPCG/src/hpcg_utils.jl:6-17) is the same call.
@@ -251,6 +252,15 @@ typedef struct {
  * receives maxiter+1 residual norms (residual0 first).  Stops at maxiter or ||r||/||r0|| <= tol. */
 int pa_cg(pa_mat *A, pa_vec *x, const pa_vec *b, int32_t maxiter, double tol, uint32_t flags,
           pa_cg_result *result, double *history);
+
+/* Per-operation device times (CUDA events) of the last solve that ran with PA_CG_TIMING, in ms — the timing_data slots of
+ * HPCG/src/ref_cg.jl:46-67 that HPCG/src/report_results.jl:89-152 reports: out6 = { DDOT, WAXPBY, SPMV, preconditioner
+ * (ldiv!), total of the timed operations, iterations }.  With PA_CG_REFERENCE_OPS the split is the reference's own
+ * op-for-op sequence; without it the fused kernels are binned by their dominant operation. */
+int pa_cg_timings(pa_ctx *ctx, double *out6);
+/* pa_cg keeps its three work vectors, the residual history buffer and the captured CUDA graph of the iteration cached per
+ * (A, x, b) — released when A or the partition is destroyed, or all at once here. */
+int pa_ctx_release_workspaces(pa_ctx *ctx);
 
 /* ------------------------------------------------------------------ HPCG multigrid preconditioner ----
  * (the caller on either side of the SpMV in HPCG/src/ref_cg.jl:48.)

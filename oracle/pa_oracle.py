@@ -113,10 +113,16 @@ class LocalIndices:
     grid: Optional[Tuple[int, ...]] = None
     parts_per_dir: Optional[Tuple[int, ...]] = None
     _g2l: Optional[dict] = field(default=None, repr=False, compare=False)
+    # own/ghost is decided by POSITION in the own ranges (src/p_range.jl:648-664), not by owner == part: with a
+    # periodic ghost layer and one part in a direction the wrapped ghosts are owned by the part itself and stay ghosts
+    own_mask: Optional[np.ndarray] = field(default=None, repr=False, compare=False)
 
     def __post_init__(self):
         self.local_to_global = np.asarray(self.local_to_global, dtype=np.int64)
         self.local_to_owner = np.asarray(self.local_to_owner, dtype=np.int32)
+        if self.own_mask is None:
+            self.own_mask = self.local_to_owner == self.part
+        self.own_mask = np.asarray(self.own_mask, dtype=bool)
 
     # --- accessors (1-based values) ---
     @property
@@ -125,15 +131,15 @@ class LocalIndices:
 
     @property
     def own_to_local(self) -> np.ndarray:
-        return (np.nonzero(self.local_to_owner == self.part)[0] + 1).astype(np.int32)
+        return (np.nonzero(self.own_mask)[0] + 1).astype(np.int32)
 
     @property
     def ghost_to_local(self) -> np.ndarray:
-        return (np.nonzero(self.local_to_owner != self.part)[0] + 1).astype(np.int32)
+        return (np.nonzero(~self.own_mask)[0] + 1).astype(np.int32)
 
     @property
     def n_own(self):
-        return int(np.count_nonzero(self.local_to_owner == self.part))
+        return int(np.count_nonzero(self.own_mask))
 
     @property
     def n_ghost(self):
@@ -153,13 +159,14 @@ class LocalIndices:
 
     def global_to_local(self, gids) -> np.ndarray:
         """gid -> lid, 0 when absent (src/p_range.jl GlobalToLocal)."""
-        if self._g2l is None:
-            self._g2l = {int(g): i + 1 for i, g in enumerate(self.local_to_global)}
+        if self._g2l is None:  # own ids win over a (self-owned, periodic) ghost copy of the same gid
+            self._g2l = {int(g): i + 1 for i, g in enumerate(self.local_to_global) if not self.own_mask[i]}
+            self._g2l.update({int(g): i + 1 for i, g in enumerate(self.local_to_global) if self.own_mask[i]})
         return np.array([self._g2l.get(int(g), 0) for g in np.atleast_1d(gids)], dtype=np.int32)
 
     def own_is_prefix(self) -> bool:
         no = self.n_own
-        return bool(np.all(self.local_to_owner[:no] == self.part))
+        return bool(np.all(self.own_mask[:no]))
 
 
 def _cartesian_linear(idx: Sequence[np.ndarray], dims: Sequence[int]) -> np.ndarray:
@@ -257,7 +264,7 @@ def uniform_partition(
             stride *= np_[d]
         owner = (owner + 1).astype(np.int32)
         owner[is_own] = rank
-        out.append(LocalIndices(nglobal, rank, gids, owner, box=own_ranges, grid=n, parts_per_dir=np_))
+        out.append(LocalIndices(nglobal, rank, gids, owner, box=own_ranges, grid=n, parts_per_dir=np_, own_mask=is_own))
     return out
 
 
@@ -317,6 +324,7 @@ def union_ghost(ind: LocalIndices, gids, owners) -> LocalIndices:
         box=ind.box,
         grid=ind.grid,
         parts_per_dir=ind.parts_per_dir,
+        own_mask=np.concatenate([ind.own_mask, np.zeros(len(cand), dtype=bool)]),
     )
 
 

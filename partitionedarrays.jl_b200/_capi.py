@@ -20,6 +20,7 @@ PA_CG_REFERENCE_OPS = 4
 PA_SPMV_INLINE_PEER_LOADS = 8
 PA_SPMV_OVERLAP = 16
 PA_SPMV_FUSED_EXCHANGE = 32
+PA_CG_TIMING = 64
 PA_OP_SUM, PA_OP_MAX, PA_OP_MIN, PA_OP_ABSSUM, PA_OP_ABSMAX, PA_OP_ABSPOW, PA_OP_INSERT = range(7)
 
 
@@ -89,6 +90,8 @@ SIGNATURES = {
     "pa_spmv": [_P, _P, _P, _D, _D, _U32],
     "pa_spmv_transpose": [_P, _P, _P, _D, _D],
     "pa_cg": [_P, _P, _P, _I32, _D, _U32, _P, _P],
+    "pa_cg_timings": [_P, _P],
+    "pa_ctx_release_workspaces": [_P],
     "pa_gs_create": [_P, _P],
     "pa_gs_set_box": [_P, _I32, _I32, _P],
     "pa_gs_commit": [_P],

@@ -18,8 +18,9 @@ __global__ void k_coo_keys(const int64_t *I, const int64_t *J, int64_t n, int64_
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = I[p], j = J[p];
     const bool ok = i >= 1 && j >= 1;
-    if (ok && (i > nrows || j > ncols)) *err = 4;
-    key[p] = ok ? (((uint64_t)(i - 1)) << 32) | (uint64_t)(j - 1) : 0ull;  // skipped entries -> stored (1,1,0)
+    const bool oob = ok && (i > nrows || j > ncols);
+    if (oob) *err = 4;  // reported as PA_EINVAL; the entry is parked on key 0 so that no later kernel indexes out of bounds
+    key[p] = (ok && !oob) ? (((uint64_t)(i - 1)) << 32) | (uint64_t)(j - 1) : 0ull;  // skipped entries -> stored (1,1,0)
     pos[p] = (int32_t)p;
     valid[p] = ok ? 1 : 0;
   }
@@ -183,6 +184,7 @@ extern "C" int pa_mat_update_coo_values(pa_mat *A, int32_t k, const double *V, i
   PA_CUDA(cudaGetLastError());
   PA_CUDA(cudaStreamSynchronize(c->stream));
   cudaFree(dV);
+  pa_mat_drop_transpose(A);  // the cached transposes copy the values: rebuild them on the next transpose product
   return PA_OK;
 }
 

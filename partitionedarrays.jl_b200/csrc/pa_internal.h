@@ -48,6 +48,33 @@ struct FlagPtrs {
   unsigned long long *p[PA_MAX_NBR];
 };
 
+// ---- folded scalar all-reduce (one part per process, or a job of one part): the LAST CTA of the producing kernel
+// pushes the part's value + a sequence number into a double-buffered slot of every part's arena header (system-scope
+// stores over NVLink); every CTA of the consuming kernel waits for all P flags in its own HBM and adds the P values in
+// PART ORDER (the order of the reference's sequential sum over parts, src/primitives.jl:693-698).  No launch of its own.
+struct RedPush {
+  unsigned long long *flag[PA_MAX_NBR];  // per destination part: red_flag[2][nparts] in its header
+  double *val[PA_MAX_NBR];               // per destination part: red_val[2][nparts]
+  unsigned long long *epoch;             // reductions posted so far (device resident: graph replay safe)
+  int me, nparts;
+};
+struct RedWait {
+  const unsigned long long *flag;  // my header
+  const double *val;
+  const unsigned long long *epoch;
+  int nparts;
+  int *err;
+};
+// neighbours' "done reading your vectors" flags in my header (WAR guard of the next vector write)
+struct DoneWait {
+  const unsigned long long *flag[PA_MAX_NBR];
+  const unsigned long long *epoch;
+  int n;
+  int *err;
+};
+
+struct CgWork;
+
 struct pa_ctx {
   int nparts = 0, nlocal = 0, device = 0;
   std::vector<int> part_ids;       // 0-based global ids of local parts
@@ -77,6 +104,10 @@ struct pa_ctx {
   int64_t launches = 0;
   std::vector<pa_plan *> pending_done;  // plans whose neighbours still have to report "done reading"
   std::map<std::string, int64_t> knobs;
+  unsigned *d_cons_ticket = nullptr;    // last-CTA ticket of the fused signal+gather+done kernel
+  std::vector<CgWork *> cg_work;        // cached CG workspaces (work vectors, history, captured graph) by (A, x, b)
+  uint64_t next_uid = 1;                // identity of matrices / vectors (cache keys survive address reuse)
+  double cg_timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // last PA_CG_TIMING solve: ddot, waxpby, spmv, precond, total (ms), iterations
 };
 
 struct PlanPart {
@@ -86,6 +117,7 @@ struct PlanPart {
   std::vector<int32_t> nbr_snd, snd_ptrs, snd_lids, snd_rlids;  // 0-based
   std::vector<int32_t> nbr_rcv, rcv_ptrs, rcv_lids, rcv_rlids;
   bool has_snd_rl = false, has_rcv_rl = false, set = false;
+  uint64_t signature = 0;  // hash of the whole local layout + exchange lists (pa_plan_commit): equal <=> identical partition
   // neighbour union (sorted global part ids) and slot lookup
   std::vector<int32_t> nbrs;
   // device tables
@@ -110,6 +142,7 @@ struct pa_plan {
 };
 
 struct pa_vec {
+  uint64_t uid = 0;
   pa_plan *plan = nullptr;
   uint64_t offset = 0;            // symmetric arena offset
   std::vector<double *> d;        // per local part
@@ -129,6 +162,7 @@ struct MatPart {
   int64_t n_grows = 0;
   int32_t *d_grows = nullptr;
   double *d_dotpart = nullptr;  // per-CTA partials of the fused dot epilogue
+  unsigned *d_dot_ticket = nullptr;  // last-CTA ticket of the folded dot epilogue
   unsigned long long *d_arrive = nullptr;  // fused consistent! (SpMV MODE 4): CTAs counted in, over all launches
   int64_t arrive_grid = 0;
   // COO pattern cache (the reference's K of sparse_matrix(...; reuse=true)): sorted permutation + segment starts
@@ -138,6 +172,7 @@ struct MatPart {
 };
 
 struct pa_mat {
+  uint64_t uid = 0;
   pa_ctx *ctx = nullptr;
   pa_plan *rows = nullptr, *cols = nullptr;
   std::vector<MatPart> parts;
@@ -156,8 +191,16 @@ static inline Coef coef_imm(double a) { return Coef{a, nullptr, nullptr, 1.0}; }
 static inline Coef coef_ratio(const double *num, const double *den, double sign) { return Coef{0.0, num, den, sign}; }
 
 // ---- runtime helpers shared between translation units ----
+bool pa_fold_ok(pa_ctx *ctx);                      // folded reductions / signalling usable (one local part, peers mapped)
+RedPush pa_red_push(pa_ctx *ctx);
+RedWait pa_red_wait(pa_ctx *ctx);
+DoneWait pa_done_wait(pa_plan *plan);              // neighbours of local part 0
+int pa_consistent_sync(pa_vec *v);                 // signal + wait + gather + done in ONE kernel (one local part)
+void pa_cg_drop_work(pa_ctx *ctx, const pa_mat *A, const pa_plan *plan, bool all);  // invalidate cached CG workspaces
 int pa_collective_begin(pa_plan *plan);   // publish my data + wait for the neighbours'
 int pa_collective_end(pa_plan *plan);     // tell the neighbours I am done reading theirs
+int pa_sync_flags(pa_plan *plan, FlagPtrs *arrive_dst, FlagPtrs *arrive_src, FlagPtrs *done_dst, int *n);
+void pa_mark_pending_done(pa_plan *plan);  // the neighbours' "done" for the current epoch has still to be waited for
 int pa_before_write(pa_ctx *ctx);         // wait until nobody is still reading my vectors
 PeerPtrs pa_peer_ptrs(const pa_vec *v, int k);
 int pa_arena_alloc(pa_ctx *ctx, uint64_t bytes, uint64_t *off);  // symmetric offset (same sequence of calls on every process)
@@ -170,5 +213,8 @@ int64_t pa_knob(pa_ctx *ctx, const char *key, int64_t dflt);
 int pa_launch_consistent(pa_vec *v);  // gather kernel only (no signalling)
 int pa_waxpby_dev(pa_vec *w, Coef ca, const pa_vec *x, Coef cb, const pa_vec *y);
 int pa_reduce_dev_to(const pa_vec *x, const pa_vec *y, int mode, double *d_out);  // mode 0 dot, 1 sumsq, 2 sum
-int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, int mode, const pa_vec *dotw, double *d_out);
-int pa_spmv_dot(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, uint32_t flags, const pa_vec *dotw, double *d_out);
+// fold != 0: the dot epilogue's last CTA pushes the part's value to the peers (RedPush) instead of k_sum_parts + all-reduce
+int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, int mode, const pa_vec *dotw, double *d_out, int fold = 0);
+int pa_spmv_dot(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, uint32_t flags, const pa_vec *dotw, double *d_out, int fold = 0);
+bool pa_spmv_dot_foldable(pa_mat *A, pa_vec *x);
+void pa_mat_drop_transpose(pa_mat *A);

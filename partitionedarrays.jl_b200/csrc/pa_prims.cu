@@ -189,6 +189,7 @@ extern "C" int pa_xchg_exchange(pa_xchg *x) {
   PA_CHECK(x && x->committed, PA_ESTATE, "pa_xchg_exchange: exchange missing or not committed");
   pa_ctx *c = x->ctx;
   PA_CUDA(cudaSetDevice(c->device));
+  PA_TRY(pa_before_write(c));  // a pending "done" of an earlier collective belongs to an earlier epoch: wait for it first
   PA_TRY(pa_collective_begin(x->plan));
   for (int k = 0; k < c->nlocal; ++k) {
     XchgPart &p = x->parts[k];

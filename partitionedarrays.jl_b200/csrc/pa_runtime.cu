@@ -153,6 +153,8 @@ extern "C" int pa_ctx_create(int32_t nparts_global, int32_t nlocal, const int32_
   PA_CUDA(cudaMemsetAsync(c->d_red_epoch, 0, sizeof(unsigned long long), c->stream));
   PA_CUDA(cudaMalloc((void **)&c->d_err, sizeof(int)));
   PA_CUDA(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
+  PA_CUDA(cudaMalloc((void **)&c->d_cons_ticket, sizeof(unsigned)));
+  PA_CUDA(cudaMemsetAsync(c->d_cons_ticket, 0, sizeof(unsigned), c->stream));
   PA_CUDA(cudaHostAlloc((void **)&c->h_scal, PA_NSCAL * sizeof(double), cudaHostAllocDefault));
   PA_CUDA(cudaHostAlloc((void **)&c->h_err, sizeof(int), cudaHostAllocDefault));
   *c->h_err = 0;
@@ -168,6 +170,8 @@ extern "C" int pa_ctx_destroy(pa_ctx *c) {
   if (!c) return PA_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  pa_cg_drop_work(c, nullptr, nullptr, true);
+  cudaFree(c->d_cons_ticket);
   if (c->nccl_comm && g_nccl) {
     nccl_destroy_t f = (nccl_destroy_t)dlsym(g_nccl, "ncclCommDestroy");
     if (f) f(c->nccl_comm);
@@ -353,6 +357,36 @@ static bool peer_allreduce_ok(pa_ctx *c) {
   return true;
 }
 
+// Folded reductions / signalling: one local part whose peers are all mapped (one part per process), or a one-part job.
+bool pa_fold_ok(pa_ctx *c) {
+  if (pa_knob(c, "no_fold", 0)) return false;
+  if (c->nlocal != 1 || c->nparts > PA_MAX_NBR) return false;
+  if (c->nparts == 1) return true;
+  return peer_allreduce_ok(c);
+}
+RedPush pa_red_push(pa_ctx *c) {
+  RedPush rp;
+  for (int p = 0; p < PA_MAX_NBR; ++p) {
+    unsigned long long *hdr = p < c->nparts ? (unsigned long long *)c->peer_base[p] : nullptr;
+    rp.flag[p] = hdr ? hdr + 2 * c->nparts : nullptr;
+    rp.val[p] = hdr ? (double *)(hdr + 4 * c->nparts) : nullptr;
+  }
+  rp.epoch = c->d_red_epoch;
+  rp.me = c->part_ids[0];
+  rp.nparts = c->nparts;
+  return rp;
+}
+RedWait pa_red_wait(pa_ctx *c) {
+  unsigned long long *mine = (unsigned long long *)c->arena[0];
+  RedWait w;
+  w.flag = mine + 2 * c->nparts;
+  w.val = (const double *)(mine + 4 * c->nparts);
+  w.epoch = c->d_red_epoch;
+  w.nparts = c->nparts;
+  w.err = c->d_err;
+  return w;
+}
+
 int pa_reduce_finish(pa_ctx *c, double *d_out) {
   if (peer_allreduce_ok(c)) {
     RedPeers rp;
@@ -474,6 +508,31 @@ int pa_collective_begin(pa_plan *plan) {
   return wait_all(plan, false);
 }
 
+DoneWait pa_done_wait(pa_plan *plan) {
+  pa_ctx *c = plan->ctx;
+  const PlanPart &pp = plan->parts[0];
+  DoneWait d;
+  d.n = (int)pp.nbrs.size();
+  for (int i = 0; i < PA_MAX_NBR; ++i) d.flag[i] = i < d.n ? flag_addr(c, c->part_ids[0], pp.nbrs[i], true) : nullptr;
+  d.epoch = c->d_epoch;
+  d.err = c->d_err;
+  return d;
+}
+
+// flag addresses of the fused signal + gather + done kernel (pa_vector.cu): arrive/done at the neighbours, arrive here
+int pa_sync_flags(pa_plan *plan, FlagPtrs *arrive_dst, FlagPtrs *arrive_src, FlagPtrs *done_dst, int *n) {
+  pa_ctx *c = plan->ctx;
+  const PlanPart &pp = plan->parts[0];
+  *n = (int)pp.nbrs.size();
+  for (int i = 0; i < *n; ++i) {
+    PA_CHECK(c->peer_base[pp.nbrs[i]], PA_ESTATE, "part %d's arena was never imported (pa_ctx_arena_import)", pp.nbrs[i] + 1);
+    arrive_dst->p[i] = flag_addr(c, pp.nbrs[i], c->part_ids[0], false);
+    arrive_src->p[i] = flag_addr(c, c->part_ids[0], pp.nbrs[i], false);
+    done_dst->p[i] = flag_addr(c, pp.nbrs[i], c->part_ids[0], true);
+  }
+  return PA_OK;
+}
+
 int pa_collective_end(pa_plan *plan) {
   PA_TRY(signal_all(plan, true));
   pa_ctx *c = plan->ctx;
@@ -482,6 +541,13 @@ int pa_collective_end(pa_plan *plan) {
   if (any && std::find(c->pending_done.begin(), c->pending_done.end(), plan) == c->pending_done.end())
     c->pending_done.push_back(plan);
   return PA_OK;
+}
+
+void pa_mark_pending_done(pa_plan *plan) {
+  pa_ctx *c = plan->ctx;
+  bool any = false;
+  for (auto &pp : plan->parts) any |= !pp.nbrs.empty();
+  if (any && std::find(c->pending_done.begin(), c->pending_done.end(), plan) == c->pending_done.end()) c->pending_done.push_back(plan);
 }
 
 int pa_before_write(pa_ctx *c) {
@@ -690,6 +756,22 @@ extern "C" int pa_plan_commit(pa_plan *plan, int64_t sym_n_local) {
     }
   }
   PA_CUDA(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < c->nlocal; ++k) {  // layout signature (FNV-1a over every index array of the part)
+    PlanPart &pp = plan->parts[k];
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void *p, size_t bytes) {
+      const unsigned char *b = (const unsigned char *)p;
+      for (size_t i = 0; i < bytes; ++i) h = (h ^ b[i]) * 1099511628211ull;
+      h = (h ^ (uint64_t)bytes) * 1099511628211ull;
+    };
+    auto mixv = [&](const std::vector<int32_t> &v) { mix(v.data(), v.size() * sizeof(int32_t)); };
+    const int64_t hdr[4] = {pp.n_local, pp.n_own, pp.prefix ? 1 : 0, (int64_t)c->part_ids[k]};
+    mix(hdr, sizeof(hdr));
+    mixv(pp.own_to_local); mixv(pp.ghost_to_local);
+    mixv(pp.nbr_snd); mixv(pp.snd_ptrs); mixv(pp.snd_lids); mixv(pp.snd_rlids);
+    mixv(pp.nbr_rcv); mixv(pp.rcv_ptrs); mixv(pp.rcv_lids); mixv(pp.rcv_rlids);
+    pp.signature = h;
+  }
   plan->committed = true;
   return PA_OK;
 }
@@ -701,6 +783,7 @@ extern "C" int pa_plan_destroy(pa_plan *plan) {
   cudaStreamSynchronize(c->stream);
   auto &pd = c->pending_done;
   pd.erase(std::remove(pd.begin(), pd.end(), plan), pd.end());
+  pa_cg_drop_work(c, nullptr, plan, false);
   for (auto &pp : plan->parts) {
     cudaFree(pp.d_own_to_local);
     cudaFree(pp.d_ghost_to_local);

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 
+#include "pa_device.cuh"
 #include "pa_internal.h"
 
 #define SPMV_BLOCK 256
@@ -40,6 +41,10 @@ struct SpmvArgs {
   const int32_t *cons_lid, *cons_slot, *cons_rlid;  // the consistent! table of x's plan (ghost slot <- owner slot, lid)
   int64_t n_cons;
   unsigned long long *arrive;                  // CTAs whose share of the gather is stored, summed over all launches
+  // folded dot epilogue: the last CTA adds the per-CTA partials in a fixed order and pushes the part's value to the peers
+  int fold;
+  unsigned *dot_ticket;
+  RedPush push;
 };
 
 // The matrix stream is read exactly once: keep it out of L1 and mark it evict-first in L2 so the
@@ -399,10 +404,34 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
     for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
     if ((tid & 31) == 0) red[tid >> 5] = dsum;
     asm volatile("bar.sync 1, %0;" ::"r"(ROWS) : "memory");
+    __shared__ bool last_cta;
     if (tid == 0) {
       double t = 0.0;
       for (int w = 0; w < (ROWS >> 5); ++w) t += red[w];
       a.dot_part[blockIdx.x] = t;
+      if (a.fold) {
+        __threadfence();
+        last_cta = atomicInc(a.dot_ticket, gridDim.x - 1) == gridDim.x - 1;  // wraps to 0: self resetting
+      }
+    }
+    if (a.fold) {
+      // the last CTA to finish adds all partials (thread t: partials t, t+ROWS, ... then a fixed tree: deterministic) and
+      // posts the part's value to every part of the job: no k_sum_parts launch, no all-reduce launch
+      asm volatile("bar.sync 1, %0;" ::"r"(ROWS) : "memory");
+      if (last_cta) {
+        __threadfence();
+        double s = 0.0;
+        for (int i = tid; i < (int)gridDim.x; i += ROWS) s += __ldcg(a.dot_part + i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((tid & 31) == 0) red[tid >> 5] = s;
+        asm volatile("bar.sync 1, %0;" ::"r"(ROWS) : "memory");
+        if (tid < 32) {
+          double t = 0.0;
+          for (int w = 0; w < (ROWS >> 5); ++w) t += red[w];
+          pa_red_post(a.push, t, tid);
+        }
+      }
     }
   }
 }
@@ -561,8 +590,9 @@ __global__ void k_sum_parts(const double *part, int n, double *out) {
 }
 
 // dotw/d_out (nullable): fused epilogue *d_out = sum_parts dot(y_own, dotw_own), only with mode 0/1 on the TMA kernel
-int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, int mode, const pa_vec *dotw, double *d_out) {
+int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, int mode, const pa_vec *dotw, double *d_out, int fold) {
   pa_ctx *c = A->ctx;
+  PA_CHECK(!fold || (dotw && pa_fold_ok(c)), PA_ESTATE, "folded dot epilogue needs one local part with mapped peers");
   for (int k = 0; k < c->nlocal; ++k) {
     MatPart &m = A->parts[k];
     if (m.nrows == 0) continue;
@@ -612,10 +642,18 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, in
       a.cons_rlid = xp.d_ghost_rlid;
       a.n_cons = xp.n_cons;
       a.arrive = m.d_arrive;
+      a.fold = fold;
+      a.dot_ticket = m.d_dot_ticket;
+      if (fold) a.push = pa_red_push(c);
     };
     if (dotw) {
       PA_CHECK(use_tma && mode != 2 && mode != 3 && rp.prefix && alpha == 1.0 && beta == 0.0, PA_ESTATE, "dot epilogue unavailable for this configuration");
       if (!m.d_dotpart) PA_CUDA(cudaMalloc((void **)&m.d_dotpart, PA_DOT_PARTS * sizeof(double)));
+      if (!m.d_dot_ticket) {
+        PA_CUDA(cudaMalloc((void **)&m.d_dot_ticket, sizeof(unsigned)));
+        PA_CUDA(cudaMemsetAsync(m.d_dot_ticket, 0, sizeof(unsigned), c->stream));
+      }
+      PA_CHECK(!fold || use_tma, PA_ESTATE, "folded dot epilogue needs the TMA kernel");
     }
     int64_t grid_used = 0;
     auto go = [&](auto &a, auto tag) -> int {
@@ -644,13 +682,13 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, in
       PA_TRY(go(a, (int32_t)0));
     }
     c->launches++;
-    if (dotw) {
+    if (dotw && !fold) {
       k_sum_parts<<<1, 256, 0, c->stream>>>(m.d_dotpart, (int)grid_used, c->nlocal == 1 ? d_out : c->d_partial + k);
       c->launches++;
     }
   }
   PA_CUDA(cudaGetLastError());
-  if (dotw) PA_TRY(pa_reduce_finish(c, d_out));
+  if (dotw && !fold) PA_TRY(pa_reduce_finish(c, d_out));
   return PA_OK;
 }
 
@@ -693,7 +731,9 @@ static int check_mul_args(pa_mat *A, pa_vec *x, pa_vec *y) {
 int pa_reduce_dev_to(const pa_vec *x, const pa_vec *y, int mode, double *d_out);
 
 // mul! with an optional fused epilogue *d_out = dot(dotw, y) (device resident; CG's u.c)
-int pa_spmv_dot(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, uint32_t flags, const pa_vec *dotw, double *d_out) {
+bool pa_spmv_dot_foldable(pa_mat *A, pa_vec *x) { return pa_fold_ok(A->ctx) && dot_fusable(A, x); }
+
+int pa_spmv_dot(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, uint32_t flags, const pa_vec *dotw, double *d_out, int fold) {
   PA_TRY(check_mul_args(A, x, y));
   pa_ctx *c = A->ctx;
   PA_CUDA(cudaSetDevice(c->device));
@@ -723,12 +763,21 @@ int pa_spmv_dot(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, uint
   if (dotw && (strategy == 2 || alpha != 1.0 || beta != 0.0 || !dot_fusable(A, x))) dotw = nullptr;
   // the exchange plan of x is the one that knows where the ghosts live (it equals the column plan)
   pa_plan *xp = x->plan;
+  PA_CHECK(!fold || (dotw && (strategy == 0 || strategy == 3)), PA_ESTATE, "pa_spmv_dot: folded dot epilogue unavailable for this configuration");
+  if (strategy == 0 && pa_fold_ok(c)) {
+    // one local part: signal + wait + gather + "done" are ONE kernel; the neighbours may overwrite their vectors as soon
+    // as the gather has finished (the local SpMV only reads this part's HBM)
+    if (any_ghost || c->nparts > 1) PA_TRY(pa_consistent_sync(x));
+    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 0, dotw, d_out, fold));
+    if (want_dot && !dotw) PA_TRY(pa_reduce_dev_to(want_dot, y, 0, d_out));
+    return PA_OK;
+  }
   PA_TRY(pa_collective_begin(xp));
   if (strategy == 0) {
     PA_TRY(pa_launch_consistent(x));
-    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 0, dotw, d_out));
+    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 0, dotw, d_out, fold));
   } else if (strategy == 3) {
-    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 4, dotw, d_out));  // consistent!(x) happens inside the SpMV kernel
+    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 4, dotw, d_out, fold));  // consistent!(x) happens inside the SpMV kernel
   } else if (strategy == 1) {
     PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 1, dotw, d_out));
     if (!(flags & PA_SPMV_SKIP_GHOST_REFRESH)) PA_TRY(pa_launch_consistent(x));
@@ -759,6 +808,7 @@ extern "C" int pa_mat_create(pa_plan *rows, pa_plan *cols, pa_mat **out) {
   PA_CHECK(rows && cols && out && rows->committed && cols->committed, PA_ESTATE, "pa_mat_create: plans missing or not committed");
   PA_CHECK(rows->ctx == cols->ctx, PA_EINVAL, "pa_mat_create: row and column plans live on different backends");
   pa_mat *A = new pa_mat();
+  A->uid = rows->ctx->next_uid++;
   A->ctx = rows->ctx;
   A->rows = rows;
   A->cols = cols;
@@ -772,6 +822,7 @@ static void free_part(MatPart &m) {
   cudaFree(m.d_coo_seg);
   cudaFree(m.d_coo_valid);
   cudaFree(m.d_dotpart);
+  cudaFree(m.d_dot_ticket);
   cudaFree(m.d_arrive);
   cudaFree(m.d_grows);
   cudaFree(m.d_rowptr);
@@ -784,13 +835,20 @@ extern "C" int pa_mat_destroy(pa_mat *A) {
   if (!A) return PA_OK;
   cudaSetDevice(A->ctx->device);
   cudaStreamSynchronize(A->ctx->stream);
+  pa_cg_drop_work(A->ctx, A, nullptr, false);
   for (auto &m : A->parts) free_part(m);
-  if (A->T) {
-    for (auto &m : A->T->parts) free_part(m);
-    delete A->T;
-  }
+  pa_mat_drop_transpose(A);
   delete A;
   return PA_OK;
+}
+
+// The cached local transposes hold a COPY of the values: every value refresh of A invalidates them.
+void pa_mat_drop_transpose(pa_mat *A) {
+  if (!A->T) return;
+  cudaStreamSynchronize(A->ctx->stream);
+  for (auto &m : A->T->parts) free_part(m);
+  delete A->T;
+  A->T = nullptr;
 }
 
 static int64_t rd(const void *p, int bits, int64_t i) { return bits == 64 ? ((const int64_t *)p)[i] : (int64_t)((const int32_t *)p)[i]; }
@@ -1016,6 +1074,7 @@ extern "C" int pa_mat_fill_stored(pa_mat *A, double a) {
       c->launches++;
     }
   PA_CUDA(cudaGetLastError());
+  pa_mat_drop_transpose(A);  // mul!(c, transpose(A), b) must see the new values
   return PA_OK;
 }
 

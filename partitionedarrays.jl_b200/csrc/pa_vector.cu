@@ -2,6 +2,7 @@
 // reductions, and the consistent!/assemble! peer-pull kernels.
 // Reference: src/p_vector.jl:587-612 (assemble_impl!), :695-708 (assemble!), :747-755 (consistent!),
 // :800-821 (copy!/fill!), :1178-1206 (sum/dot/norm), :1194-1199 (rmul!), :1208-1277 (broadcast).
+#include "pa_device.cuh"
 #include "pa_internal.h"
 
 // ------------------------------------------------------------------ symmetric arena
@@ -24,6 +25,7 @@ extern "C" int pa_vec_create(pa_plan *plan, pa_vec **out) {
   PA_CHECK(plan && out && plan->committed, PA_ESTATE, "pa_vec_create: plan missing or not committed");
   pa_ctx *c = plan->ctx;
   pa_vec *v = new pa_vec();
+  v->uid = c->next_uid++;
   v->plan = plan;
   int r = pa_arena_alloc(c, plan->vec_bytes, &v->offset);
   if (r != PA_OK) {
@@ -91,7 +93,13 @@ __global__ void __launch_bounds__(PA_RED_THREADS) k_fill(double *__restrict__ v,
 }
 
 // w = ca*x + cb*y ; coefficients either immediate or num/den read from device scalars
-__device__ __forceinline__ double coef_value(const Coef &c) { return c.num ? c.sign * (*c.num / *c.den) : c.imm; }
+// num == 0 (an EXACTLY zero residual: the reference's CG stops there, ref_cg.jl:22-26) gives 0 instead of 0/0, so the
+// iterations a device-resident loop still runs after exact convergence leave x, r and u unchanged
+__device__ __forceinline__ double coef_value(const Coef &c) {
+  if (!c.num) return c.imm;
+  const double n = *c.num;
+  return n == 0.0 ? 0.0 : c.sign * (n / *c.den);
+}
 
 __global__ void __launch_bounds__(PA_RED_THREADS)
     k_waxpby(double *w, Coef ca, const double *x, Coef cb, const double *y, int64_t n) {
@@ -134,9 +142,13 @@ static int same_plan(const pa_vec *a, const pa_vec *b, const char *who) {
 
 // number of leading local entries a broadcast update touches on part k: all local entries when the vectors share the
 // partition, the own entries only otherwise (BroadcastedPVector materialize!, src/p_vector.jl:1271-1276)
+// "Identical partition" = the same plan object (the reference tests `a.index_partition === b.index_partition`), or two
+// plans whose layout signature (own/ghost permutation, neighbours, local and owner-side ids of every ghost: computed
+// once at pa_plan_commit) is equal — e.g. the column partitions of two matrices built from the same ghost set.
 static int64_t bcast_extent(const pa_vec *w, const pa_vec *x, const pa_vec *y, int k) {
   const PlanPart &pw = w->plan->parts[k], &px = x->plan->parts[k], &py = y->plan->parts[k];
-  const bool same = (w->plan == x->plan || pw.n_local == px.n_local) && (w->plan == y->plan || pw.n_local == py.n_local);
+  const bool same = (w->plan == x->plan || (pw.n_local == px.n_local && pw.signature == px.signature)) &&
+                    (w->plan == y->plan || (pw.n_local == py.n_local && pw.signature == py.signature));
   return same ? pw.n_local : pw.n_own;
 }
 
@@ -359,6 +371,56 @@ static int small_grid(int64_t n) {
   return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
 }
 
+// consistent! with its signalling folded in (one local part): signal "my values are final" to the neighbours, wait for
+// theirs, gather, and — by the last CTA to finish — tell the neighbours "done reading" and advance the epoch.
+// One launch instead of k_signal_wait + k_consistent + k_signal(done).
+__global__ void __launch_bounds__(256) k_consistent_sync(double *v, const int32_t *__restrict__ lid, const int32_t *__restrict__ slot,
+                                                          const int32_t *__restrict__ rlid, int64_t n, PeerPtrs peers,
+                                                          unsigned long long *epoch, FlagPtrs arrive_dst, FlagPtrs arrive_src,
+                                                          FlagPtrs done_dst, int nnbr, unsigned *ticket, int *err) {
+  __shared__ bool last;
+  const unsigned long long e = *epoch + 1ull;  // nobody writes *epoch before every CTA has passed its ticket
+  if ((int)threadIdx.x < nnbr) {
+    if (blockIdx.x == 0) {
+      // all earlier kernels of this stream are complete (stream order): publish their writes system wide, then the epoch
+      __threadfence_system();
+      pa_st_release_sys(arrive_dst.p[threadIdx.x], e);
+    }
+    pa_spin_until(arrive_src.p[threadIdx.x], e, err);
+  }
+  __syncthreads();
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+    v[lid[j]] = __ldcg(peers.p[slot[j]] + rlid[j]);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;  // wraps to 0: self resetting
+  }
+  __syncthreads();
+  if (last) {
+    if ((int)threadIdx.x < nnbr) pa_st_release_sys(done_dst.p[threadIdx.x], e);
+    if (threadIdx.x == 0) *epoch = e;
+  }
+}
+
+int pa_consistent_sync(pa_vec *v) {
+  pa_ctx *c = v->plan->ctx;
+  const PlanPart &pp = v->plan->parts[0];
+  FlagPtrs adst, asrc, ddst;
+  int n = 0;
+  PA_TRY(pa_sync_flags(v->plan, &adst, &asrc, &ddst, &n));
+  if (!n && c->nparts == 1) return PA_OK;  // a job of one part: nothing to order, nothing to gather
+  // the grid is capped so that every CTA is resident (each CTA polls the neighbours' flags before it gathers)
+  int64_t g = (pp.n_cons + 255) / 256;
+  g = g < 1 ? 1 : (g > 148 * 4 ? 148 * 4 : g);
+  k_consistent_sync<<<(unsigned)g, 256, 0, c->stream>>>(v->d[0], pp.d_ghost_lid, pp.d_ghost_slot, pp.d_ghost_rlid, pp.n_cons, pa_peer_ptrs(v, 0),
+                                                        c->d_epoch, adst, asrc, ddst, n, c->d_cons_ticket, c->d_err);
+  c->launches++;
+  PA_CUDA(cudaGetLastError());
+  pa_mark_pending_done(v->plan);
+  return PA_OK;
+}
+
 int pa_launch_consistent(pa_vec *v) {
   pa_ctx *c = v->plan->ctx;
   for (int k = 0; k < c->nlocal; ++k) {
@@ -377,6 +439,7 @@ extern "C" int pa_vec_consistent(pa_vec *v) {
   pa_ctx *c = v->plan->ctx;
   PA_CUDA(cudaSetDevice(c->device));
   PA_TRY(pa_before_write(c));
+  if (pa_fold_ok(c)) return pa_consistent_sync(v);
   PA_TRY(pa_collective_begin(v->plan));
   PA_TRY(pa_launch_consistent(v));
   return pa_collective_end(v->plan);

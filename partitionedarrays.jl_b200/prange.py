@@ -92,14 +92,16 @@ class LocalIndices:
     (column-major positions in the own box) so a 512^3 part never materialises a 1 GB id list."""
 
     def __init__(self, n_global, part, local_to_global=None, local_to_owner=None, block=None, *, n_own=None,
-                 ghost_to_global=None, ghost_to_owner=None):
+                 ghost_to_global=None, ghost_to_owner=None, is_own=None):
         self.n_global, self.part, self.block = int(n_global), int(part), block
         self._g2l = None
         self._own_to_global = None
         if local_to_global is not None:
             l2g = np.asarray(local_to_global, dtype=np.int64)
             l2o = np.asarray(local_to_owner, dtype=np.int32)
-            own = l2o == self.part
+            # own vs ghost is positional when the caller knows it (block_with_constant_size, src/p_range.jl:648-664): the
+            # wrapped ghosts of a periodic direction with ONE part are owned by the part itself and are still ghosts
+            own = (l2o == self.part) if is_own is None else np.asarray(is_own, dtype=bool)
             self.n_local, self.n_own = len(l2g), int(np.count_nonzero(own))
             self.own_is_prefix = bool(np.all(own[: self.n_own]))
             self._own_to_global = l2g[own]
@@ -168,12 +170,16 @@ class LocalIndices:
             return out.astype(np.int32)
         if self._g2l is None:  # sorted table of the local gids (vectorised lookup: FEM-size id lists)
             l2g = self.local_to_global
-            order = np.argsort(l2g, kind="stable")
+            # duplicate gids (periodic ghost layers): the own id wins, else the LAST ghost copy (the reference's
+            # global_to_ghost is a Dict filled in ghost order, src/p_range.jl:928-935)
+            rank = -np.arange(1, self.n_local + 1, dtype=np.int64)
+            rank[self.own_to_local - 1] = -(self.n_local + 1)
+            order = np.lexsort((rank, l2g))
             self._g2l = (l2g[order], order)
         sg, order = self._g2l
         out = np.zeros(len(gids), dtype=np.int32)
         if len(sg):
-            pos = np.clip(np.searchsorted(sg, gids), 0, len(sg) - 1)
+            pos = np.clip(np.searchsorted(sg, gids, side="left"), 0, len(sg) - 1)
             hit = sg[pos] == gids
             out[hit] = order[pos[hit]] + 1
         return out
@@ -203,7 +209,7 @@ def uniform_partition_part(rank: int, np_: Sequence[int], n: Sequence[int], ghos
         is_own &= (pts[d] >= own[d][0]) & (pts[d] <= own[d][1])
     owner = info.owner_of(gids)
     owner[is_own] = rank
-    return LocalIndices(nglobal, rank, gids, owner, block=info)
+    return LocalIndices(nglobal, rank, gids, owner, block=info, is_own=is_own)
 
 
 def variable_partition_part(rank: int, n_own_all: Sequence[int], n_global: int) -> LocalIndices:
@@ -230,8 +236,10 @@ def union_ghost(ind: LocalIndices, gids, owners) -> LocalIndices:
         return LocalIndices(ind.n_global, ind.part, block=ind.block, n_own=ind.n_own,
                             ghost_to_global=np.concatenate([ind.ghost_to_global, cand]),
                             ghost_to_owner=np.concatenate([ind.ghost_to_owner, cown]))
+    is_own = np.zeros(ind.n_local + len(cand), dtype=bool)
+    is_own[ind.own_to_local - 1] = True
     return LocalIndices(ind.n_global, ind.part, np.concatenate([ind.local_to_global, cand]),
-                        np.concatenate([ind.local_to_owner, cown]), block=ind.block)
+                        np.concatenate([ind.local_to_owner, cown]), block=ind.block, is_own=is_own)
 
 
 @dataclass
@@ -265,7 +273,9 @@ def build_plans(local_inds: List[LocalIndices], gather_all) -> List[PartPlan]:
     mine = []
     for ind in local_inds:
         gown, glid, ggid = ind.ghost_to_owner, ind.ghost_to_local, ind.ghost_to_global
-        nbr = np.unique(gown).astype(np.int32)
+        # ghosts owned by the part itself (periodic, one part in that direction) are never exchanged:
+        # compute_assembly_neighbors skips owner == rank (src/p_range.jl:436-450)
+        nbr = np.unique(gown[gown != ind.part]).astype(np.int32)
         if not ind.own_is_prefix:  # send lists follow local-id order (src/p_range.jl:506-513)
             o = np.argsort(glid, kind="stable")
             gown, glid, ggid = gown[o], glid[o], ggid[o]

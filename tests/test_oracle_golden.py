@@ -277,3 +277,34 @@ def test_hash_uniform_range_and_determinism():
     a = o.hash_uniform(g, 7)
     assert a.min() >= -1.0 and a.max() < 1.0 and abs(a.mean()) < 0.02
     assert np.array_equal(a, o.hash_uniform(g, 7)) and not np.array_equal(a, o.hash_uniform(g, 8))
+
+
+def test_periodic_single_part_ghosts_stay_ghosts():
+    # block_with_constant_size (src/p_range.jl:620-671) decides own vs ghost by POSITION in the own ranges: with a periodic
+    # ghost layer and one part in a direction the wrapped layer is owned by the part itself and is still a ghost layer.
+    # Values derived from that source (np=1, n=6: local range 0:7 wraps to 6,1..6,1); no reference test holds them.
+    (ind,) = o.uniform_partition((1,), (6,), (True,), (True,))
+    assert ind.local_to_global.tolist() == [6, 1, 2, 3, 4, 5, 6, 1]
+    assert (ind.n_own, ind.n_ghost) == (6, 2)
+    assert ind.own_to_global.tolist() == [1, 2, 3, 4, 5, 6] and ind.ghost_to_owner.tolist() == [1, 1]
+    assert ind.global_to_local([1, 6]).tolist() == [2, 7]  # the own id wins over the ghost copy
+    snd, rcv = o.assembly_neighbors([ind])
+    assert snd[0].tolist() == [] and rcv[0].tolist() == []  # owner == rank is skipped (src/p_range.jl:436-450)
+    parts = o.uniform_partition((1, 2), (4, 4), (True, True), (True, True))
+    assert [p.n_own for p in parts] == [8, 8] and [p.n_ghost for p in parts] == [16, 16]
+    # the product's host mirror builds the same index sets and plans
+    from pa_b200 import prange as pr
+
+    for rank, po in enumerate(parts, start=1):
+        pp = pr.uniform_partition_part(rank, (1, 2), (4, 4), (True, True), (True, True))
+        assert pp.local_to_global.tolist() == po.local_to_global.tolist()
+        assert pp.own_to_local.tolist() == po.own_to_local.tolist() and pp.ghost_to_owner.tolist() == po.ghost_to_owner.tolist()
+        q = np.arange(0, 18)
+        assert pp.global_to_local(q).tolist() == po.global_to_local(q).tolist()
+    mine = [pr.uniform_partition_part(r, (1, 2), (4, 4), (True, True), (True, True)) for r in (1, 2)]
+    plans = pr.build_plans(mine, lambda x: x)
+    plan_o = o.assembly_plan(parts)
+    for k in range(2):
+        assert plans[k].nbr_snd.tolist() == plan_o.neighbors_snd[k].tolist() == [2 - k]
+        assert plans[k].snd_lids.tolist() == plan_o.local_indices_snd[k].data.tolist()
+        assert plans[k].rcv_lids.tolist() == plan_o.local_indices_rcv[k].data.tolist()
