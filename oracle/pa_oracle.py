@@ -159,10 +159,24 @@ class LocalIndices:
 
     def global_to_local(self, gids) -> np.ndarray:
         """gid -> lid, 0 when absent (src/p_range.jl GlobalToLocal)."""
+        gids = np.atleast_1d(np.asarray(gids, dtype=np.int64))
+        if self.n_local > 200000:  # large parts (bench-size CPU baseline): sorted-table lookup instead of a Python dict
+            if self._g2l is None:
+                # duplicates: the own id wins over a (self-owned, periodic) ghost copy, else the LAST ghost (Dict order)
+                rank = -np.arange(1, self.n_local + 1, dtype=np.int64)
+                rank[self.own_mask] = -(self.n_local + 1)
+                order = np.lexsort((rank, self.local_to_global))
+                self._g2l = (self.local_to_global[order], order)
+            sg, order = self._g2l
+            out = np.zeros(len(gids), dtype=np.int32)
+            pos = np.clip(np.searchsorted(sg, gids, side="left"), 0, len(sg) - 1)
+            hit = sg[pos] == gids
+            out[hit] = order[pos[hit]] + 1
+            return out
         if self._g2l is None:  # own ids win over a (self-owned, periodic) ghost copy of the same gid
             self._g2l = {int(g): i + 1 for i, g in enumerate(self.local_to_global) if not self.own_mask[i]}
             self._g2l.update({int(g): i + 1 for i, g in enumerate(self.local_to_global) if self.own_mask[i]})
-        return np.array([self._g2l.get(int(g), 0) for g in np.atleast_1d(gids)], dtype=np.int32)
+        return np.array([self._g2l.get(int(g), 0) for g in gids], dtype=np.int32)
 
     def own_is_prefix(self) -> bool:
         no = self.n_own

