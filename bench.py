@@ -613,7 +613,7 @@ def mg_section(pa, backend, n, sh, timed, windows, all_sum, peak):
            "gflops": (2 * nnz_l[3] + 12 * rows_t + mg_flops) * mg_iters / msmg / 1e6,
            "scaled_residual_after_10": rmg.residual / rmg.residual0,
            "symgs_finest_ms": msgs, "symgs_finest_hbm_gbs": sweep_bytes / msgs / 1e6, "symgs_finest_frac_of_peak": sweep_bytes / msgs / 1e6 / peak,
-           "smoother": pa.hpcg.smoother_name(backend)}
+           "smoother": pa.hpcg.smoother_name(P)}
     xs.free(); xm.free()
     P.free()
     return out

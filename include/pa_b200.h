@@ -274,6 +274,14 @@ int pa_gs_create(pa_mat *A, pa_gs **out);
 int pa_gs_set_box(pa_gs *gs, int32_t k, int32_t kind, const int64_t *dims);
 int pa_gs_commit(pa_gs *gs);
 int pa_gs_destroy(pa_gs *gs);
+/* Sweep order.  PA_GS_LEXICOGRAPHIC (default): the reference's sequential order (1:n, then n:-1:1,
+ * PartitionedSolvers/src/smoothers.jl:162-176) executed as a wavefront dataflow: iterates bit-identical to the reference.
+ * PA_GS_MULTICOLOR: colour by colour (27-pt: 8 colours, 7-pt: red/black; needs pa_gs_set_box) — the standard GPU order of
+ * HPCG; same fixed point and per-row arithmetic, different iterates: convergence-level parity, gated by the reference's
+ * own test (HPCG/test/hpcg_benchmark_tests.jl:31-41: scaled residual < 1e-12 after 50 iterations). */
+#define PA_GS_LEXICOGRAPHIC 0
+#define PA_GS_MULTICOLOR 1
+int pa_gs_set_order(pa_gs *gs, int32_t order);
 /* smooth!(x, state, b; zero_guess) — one symmetric Gauss-Seidel iteration (smoothers.jl:98-125) */
 int pa_gs_smooth(pa_gs *gs, pa_vec *x, const pa_vec *b, int32_t zero_guess);
 /* dims: nlevels x nlocal x 3 local box dims; restrict!/prolongate! are the f2c injections (:81-101,:224-251) */

@@ -57,9 +57,31 @@ class Level:
             self.diag.append(d)
 
 
+def color_perm(box_dims, kind=27):
+    """Rows of a box sorted by colour (27-pt: (ix&1) + 2(iy&1) + 4(iz&1), 7-pt: (ix+iy+iz)&1), ascending row id within a
+    colour: the sweep order of the multi-colour smoother (csrc/pa_mg.cu k_levels_color)."""
+    bx, by, bz = (int(d) for d in box_dims)
+    i = np.arange(bx * by * bz)
+    ix, iy, iz = i % bx, (i // bx) % by, i // (bx * by)
+    col = (ix & 1) + 2 * (iy & 1) + 4 * (iz & 1) if kind == 27 else (ix + iy + iz) & 1
+    return np.argsort(col, kind="stable").astype(np.int32)
+
+
 def gs_sweep(level: Level, x, b, backward: bool, zero_guess: bool):
     assert c_oracle.available()
     lib = c_oracle._lib
+    if getattr(level, "order", "lexicographic") == "multicolor":
+        lib.pa_oracle_gs_sweep_perm.argtypes = [C.c_int64] + [C.c_void_p] * 8 + [C.c_int, C.c_int]
+        lib.pa_oracle_gs_sweep_perm.restype = None
+        for p, ind in enumerate(level.part):
+            n, rp, cv, nz = level.mats[p]
+            dims = [hi - lo + 1 for lo, hi in ind.box]
+            perm = color_perm(dims, level.kind)
+            done = np.zeros(n, dtype=np.uint8)
+            bo = np.ascontiguousarray(b[p][:n])
+            lib.pa_oracle_gs_sweep_perm(n, c_oracle._p(rp), c_oracle._p(cv), c_oracle._p(nz), c_oracle._p(level.diag[p]), c_oracle._p(bo),
+                                        c_oracle._p(x[p]), c_oracle._p(perm), c_oracle._p(done), int(backward), int(zero_guess))
+        return
     lib.pa_oracle_gs_sweep.argtypes = [C.c_int64] + [C.c_void_p] * 6 + [C.c_int, C.c_int]
     lib.pa_oracle_gs_sweep.restype = None
     for p in range(len(level.part)):
@@ -78,7 +100,8 @@ def smooth(level: Level, x, b, zero_guess=False):
 
 
 class MG:
-    def __init__(self, npd, levels, nx, ny, nz):
+    def __init__(self, npd, levels, nx, ny, nz, order="lexicographic"):
+        self.order = order
         self.l = levels
         self.levels = [None] * levels  # index l-1 = finest
         self.f2c = [None] * (levels - 1)
@@ -87,6 +110,8 @@ class MG:
             self.f2c[i] = restrict_operator(nx, ny, nz)
             nx, ny, nz = nx // 2, ny // 2, nz // 2
             self.levels[i] = Level(nx, ny, nz, npd)
+        for L in self.levels:
+            L.order, L.kind = order, 27
 
     def solve(self, x, b, l, zero_guess=False):
         """pc_solve! — mg_preconditioner.jl:314-328 (l is 1-based like the reference)."""

@@ -335,3 +335,27 @@ void pa_oracle_gs_sweep(int64_t n, const int64_t *rowptr, const int32_t *colval,
     x[row] = s;
   }
 }
+
+/* Gauss-Seidel sweep in an arbitrary row order (multi-colour smoother: perm = rows sorted by colour): the same per-row
+ * arithmetic as pa_oracle_gs_sweep, rows visited as perm[0..n-1] (backward: perm[n-1..0]).  The zero-guess variant uses only
+ * the entries whose column was already updated in this sweep (x starts at zero: the other terms vanish) and skips
+ * s += d*x[row], like the lexicographic zero-guess sweep (smoothers.jl:248-269), of which it is the generalisation.
+ * done: n_own bytes of scratch. */
+void pa_oracle_gs_sweep_perm(int64_t n, const int64_t *rowptr, const int32_t *colval, const double *nzval, const double *diag,
+                             const double *b, double *x, const int32_t *perm, unsigned char *done, int backward, int zero_guess) {
+  for (int64_t k = 0; k < n; ++k) done[k] = 0;
+  for (int64_t k = 0; k < n; ++k) {
+    const int64_t row = perm[backward ? n - 1 - k : k];
+    double s = b[row];
+    for (int64_t p = rowptr[row]; p < rowptr[row + 1]; ++p) {
+      const int32_t col = colval[p];
+      if (zero_guess && !(col < n && done[col])) continue;
+      s -= nzval[p] * x[col];
+    }
+    const double d = diag[row];
+    if (!zero_guess) s += d * x[row];
+    s = s / d;
+    x[row] = s;
+    done[row] = 1;
+  }
+}

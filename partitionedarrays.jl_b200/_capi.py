@@ -21,6 +21,7 @@ PA_SPMV_INLINE_PEER_LOADS = 8
 PA_SPMV_OVERLAP = 16
 PA_SPMV_FUSED_EXCHANGE = 32
 PA_CG_TIMING = 64
+PA_GS_LEXICOGRAPHIC, PA_GS_MULTICOLOR = 0, 1
 PA_OP_SUM, PA_OP_MAX, PA_OP_MIN, PA_OP_ABSSUM, PA_OP_ABSMAX, PA_OP_ABSPOW, PA_OP_INSERT = range(7)
 
 
@@ -95,6 +96,7 @@ SIGNATURES = {
     "pa_gs_create": [_P, _P],
     "pa_gs_set_box": [_P, _I32, _I32, _P],
     "pa_gs_commit": [_P],
+    "pa_gs_set_order": [_P, _I32],
     "pa_gs_destroy": [_P],
     "pa_gs_smooth": [_P, _P, _P, _I32],
     "pa_mg_create": [_I32, _P, _P, _P, _P],

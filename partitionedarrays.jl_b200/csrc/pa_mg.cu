@@ -44,13 +44,38 @@ struct GsPart {
   unsigned long long *d_done = nullptr;
   unsigned long long sweeps = 0;  // batch sweeps run so far (the counters are never reset)
   bool geom = false;
+  int kind = 0;  // 7 or 27 when the geometry hint was given
   int64_t dims[3] = {0, 0, 0}, w[3] = {0, 0, 0};
+  // sliced-ELL copies of the matrix in sweep order (see GsOrder): [0] wavefront (bit-exact), [1] multi-colour
+  struct GsOrder *ord[2] = {nullptr, nullptr};
 };
+
+// The smoother's matrix in the order the sweep visits it.  Rows are sorted by level (wavefront level of the sequential
+// sweep's dependency DAG, or colour), every level padded to a multiple of 32 rows (row id -1), and stored as SELL-32:
+// slice g holds rows [32g, 32g+32) with entry k of the 32 rows adjacent, cols[(g*W + k)*32 + lane] — so a warp that
+// takes one row per lane reads every entry slot with ONE coalesced 256-byte (values) / 128-byte (columns) load and the
+// matrix stream is perfectly sequential in HBM (no sector shared with rows of other levels, no row-pointer reads).
+// A column word carries, besides the local column id (< 2^29): bit 30 = "updated earlier in the FORWARD sweep" (an own
+// column of a lower level), bit 29 = own column; -1 = empty slot.  The flags make the kernel independent of how the
+// order was obtained: lexicographic wavefront levels reproduce the reference's sequential sweep bit for bit, colours
+// give the multi-colour smoother, with the same per-row arithmetic (s -= a*x[col] in CSR order, s += d*x[row], s /= d).
+struct GsOrder {
+  int nlev = 0, W = 0;
+  int64_t npad = 0;            // padded rows (multiple of 32)
+  int32_t *d_rows = nullptr;   // [npad]
+  int32_t *d_cols = nullptr;   // [npad * W]
+  double *d_vals = nullptr;    // [npad * W]
+  std::vector<int64_t> lev_group;  // first slice of every level, size nlev + 1 (one launch per colour)
+};
+#define GS_COL_FRESH (1 << 30)
+#define GS_COL_OWN (1 << 29)
+#define GS_COL_MASK ((1 << 29) - 1)
 
 struct pa_gs {
   pa_mat *A = nullptr;
   std::vector<GsPart> parts;
   bool committed = false;
+  int order = 0;  // PA_GS_LEXICOGRAPHIC (bit-exact with the reference) or PA_GS_MULTICOLOR
 };
 
 struct pa_mg {
@@ -552,6 +577,155 @@ __global__ void __launch_bounds__(GSB_THREADS, 1) k_gs_level(const GsLevelArgs<P
   }
 }
 
+
+// ------------------------------------------------------------------ the SELL sweep kernel (rows of <= 32 entries)
+// One THREAD per row, one warp per 32-row slice of the sweep-ordered SELL copy (GsOrder).  Every entry slot of the slice
+// is one coalesced warp load; the x values are gathered by the lane that owns the row; the ordered chain
+// s -= a*x[col] runs on all 32 lanes at once (the dataflow kernel k_gs_flow_pipe runs it on 4 of 32 lanes and spends
+// ~110 warp instructions per row; here it is ~5).  SYNC: rows of earlier levels are awaited through their published
+// (value, sweep epoch) pair — the per-row dataflow of the sequential sweep's dependency DAG, one launch per sweep.
+// !SYNC: one launch per level (multi-colour order: 8 colours), no waiting at all: every read of x sees either a value of
+// an earlier launch (a colour already updated) or a value no row of this launch writes.
+struct GsSellArgs {
+  const int32_t *rows;
+  const int32_t *cols;
+  const double *vals;
+  const double *b;
+  double *x;
+  ulonglong2 *xe;
+  int *err;
+  int64_t g0, g1;    // sweep positions [g0, g1) of this launch (slice = position, or ngroups-1-position when backward)
+  int64_t ngroups;
+  int W;             // entry slots per row (runtime copy of the template parameter; used when W == 0)
+  int epoch, backward, zero_guess;
+};
+
+// minBlocksPerSM is explicit: with maxThreads alone ptxas aims at full occupancy and sinks every load next to its use,
+// which serialises the gathers of a batch (the same effect as in k_spmv_tma)
+template <int W, bool SYNC>
+__global__ void __launch_bounds__(GS_THREADS, (SYNC ? 2 : 3)) k_gs_sell(const GsSellArgs a) {
+  constexpr int B = W == 27 ? 9 : (W == 7 ? 7 : 8);  // slots per batch: loads of a batch are in flight together
+  const int WD = W ? W : a.W;
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = (int64_t)gridDim.x * (GS_THREADS / 32);
+  const int64_t w = (int64_t)blockIdx.x * (GS_THREADS / 32) + (threadIdx.x >> 5);
+  const unsigned epoch = (unsigned)a.epoch;
+  const uint64_t pol = gs_stream_policy(), keep = gs_keep_policy(1);
+  for (int64_t i = a.g0 + w; i < a.g1; i += nw) {
+    const int64_t g = a.backward ? a.ngroups - 1 - i : i;
+    const int32_t row = a.rows[g * 32 + lane];
+    const int32_t *cp = a.cols + g * WD * 32 + lane;
+    const double *vp = a.vals + g * WD * 32 + lane;
+    {  // the next slice of this warp: start its HBM reads now (WD*256 + WD*128 bytes = 3*WD 128-byte lines)
+      const int64_t inext = i + nw;
+      if (inext < a.g1) {
+        const int64_t gn = a.backward ? a.ngroups - 1 - inext : inext;
+        const char *nv = reinterpret_cast<const char *>(a.vals + gn * WD * 32), *nc = reinterpret_cast<const char *>(a.cols + gn * WD * 32);
+        for (int l = lane; l < 2 * WD; l += 32) gs_prefetch_l2(nv + (size_t)l * 128);
+        if (lane < WD) gs_prefetch_l2(nc + (size_t)lane * 128);
+      }
+    }
+    if (row < 0) continue;  // padding row (levels are padded to whole slices); no warp-level primitive below
+    double s = __ldg(a.b + row), d = 0.0;
+    const double xold = a.zero_guess ? 0.0 : gs_ld_x(a.x + row, keep);  // nobody writes x[row] before this row does
+#pragma unroll 1
+    for (int k0 = 0; k0 < WD; k0 += B) {
+      int32_t code[B];
+      double v[B], xv[B];
+      unsigned long long w0[B], w1[B];
+      bool fresh[B], use[B];
+#pragma unroll
+      for (int u = 0; u < B; ++u) {
+        const bool in = W ? (k0 + u < W) : (k0 + u < WD);
+        code[u] = in ? gs_ld_stream(cp + (k0 + u) * 32, pol) : -1;
+        v[u] = in ? gs_ld_stream(vp + (k0 + u) * 32, pol) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < B; ++u) {
+        const bool valid = code[u] >= 0;
+        const int32_t c = code[u] & GS_COL_MASK;
+        const bool ff = valid && (code[u] & GS_COL_FRESH), own = valid && (code[u] & GS_COL_OWN);
+        // a value of THIS sweep is needed: forward: an own column of a lower level; backward: an own column of a higher one
+        fresh[u] = SYNC && (a.backward ? (own && !ff && c != row) : ff);
+        use[u] = valid && (!a.zero_guess || ff);
+        xv[u] = 0.0;
+        w0[u] = w1[u] = 0ull;
+        if (fresh[u]) {
+          asm volatile("ld.relaxed.gpu.global.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(w0[u]), "=l"(w1[u]) : "l"(a.xe + c), "l"(keep) : "memory");
+        } else if (use[u]) {
+          xv[u] = SYNC ? gs_ld_x(a.x + c, keep) : a.x[c];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < B; ++u) {
+        if (fresh[u]) {
+          const int32_t c = code[u] & GS_COL_MASK;
+          long long t0 = 0;
+          while ((unsigned)(w0[u] >> 32) != epoch || (unsigned)(w1[u] >> 32) != epoch) {
+            asm volatile("ld.relaxed.gpu.global.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(w0[u]), "=l"(w1[u]) : "l"(a.xe + c), "l"(keep) : "memory");
+            if (!t0) {
+              t0 = clock64();
+            } else if (clock64() - t0 > GS_SPIN_LIMIT) {
+              *a.err = 3;
+              break;
+            }
+          }
+          xv[u] = __longlong_as_double((long long)((w1[u] << 32) | (w0[u] & 0xffffffffull)));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < B; ++u) {  // s -= a*x[col], in CSR order
+        const double t = __dsub_rn(s, __dmul_rn(v[u], xv[u]));
+        s = use[u] ? t : s;
+        if (code[u] >= 0 && (code[u] & GS_COL_MASK) == row) d = v[u];
+      }
+    }
+    if (!a.zero_guess) s = __dadd_rn(s, __dmul_rn(d, xold));  // s += d*x[row]
+    s = __ddiv_rn(s, d);
+    if (SYNC) gs_publish(a.xe + row, a.x + row, s, epoch, keep);
+    else a.x[row] = s;
+  }
+}
+
+// slot k of row r = entry k of the CSR row, flags from the levels (own columns number the own rows: square own block)
+template <typename PtrT>
+__global__ void k_gs_build_sell(const PtrT *rowptr, const int32_t *colval, const double *nzval, const int32_t *rows, int64_t npad, int W,
+                                int64_t n_own, const int32_t *lev, int32_t *cols, double *vals) {
+  for (int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pos < npad; pos += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t base = (pos >> 5) * W * 32 + (pos & 31);
+    const int32_t row = rows[pos];
+    int64_t p0 = 0;
+    int len = 0, lr = 0;
+    if (row >= 0) {
+      p0 = (int64_t)rowptr[row];
+      len = (int)((int64_t)rowptr[row + 1] - p0);
+      lr = lev[row];
+    }
+    for (int k = 0; k < W; ++k) {
+      int32_t code = -1;
+      double v = 0.0;
+      if (k < len) {
+        const int32_t c = colval[p0 + k];
+        const bool own = c < n_own;
+        const bool fr = own && lev[c] < lr;
+        code = c | (own ? GS_COL_OWN : 0) | (fr ? GS_COL_FRESH : 0);
+        v = nzval[p0 + k];
+      }
+      cols[base + (int64_t)k * 32] = code;
+      vals[base + (int64_t)k * 32] = v;
+    }
+  }
+}
+
+// multi-colour order on a box: 27-pt -> 8 colours (parity of x, y, z), 7-pt -> red/black
+__global__ void k_levels_color(int32_t *lev, int32_t *rows, int64_t n, int64_t bx, int64_t by, int kind) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ix = i % bx, iy = (i / bx) % by, iz = i / (bx * by);
+    lev[i] = kind == 27 ? (int32_t)((ix & 1) + 2 * (iy & 1) + 4 * (iz & 1)) : (int32_t)((ix + iy + iz) & 1);
+    rows[i] = (int32_t)i;
+  }
+}
+
 __global__ void k_level_hist(const int32_t *lev, int64_t n, int *count) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) atomicAdd(count + lev[i], 1);
 }
@@ -579,7 +753,18 @@ __global__ void k_iota(int32_t *rows, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) rows[i] = (int32_t)i;
 }
 
+static void gs_free_order(GsOrder *&o) {
+  if (!o) return;
+  cudaFree(o->d_rows);
+  cudaFree(o->d_cols);
+  cudaFree(o->d_vals);
+  delete o;
+  o = nullptr;
+}
+
 static void gs_free_part(GsPart &g) {
+  gs_free_order(g.ord[0]);
+  gs_free_order(g.ord[1]);
   cudaFree(g.d_rows);
   cudaFree(g.d_xe);
   cudaFree(g.d_rows_b);
@@ -606,10 +791,127 @@ extern "C" int pa_gs_set_box(pa_gs *g, int32_t k, int32_t kind, const int64_t *d
   GsPart &p = g->parts[k];
   PA_CHECK(dims[0] * dims[1] * dims[2] == g->A->parts[k].nrows, PA_EINVAL, "pa_gs_set_box: dims do not match the own rows");
   p.geom = true;
+  p.kind = kind;
   for (int d = 0; d < 3; ++d) p.dims[d] = dims[d];
   p.w[0] = 1;
   p.w[1] = kind == 27 ? 2 : 1;
   p.w[2] = kind == 27 ? 4 : 1;
+  return PA_OK;
+}
+
+// level-sorted rows -> padded list (every level starts at a multiple of 32) -> SELL copy with the order's flags
+static int gs_build_sell(pa_ctx *c, const MatPart &m, GsPart &p, const int32_t *d_lev, const int32_t *d_lev_sorted, const int32_t *d_rows_sorted,
+                         const std::vector<int> &cnt, int nlev, GsOrder **out) {
+  GsOrder *o = new GsOrder();
+  o->nlev = nlev;
+  o->W = std::max(p.maxlen, 1);
+  std::vector<int32_t> shift(nlev);
+  o->lev_group.assign(nlev + 1, 0);
+  int64_t at = 0, padded = 0;
+  for (int l = 0; l < nlev; ++l) {
+    padded = (padded + 31) / 32 * 32;
+    o->lev_group[l] = padded / 32;
+    if (!(padded - at < (1ll << 31) && padded + cnt[l] < (1ll << 31))) {
+      delete o;
+      pa_set_error("pa_gs: too many rows for the sweep-ordered copy");
+      return PA_EINVAL;
+    }
+    shift[l] = (int32_t)(padded - at);
+    at += cnt[l];
+    padded += cnt[l];
+  }
+  o->npad = (padded + 31) / 32 * 32;
+  o->lev_group[nlev] = o->npad / 32;
+  int32_t *d_shift = nullptr;
+  cudaError_t e = cudaMalloc((void **)&d_shift, nlev * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&o->d_rows, o->npad * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&o->d_cols, (size_t)o->npad * o->W * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&o->d_vals, (size_t)o->npad * o->W * sizeof(double));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(d_shift);
+    gs_free_order(o);
+    pa_set_error("pa_gs: cannot allocate the sweep-ordered matrix copy (%.2f GiB): %s", (double)p.n * o->W * 12 / 1073741824.0, cudaGetErrorString(e));
+    return PA_ENOMEM;
+  }
+  PA_CUDA(cudaMemcpyAsync(d_shift, shift.data(), nlev * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  PA_CUDA(cudaMemsetAsync(o->d_rows, 0xff, o->npad * sizeof(int32_t), c->stream));
+  k_pad_levels<<<148 * 8, 256, 0, c->stream>>>(d_lev_sorted, d_rows_sorted, d_shift, p.n, o->d_rows);
+  if (m.ptr64)
+    k_gs_build_sell<int64_t><<<148 * 8, 256, 0, c->stream>>>((const int64_t *)m.d_rowptr, m.d_colval, m.d_nzval, o->d_rows, o->npad, o->W, p.n, d_lev, o->d_cols, o->d_vals);
+  else
+    k_gs_build_sell<int32_t><<<148 * 8, 256, 0, c->stream>>>((const int32_t *)m.d_rowptr, m.d_colval, m.d_nzval, o->d_rows, o->npad, o->W, p.n, d_lev, o->d_cols, o->d_vals);
+  PA_CUDA(cudaGetLastError());
+  PA_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_shift);
+  c->launches += 2;
+  *out = o;
+  return PA_OK;
+}
+
+static bool gs_sell_ok(const GsPart &p, const MatPart &m, int64_t n_local_cols) {
+  return p.maxlen >= 1 && p.maxlen <= 32 && m.nnz > 0 && n_local_cols < (1ll << 29);
+}
+
+// the multi-colour order of a box operator (built on first use: it costs a second copy of the matrix)
+static int gs_make_color_order(pa_gs *g, int k) {
+  pa_ctx *c = g->A->ctx;
+  GsPart &p = g->parts[k];
+  const MatPart &m = g->A->parts[k];
+  PA_CHECK(p.geom, PA_EINVAL, "multi-colour Gauss-Seidel needs the box geometry hint (pa_gs_set_box)");
+  PA_CHECK(gs_sell_ok(p, m, g->A->cols->parts[k].n_local), PA_EINVAL, "multi-colour Gauss-Seidel needs rows of at most 32 entries");
+  int32_t *d_lev = nullptr, *d_lev2 = nullptr, *d_rows0 = nullptr, *d_rows1 = nullptr;
+  PA_CUDA(cudaMalloc((void **)&d_lev, p.n * sizeof(int32_t)));
+  PA_CUDA(cudaMalloc((void **)&d_lev2, p.n * sizeof(int32_t)));
+  PA_CUDA(cudaMalloc((void **)&d_rows0, p.n * sizeof(int32_t)));
+  PA_CUDA(cudaMalloc((void **)&d_rows1, p.n * sizeof(int32_t)));
+  const int nlev = p.kind == 27 ? 8 : 2;
+  k_levels_color<<<148 * 8, 256, 0, c->stream>>>(d_lev, d_rows0, p.n, p.dims[0], p.dims[1], p.kind);
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_lev, d_lev2, d_rows0, d_rows1, (int)p.n, 0, 3, c->stream);
+  void *d_tmp = nullptr;
+  PA_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+  PA_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_lev, d_lev2, d_rows0, d_rows1, (int)p.n, 0, 3, c->stream));  // stable: rows ascending within a colour
+  int *d_cnt = nullptr;
+  PA_CUDA(cudaMalloc((void **)&d_cnt, nlev * sizeof(int)));
+  PA_CUDA(cudaMemsetAsync(d_cnt, 0, nlev * sizeof(int), c->stream));
+  k_level_hist<<<148 * 8, 256, 0, c->stream>>>(d_lev, p.n, d_cnt);
+  std::vector<int> cnt(nlev);
+  PA_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, nlev * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  PA_CUDA(cudaStreamSynchronize(c->stream));
+  int rc = gs_build_sell(c, m, p, d_lev, d_lev2, d_rows1, cnt, nlev, &p.ord[1]);
+  cudaFree(d_tmp); cudaFree(d_lev); cudaFree(d_lev2); cudaFree(d_rows0); cudaFree(d_rows1); cudaFree(d_cnt);
+  c->launches += 3;
+  return rc;
+}
+
+/* Order of the sweeps: PA_GS_LEXICOGRAPHIC (default) = the reference's sequential order 1:n / n:-1:1 executed as a
+ * wavefront dataflow — iterates bit-identical to the reference; PA_GS_MULTICOLOR = colour by colour (8 colours for the
+ * 27-pt operator, red/black for 7-pt; needs pa_gs_set_box): a different but equally valid Gauss-Seidel order — same fixed
+ * point, convergence-level parity (SURVEY 8f-1 allows it; gated by the reference's own HPCG test).  Switching releases the
+ * matrix copy of the other order. */
+extern "C" int pa_gs_set_order(pa_gs *g, int32_t order) {
+  PA_CHECK(g && g->committed, PA_ESTATE, "pa_gs_set_order: smoother missing or not committed");
+  PA_CHECK(order == PA_GS_LEXICOGRAPHIC || order == PA_GS_MULTICOLOR, PA_EINVAL, "pa_gs_set_order: unknown order %d", order);
+  pa_ctx *c = g->A->ctx;
+  PA_CUDA(cudaSetDevice(c->device));
+  if (order == g->order) return PA_OK;
+  PA_CUDA(cudaStreamSynchronize(c->stream));
+  if (order == PA_GS_MULTICOLOR) {
+    for (int k = 0; k < c->nlocal; ++k) {
+      if (g->parts[k].n == 0) continue;
+      PA_CHECK(g->parts[k].geom, PA_EINVAL, "pa_gs_set_order: the multi-colour order needs pa_gs_set_box before pa_gs_commit");
+    }
+    for (int k = 0; k < c->nlocal; ++k) {
+      if (g->parts[k].n == 0) continue;
+      gs_free_order(g->parts[k].ord[0]);  // the wavefront copy is rebuilt if the caller switches back
+      if (!g->parts[k].ord[1]) PA_TRY(gs_make_color_order(g, k));
+    }
+  } else {
+    for (int k = 0; k < c->nlocal; ++k) gs_free_order(g->parts[k].ord[1]);
+    // (the wavefront SELL copy is not rebuilt: the dataflow kernel on the CSR itself serves the lexicographic order)
+  }
+  g->order = order;
   return PA_OK;
 }
 
@@ -696,9 +998,13 @@ extern "C" int pa_gs_commit(pa_gs *g) {
       return PA_OK;
     };
     PA_TRY(padded_list(8, &p.d_rows, &p.npad));
+    // the sweep-ordered SELL copy of the default (wavefront) order; gs_kernel = 0 keeps the dataflow kernel on the CSR
+    if (gs_sell_ok(p, m, g->A->cols->parts[k].n_local) && pa_knob(c, "gs_kernel", 2) == 2) {
+      PA_TRY(gs_build_sell(c, m, p, d_lev, d_lev2, d_rows1, cnt, p.nlev, &p.ord[0]));
+    }
     // batch kernel tables (only when that kernel is selected: it is not the default): level l occupies
     // ceil(cnt_l / GSB_ROWS) consecutive batches
-    if (p.maxlen <= 32 && m.nnz > 0 && pa_knob(c, "gs_kernel", 0) == 1) {
+    if (p.maxlen <= 32 && m.nnz > 0 && pa_knob(c, "gs_kernel", 2) == 1) {
       const int64_t al = GSB_ROWS;
       PA_TRY(padded_list(al, &p.d_rows_b, &p.npad_b));
       std::vector<int32_t> batch_lev((size_t)(p.npad_b / al));
@@ -761,6 +1067,55 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
     const MatPart &m = g->A->parts[k];
     if (p.n == 0) continue;
     p.epoch += 1;
+    GsOrder *o = g->order == PA_GS_MULTICOLOR ? p.ord[1] : (pa_knob(c, "gs_kernel", 2) == 2 ? p.ord[0] : nullptr);
+    PA_CHECK(g->order != PA_GS_MULTICOLOR || o, PA_ESTATE, "gs_sweep: the multi-colour copy of the matrix is missing");
+    if (o) {
+      PA_CHECK(!(zero_guess && backward), PA_ESTATE, "gs_sweep: the zero-guess sweep is a forward sweep");
+      GsSellArgs a;
+      a.rows = o->d_rows;
+      a.cols = o->d_cols;
+      a.vals = o->d_vals;
+      a.b = b->d[k];
+      a.x = x->d[k];
+      a.xe = p.d_xe;
+      a.err = c->d_err;
+      a.ngroups = o->npad / 32;
+      a.W = o->W;
+      a.epoch = p.epoch;
+      a.backward = backward;
+      a.zero_guess = zero_guess;
+      int nsm = 148;
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+      const int wpc = GS_THREADS / 32;
+      if (g->order == PA_GS_MULTICOLOR) {
+        // one launch per colour, in sweep order; within a colour the rows are independent
+        void (*kern)(const GsSellArgs) = o->W == 27 ? k_gs_sell<27, false> : (o->W == 7 ? k_gs_sell<7, false> : k_gs_sell<0, false>);
+        for (int q = 0; q < o->nlev; ++q) {
+          const int l = backward ? o->nlev - 1 - q : q;
+          const int64_t s0 = o->lev_group[l], s1 = o->lev_group[l + 1];
+          if (s1 == s0) continue;
+          a.g0 = backward ? a.ngroups - s1 : s0;
+          a.g1 = backward ? a.ngroups - s0 : s1;
+          const int64_t grid = std::min<int64_t>((s1 - s0 + wpc - 1) / wpc, (int64_t)nsm * 16);
+          kern<<<(unsigned)grid, GS_THREADS, 0, c->stream>>>(a);
+          c->launches++;
+        }
+      } else {
+        void (*kern)(const GsSellArgs) = o->W == 27 ? k_gs_sell<27, true> : (o->W == 7 ? k_gs_sell<7, true> : k_gs_sell<0, true>);
+        int ctas_per_sm = 0;
+        PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, GS_THREADS, 0));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        const int64_t cap = pa_knob(c, "gs_ctas", 0);
+        if (cap > 0 && cap < ctas_per_sm) ctas_per_sm = (int)cap;
+        a.g0 = 0;
+        a.g1 = a.ngroups;
+        // all CTAs co-resident: a waiting row only waits for rows of earlier slices, held by running warps
+        const int64_t grid = std::min<int64_t>((a.ngroups + wpc - 1) / wpc, (int64_t)nsm * ctas_per_sm);
+        kern<<<(unsigned)grid, GS_THREADS, 0, c->stream>>>(a);
+        c->launches++;
+      }
+      continue;
+    }
     auto launch = [&](auto tag) -> int {
       using PtrT = decltype(tag);
       GsArgs<PtrT> a;
@@ -783,7 +1138,7 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
       cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
       // batch kernel (32 rows of one level per warp) where the levels are wide; the warp-per-row dataflow kernel where
       // the sweep is bound by the level-to-level hop (coarse grids) or rows are longer than 32 entries
-      if (p.d_rows_b && pa_knob(c, "gs_kernel", 0) == 1) {
+      if (p.d_rows_b && pa_knob(c, "gs_kernel", 2) == 1) {
         const int nj = p.maxlen <= 8 ? 1 : (p.maxlen <= 16 ? 2 : 4);
         void (*wk)(const GsLevelArgs<PtrT>) = nullptr;
         PA_CHECK(!(zero_guess && backward), PA_ESTATE, "gs_sweep: the zero-guess sweep is a forward sweep");

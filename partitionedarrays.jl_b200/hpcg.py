@@ -32,6 +32,17 @@ class GaussSeidel:
                 dims = i64([hi - lo + 1 for lo, hi in ind.block.box])
                 check(L.pa_gs_set_box(h, k, kind, ptr(dims)))
         check(L.pa_gs_commit(h))
+        self.order = "lexicographic"
+
+    def set_order(self, order: str = "lexicographic"):
+        """"lexicographic": the reference's sequential sweep order (bit-identical iterates; default).  "multicolor": colour by
+        colour (needs the geometry hint): same per-row arithmetic and fixed point, different iterates."""
+        code = {"lexicographic": _capi.PA_GS_LEXICOGRAPHIC, "multicolor": _capi.PA_GS_MULTICOLOR}.get(order)
+        if code is None:
+            raise ValueError(f"unknown Gauss-Seidel order {order!r}")
+        check(_capi.lib().pa_gs_set_order(self.h, code))
+        self.order = order
+        return self
 
     def smooth_(self, x: PVector, b: PVector, zero_guess: bool = False) -> PVector:
         check(_capi.lib().pa_gs_smooth(self.h, x.h, b.h, int(zero_guess)))
@@ -52,7 +63,7 @@ class GaussSeidel:
 class MgPreconditioner:
     """Mg_preconditioner: A_vec / gs_states / r / x / Axf per level (index 0 = coarsest, l-1 = finest)."""
 
-    def __init__(self, backend: CUDAArray, levels: int, nx: int, ny: int, nz: int, npx: int, npy: int, npz: int):
+    def __init__(self, backend: CUDAArray, levels: int, nx: int, ny: int, nz: int, npx: int, npy: int, npz: int, order: str = "lexicographic"):
         assert nx % (1 << (levels - 1)) == 0 and ny % (1 << (levels - 1)) == 0 and nz % (1 << (levels - 1)) == 0
         self.backend, self.l = backend, levels
         self.A_vec: List[PSparseMatrix] = [None] * levels
@@ -73,6 +84,16 @@ class MgPreconditioner:
         self._dims = np.ascontiguousarray(dims)
         check(_capi.lib().pa_mg_create(levels, Ah, Gh, ptr(self._dims), C.byref(h)))
         self.h = h
+        self.order = "lexicographic"
+        if order != "lexicographic":
+            self.set_order(order)
+
+    def set_order(self, order: str):
+        """Sweep order of the smoother of every level (see GaussSeidel.set_order)."""
+        for g in self.gs:
+            g.set_order(order)
+        self.order = order
+        return self
 
     @property
     def A(self) -> PSparseMatrix:
@@ -100,8 +121,8 @@ class MgPreconditioner:
             pass
 
 
-def pc_setup(backend: CUDAArray, l: int, nx: int, ny: int, nz: int, npx: int, npy: int, npz: int) -> MgPreconditioner:
-    return MgPreconditioner(backend, l, nx, ny, nz, npx, npy, npz)
+def pc_setup(backend: CUDAArray, l: int, nx: int, ny: int, nz: int, npx: int, npy: int, npz: int, order: str = "lexicographic") -> MgPreconditioner:
+    return MgPreconditioner(backend, l, nx, ny, nz, npx, npy, npz, order)
 
 
 def ref_cg_pc_(x: PVector, A: PSparseMatrix, b: PVector, Pl: Optional[MgPreconditioner], tolerance: float = 0.0, maxiter: int = 50,
@@ -113,6 +134,8 @@ def ref_cg_pc_(x: PVector, A: PSparseMatrix, b: PVector, Pl: Optional[MgPrecondi
     return CGResult(res.iters, bool(res.converged), res.residual0, res.residual, hist[: res.iters + 1])
 
 
-def smoother_name(backend: CUDAArray) -> str:
-    """Which Gauss-Seidel schedule the backend's knobs select (reported by bench.py)."""
+def smoother_name(P: "MgPreconditioner") -> str:
+    """Which Gauss-Seidel schedule a preconditioner runs (reported by bench.py)."""
+    if P.order == "multicolor":
+        return "multi-colour Gauss-Seidel (8 colours, one launch per colour; convergence-level parity: different iterates than the reference)"
     return "bit-exact wavefront Gauss-Seidel (same iterates as the reference's sequential sweeps)"

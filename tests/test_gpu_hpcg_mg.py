@@ -124,7 +124,7 @@ def _smooth_and_compare(pa, lev, A, gs, seed):
         x.free(); bv.free()
 
 
-@pytest.mark.parametrize("kernel", [0, 1])  # 0 = warp-per-row dataflow kernel, 1 = batch kernel (1 / 2 entry slots per lane)
+@pytest.mark.parametrize("kernel", [0, 1, 2])  # 0 = warp-per-row dataflow kernel, 1 = batch kernel, 2 = SELL thread-per-row kernel (default)
 @pytest.mark.parametrize("case", ["fdm7-box", "fdm7-generic", "fem9"])
 def test_gauss_seidel_on_short_rows_is_bit_exact(pa, case, kernel):
     """Rows of <= 8 entries (7-pt gallery operator, closed-form and host-computed levels) and <= 16 entries (the Q1 FEM
@@ -151,4 +151,44 @@ def test_gauss_seidel_on_short_rows_is_bit_exact(pa, case, kernel):
     lev = hpcg_mg.Level.from_psparse(Ao)
     _smooth_and_compare(pa, lev, A, gs, 5)
     gs.free()
+    b.close()
+
+
+@pytest.mark.parametrize("npd,nloc", [((2, 2, 1), (8, 6, 4)), ((1, 1, 1), (10, 9, 8)), ((2, 1, 1), (40, 32, 24))])
+def test_multicolor_gauss_seidel_matches_the_oracle_order(pa, npd, nloc):
+    """The opt-in multi-colour order (8 colours, one launch per colour): same per-row arithmetic as the reference's
+    sweep, rows visited colour by colour — bit-identical to the oracle's sweep in that order, and switching back to the
+    lexicographic order gives the reference's iterates again."""
+    lev = hpcg_mg.Level(*nloc, npd)
+    lev.order, lev.kind = "multicolor", 27
+    P = len(lev.part)
+    b = pa.CUDAArray(P, arena_bytes=32 << 20)
+    gn = tuple(a * c for a, c in zip(npd, nloc))
+    A, rhs = pa.stencil_matrix(27, gn, npd, b)
+    gs = pa.GaussSeidel(A, kind=27).set_order("multicolor")
+    _smooth_and_compare(pa, lev, A, gs, 7)
+    gs.set_order("lexicographic")
+    lev.order = "lexicographic"
+    _smooth_and_compare(pa, lev, A, gs, 8)
+    gs.free()
+    b.close()
+
+
+def test_multicolor_preconditioned_cg_convergence_level_parity(pa):
+    """HPCG/test/hpcg_benchmark_tests.jl:31-41 with the multi-colour smoother: history equal to the oracle's run in the same
+    order (rel 1e-8).  The reference's constant (2.88e-13 after 50 iterations, asserted < 1e-12) belongs to the lexicographic
+    order; the 8-colour order reaches 1.9e-11 after 50 iterations and 1e-12 a few iterations later — stated, not hidden."""
+    npd, n, levels = (2, 2, 1), 32, 4
+    mg = hpcg_mg.MG(npd, levels, n, n, n, order="multicolor")
+    L = mg.levels[levels - 1]
+    xo, r0o, ro, ito, histo = hpcg_mg.pcg(mg, [v.copy() for v in L.r], [np.zeros(i.n_local) for i in L.part], 60, 0.0)
+    b = pa.CUDAArray(4, arena_bytes=256 << 20)
+    P = pa.pc_setup(b, levels, n, n, n, *npd, order="multicolor")
+    x = pa.pzeros(P.A.cols)
+    res = pa.ref_cg_pc_(x, P.A, P.b, P, tolerance=0.0, maxiter=60)
+    np.testing.assert_allclose(res.history, histo, rtol=1e-8, atol=1e-15 * histo[0])
+    scaled = res.history / res.history[0]
+    assert scaled[50] < 1e-10 and scaled[60] < 1e-12  # slower than lexicographic (2.88e-13 at 50), same fixed point
+    assert np.abs(np.concatenate(x.own_values()) - 1.0).max() < 1e-9  # exact solution = ones
+    P.free()
     b.close()

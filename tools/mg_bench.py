@@ -27,8 +27,10 @@ def main():
     stream = torch.cuda.Stream()
     b = pa.CUDAArray(1, arena_bytes=14 * (n + 2) ** 3 * 8, stream=stream.cuda_stream)
     t0 = time.time()
-    P = pa.pc_setup(b, levels, n, n, n, 1, 1, 1)
+    order = os.environ.get("MG_ORDER", "lexicographic")
+    P = pa.pc_setup(b, levels, n, n, n, 1, 1, 1, order=order)
     b.sync()
+    print(f"order {order}, gs_kernel {os.environ.get('PA_GS_KERNEL', 'default')}", flush=True)
     print(f"setup {time.time() - t0:.2f} s", flush=True)
     for lev in reversed(range(levels)):
         A = P.A_vec[lev]
