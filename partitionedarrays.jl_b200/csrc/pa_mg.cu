@@ -66,6 +66,11 @@ struct GsOrder {
   int32_t *d_cols = nullptr;   // [npad * W]
   double *d_vals = nullptr;    // [npad * W]
   std::vector<int64_t> lev_group;  // first slice of every level, size nlev + 1 (one launch per colour)
+  // level-gated sweeps (MODE 2): level of every slice, slices per level, slices finished per level summed over all sweeps
+  int32_t *d_slice_lev = nullptr;
+  uint32_t *d_lev_n = nullptr;
+  unsigned long long *d_done = nullptr;
+  unsigned long long sweeps = 0;
 };
 #define GS_COL_FRESH (1 << 30)
 #define GS_COL_OWN (1 << 29)
@@ -598,12 +603,23 @@ struct GsSellArgs {
   int64_t ngroups;
   int W;             // entry slots per row (runtime copy of the template parameter; used when W == 0)
   int epoch, backward, zero_guess;
+  // MODE 2: per-level completion counters
+  const int32_t *slice_lev;
+  const uint32_t *lev_n;
+  unsigned long long *done;
+  unsigned long long sweep;
+  int nlev;
 };
 
 // minBlocksPerSM is explicit: with maxThreads alone ptxas aims at full occupancy and sinks every load next to its use,
 // which serialises the gathers of a batch (the same effect as in k_spmv_tma)
-template <int W, bool SYNC>
-__global__ void __launch_bounds__(GS_THREADS, (SYNC ? 2 : 3)) k_gs_sell(const GsSellArgs a) {
+// MODE 0: no waiting (one launch per level/colour)   MODE 1: per-row dataflow (published (value, epoch) pairs)
+// MODE 2: level gate — a slice of level L starts when the counter of level L-1 (L+1 backward) says all its slices are
+//         stored; one lane per warp polls one hot line, the other lanes cost nothing while they wait, and the NEW values
+//         are then simply what x holds (no per-row flags, no 16-byte pairs)
+template <int W, int MODE>
+__global__ void __launch_bounds__(GS_THREADS, (MODE == 1 ? 2 : 3)) k_gs_sell(const GsSellArgs a) {
+  constexpr bool SYNC = MODE == 1;
   constexpr int B = W == 27 ? 9 : (W == 7 ? 7 : 8);  // slots per batch: loads of a batch are in flight together
   const int WD = W ? W : a.W;
   const int lane = threadIdx.x & 31;
@@ -625,9 +641,32 @@ __global__ void __launch_bounds__(GS_THREADS, (SYNC ? 2 : 3)) k_gs_sell(const Gs
         if (lane < WD) gs_prefetch_l2(nc + (size_t)lane * 128);
       }
     }
-    if (row < 0) continue;  // padding row (levels are padded to whole slices); no warp-level primitive below
-    double s = __ldg(a.b + row), d = 0.0;
-    const double xold = a.zero_guess ? 0.0 : gs_ld_x(a.x + row, keep);  // nobody writes x[row] before this row does
+    if (MODE != 2 && row < 0) continue;  // padding row (levels are padded to whole slices); no warp-level primitive below
+    double s = row >= 0 ? __ldg(a.b + row) : 0.0, d = 0.0;
+    const double xold = (a.zero_guess || row < 0) ? 0.0 : gs_ld_x(a.x + row, keep);  // nobody writes x[row] before this row does
+    int lev = 0;
+    if (MODE == 2) {
+      lev = a.slice_lev[g];
+      const int glev = a.backward ? lev + 1 : lev - 1;  // the level whose completion opens this one (and, by induction, all before it)
+      if (glev >= 0 && glev < a.nlev) {
+        if (lane == 0) {
+          const unsigned long long target = a.sweep * (unsigned long long)a.lev_n[glev];
+          long long t0 = 0;
+          while (gs_ld_relaxed(a.done + glev) < target) {
+            if (!t0) {
+              t0 = clock64();
+            } else if (clock64() - t0 > GS_SPIN_LIMIT) {
+              *a.err = 3;
+              break;
+            }
+            __nanosleep(20);
+          }
+          gs_fence_acq_rel();  // acquire: relaxed polls + one fence; __syncwarp extends it to the warp
+        }
+        __syncwarp();
+      }
+    }
+    if (row >= 0) {
 #pragma unroll 1
     for (int k0 = 0; k0 < WD; k0 += B) {
       int32_t code[B];
@@ -653,7 +692,7 @@ __global__ void __launch_bounds__(GS_THREADS, (SYNC ? 2 : 3)) k_gs_sell(const Gs
         if (fresh[u]) {
           asm volatile("ld.relaxed.gpu.global.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(w0[u]), "=l"(w1[u]) : "l"(a.xe + c), "l"(keep) : "memory");
         } else if (use[u]) {
-          xv[u] = SYNC ? gs_ld_x(a.x + c, keep) : a.x[c];
+          xv[u] = MODE != 0 ? gs_ld_x(a.x + c, keep) : a.x[c];  // x changes during a one-launch sweep: through L2
         }
       }
 #pragma unroll
@@ -669,6 +708,7 @@ __global__ void __launch_bounds__(GS_THREADS, (SYNC ? 2 : 3)) k_gs_sell(const Gs
               *a.err = 3;
               break;
             }
+            __nanosleep(40);  // 32 lanes polling 32 different sectors flat out saturate the SM's LSU and starve the rows that can run
           }
           xv[u] = __longlong_as_double((long long)((w1[u] << 32) | (w0[u] & 0xffffffffull)));
         }
@@ -684,6 +724,15 @@ __global__ void __launch_bounds__(GS_THREADS, (SYNC ? 2 : 3)) k_gs_sell(const Gs
     s = __ddiv_rn(s, d);
     if (SYNC) gs_publish(a.xe + row, a.x + row, s, epoch, keep);
     else a.x[row] = s;
+    }  // row >= 0
+    if (MODE == 2) {
+      // publish the slice: the warp's stores are ordered before lane 0's release (syncwarp + cumulative fence)
+      __syncwarp();
+      if (lane == 0) {
+        gs_fence_acq_rel();
+        asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(a.done + lev) : "memory");
+      }
+    }
   }
 }
 
@@ -758,6 +807,9 @@ static void gs_free_order(GsOrder *&o) {
   cudaFree(o->d_rows);
   cudaFree(o->d_cols);
   cudaFree(o->d_vals);
+  cudaFree(o->d_slice_lev);
+  cudaFree(o->d_lev_n);
+  cudaFree(o->d_done);
   delete o;
   o = nullptr;
 }
@@ -842,6 +894,22 @@ static int gs_build_sell(pa_ctx *c, const MatPart &m, GsPart &p, const int32_t *
   else
     k_gs_build_sell<int32_t><<<148 * 8, 256, 0, c->stream>>>((const int32_t *)m.d_rowptr, m.d_colval, m.d_nzval, o->d_rows, o->npad, o->W, p.n, d_lev, o->d_cols, o->d_vals);
   PA_CUDA(cudaGetLastError());
+  {  // level of every slice, slices per level, completion counters (level-gated sweeps)
+    const int64_t ng = o->npad / 32;
+    std::vector<int32_t> sl((size_t)ng);
+    std::vector<uint32_t> ln((size_t)nlev);
+    for (int l = 0; l < nlev; ++l) {
+      ln[l] = (uint32_t)(o->lev_group[l + 1] - o->lev_group[l]);
+      for (int64_t q = o->lev_group[l]; q < o->lev_group[l + 1]; ++q) sl[(size_t)q] = l;
+    }
+    PA_CUDA(cudaMalloc((void **)&o->d_slice_lev, std::max<int64_t>(ng, 1) * sizeof(int32_t)));
+    PA_CUDA(cudaMalloc((void **)&o->d_lev_n, (size_t)nlev * sizeof(uint32_t)));
+    PA_CUDA(cudaMalloc((void **)&o->d_done, (size_t)nlev * sizeof(unsigned long long)));
+    PA_CUDA(cudaMemcpyAsync(o->d_slice_lev, sl.data(), (size_t)ng * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    PA_CUDA(cudaMemcpyAsync(o->d_lev_n, ln.data(), (size_t)nlev * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    PA_CUDA(cudaMemsetAsync(o->d_done, 0, (size_t)nlev * sizeof(unsigned long long), c->stream));
+    PA_CUDA(cudaStreamSynchronize(c->stream));
+  }
   PA_CUDA(cudaStreamSynchronize(c->stream));
   cudaFree(d_shift);
   c->launches += 2;
@@ -1084,12 +1152,17 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
       a.epoch = p.epoch;
       a.backward = backward;
       a.zero_guess = zero_guess;
+      a.slice_lev = nullptr;
+      a.lev_n = nullptr;
+      a.done = nullptr;
+      a.sweep = 0;
+      a.nlev = o->nlev;
       int nsm = 148;
       cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
       const int wpc = GS_THREADS / 32;
       if (g->order == PA_GS_MULTICOLOR) {
         // one launch per colour, in sweep order; within a colour the rows are independent
-        void (*kern)(const GsSellArgs) = o->W == 27 ? k_gs_sell<27, false> : (o->W == 7 ? k_gs_sell<7, false> : k_gs_sell<0, false>);
+        void (*kern)(const GsSellArgs) = o->W == 27 ? k_gs_sell<27, 0> : (o->W == 7 ? k_gs_sell<7, 0> : k_gs_sell<0, 0>);
         for (int q = 0; q < o->nlev; ++q) {
           const int l = backward ? o->nlev - 1 - q : q;
           const int64_t s0 = o->lev_group[l], s1 = o->lev_group[l + 1];
@@ -1101,7 +1174,15 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
           c->launches++;
         }
       } else {
-        void (*kern)(const GsSellArgs) = o->W == 27 ? k_gs_sell<27, true> : (o->W == 7 ? k_gs_sell<7, true> : k_gs_sell<0, true>);
+        // gs_sell_mode 2 (default): level gate; 1: per-row dataflow
+        const bool gate = pa_knob(c, "gs_sell_mode", 2) == 2;
+        void (*kern)(const GsSellArgs) = gate ? (o->W == 27 ? k_gs_sell<27, 2> : (o->W == 7 ? k_gs_sell<7, 2> : k_gs_sell<0, 2>))
+                                              : (o->W == 27 ? k_gs_sell<27, 1> : (o->W == 7 ? k_gs_sell<7, 1> : k_gs_sell<0, 1>));
+        a.slice_lev = o->d_slice_lev;
+        a.lev_n = o->d_lev_n;
+        a.done = o->d_done;
+        a.sweep = gate ? ++o->sweeps : 0;  // every gated sweep advances every level counter by its slice count, once
+        a.nlev = o->nlev;
         int ctas_per_sm = 0;
         PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, GS_THREADS, 0));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
