@@ -133,6 +133,89 @@ __global__ void __launch_bounds__(PA_RED_THREADS)
   if (j < n) u[j] = __dadd_rn(__dmul_rn(1.0, r[j]), __dmul_rn(beta, u[j]));
 }
 
+// The same update with consistent!(u) fused in (jobs of several parts): the ghost exchange rides inside the kernel that
+// PRODUCES u, so the SpMV that follows is purely local and no exchange latency is exposed:
+//   A  every CTA updates its share of the BOUNDARY entries of u (the own entries some neighbour reads: the plan's assemble
+//      destinations); the last CTA through the ticket publishes "my boundary is final" to the neighbours (system scope);
+//   B  the bulk: all other own entries (a bitmap marks the boundary entries: they must not be updated twice) — ~0.5 ms of
+//      pure HBM streaming during which the neighbours' boundaries become final;
+//   C  every CTA waits for the neighbours' signals (they arrived long ago) and pulls its share of the ghost values from
+//      the owners' HBM over NVLink into u's ghost slots; the last CTA tells the neighbours "done reading" and advances
+//      the exchange epoch.
+struct XchgArgs {
+  const int32_t *bnd;        // boundary local ids
+  int64_t n_bnd;
+  const uint32_t *bitmap;    // bit l: local entry l is a boundary entry
+  const int32_t *lid, *slot, *rlid;  // the consistent! table (ghost slot <- neighbour slot, local id on the owner)
+  int64_t n_cons;
+  PeerPtrs peers;
+  unsigned long long *epoch;
+  FlagPtrs arrive_dst, arrive_src, done_dst;
+  int nnbr;
+  unsigned *tickets;         // [2]
+  int *err;
+};
+
+__global__ void __launch_bounds__(PA_RED_THREADS)
+    k_cg_direction_xchg(double *u, const double *r, int64_t n_own, RedWait w, double *hist, const int *it, const XchgArgs xa) {
+  __shared__ double sm[PA_MAX_NBR + 1];
+  __shared__ bool last;
+  const int i = *it;
+  double rho, rho_prev = 1.0;
+  if (i == 0) {
+    rho = hist[0];
+  } else {
+    rho = pa_red_sum(w, sm);
+    rho_prev = hist[i - 1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) hist[i] = rho;
+  }
+  const double beta = cg_ratio(rho, rho_prev);
+  const unsigned long long e = *xa.epoch + 1ull;  // nobody writes *epoch before every CTA has passed the second ticket
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  // ---- A: boundary entries first
+  for (int64_t j = tid; j < xa.n_bnd; j += nth) {
+    const int32_t l = xa.bnd[j];
+    u[l] = __dadd_rn(__dmul_rn(1.0, r[l]), __dmul_rn(beta, u[l]));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();  // this CTA's boundary stores, before it is counted in
+    last = atomicInc(xa.tickets, gridDim.x - 1) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && (int)threadIdx.x < xa.nnbr) {
+    __threadfence_system();
+    pa_st_release_sys(xa.arrive_dst.p[threadIdx.x], e);
+  }
+  // ---- B: the bulk of the own entries (boundary entries are skipped)
+  for (int64_t j = tid * 2; j < n_own; j += nth * 2) {
+    const unsigned bits = xa.bitmap ? ((xa.bitmap[j >> 5] >> (j & 31)) & 3u) : 0u;  // j is even: both bits in one word
+    if (bits == 0u && j + 1 < n_own) {
+      double2 rv = *reinterpret_cast<const double2 *>(r + j), uv = *reinterpret_cast<double2 *>(u + j);
+      uv.x = __dadd_rn(__dmul_rn(1.0, rv.x), __dmul_rn(beta, uv.x));
+      uv.y = __dadd_rn(__dmul_rn(1.0, rv.y), __dmul_rn(beta, uv.y));
+      *reinterpret_cast<double2 *>(u + j) = uv;
+    } else {
+      if (!(bits & 1u)) u[j] = __dadd_rn(__dmul_rn(1.0, r[j]), __dmul_rn(beta, u[j]));
+      if (j + 1 < n_own && !(bits & 2u)) u[j + 1] = __dadd_rn(__dmul_rn(1.0, r[j + 1]), __dmul_rn(beta, u[j + 1]));
+    }
+  }
+  // ---- C: the ghost values
+  if ((int)threadIdx.x < xa.nnbr) pa_spin_until(xa.arrive_src.p[threadIdx.x], e, xa.err);
+  __syncthreads();
+  for (int64_t j = tid; j < xa.n_cons; j += nth) u[xa.lid[j]] = __ldcg(xa.peers.p[xa.slot[j]] + xa.rlid[j]);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicInc(xa.tickets + 1, gridDim.x - 1) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    if ((int)threadIdx.x < xa.nnbr) pa_st_release_sys(xa.done_dst.p[threadIdx.x], e);
+    if (threadIdx.x == 0) *xa.epoch = e;
+  }
+}
+
 __global__ void __launch_bounds__(PA_RED_THREADS)
     k_cg_update_fold(double *x, const double *u, double *r, const double *c, int64_t n_local, int64_t n_own, RedWait w, DoneWait dw,
                      RedPush push, const double *hist, int *it, double *blockpart, unsigned *ticket) {
@@ -400,8 +483,42 @@ extern "C" int pa_cg_precond(pa_mat *A, pa_vec *x, const pa_vec *b, pa_mg *mg, i
       const int64_t per = 2 * PA_RED_THREADS * 4;
       int ugrid = (int)((xp.n_local + per - 1) / per);
       ugrid = ugrid < 1 ? 1 : (ugrid > PA_RED_BLOCKS ? PA_RED_BLOCKS : ugrid);
+      // consistent!(u) fused into the kernel that produces u (several parts, own-first layout, default mul! schedule)
+      const bool fuse_x = c->nparts > 1 && xp.prefix && pa_knob(c, "cg_fuse_exchange", 1) != 0 && pa_knob(c, "spmv_strategy", -1) <= 0;
+      XchgArgs xa;
+      if (fuse_x) {
+        xa.bnd = xp.d_asm_dst;
+        xa.n_bnd = xp.n_asm_dst;
+        xa.bitmap = xp.d_bnd_bitmap;
+        xa.lid = xp.d_ghost_lid;
+        xa.slot = xp.d_ghost_slot;
+        xa.rlid = xp.d_ghost_rlid;
+        xa.n_cons = xp.n_cons;
+        xa.peers = pa_peer_ptrs(u, 0);
+        xa.epoch = c->d_epoch;
+        PA_TRY(pa_sync_flags(x->plan, &xa.arrive_dst, &xa.arrive_src, &xa.done_dst, &xa.nnbr));
+        xa.tickets = c->d_cons_ticket;
+        xa.err = c->d_err;
+      }
+      int xgrid = ugrid;
+      if (fuse_x) {  // every CTA must be resident: a CTA waits (phase C) for signals that need all CTAs of the peers' grids
+        int per_sm = 0, nsm = 148;
+        PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_direction_xchg, PA_RED_THREADS, 0));
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+        xgrid = std::max(1, std::min(ugrid, nsm * std::max(per_sm, 1)));
+      }
       auto iteration = [&]() -> int {
         PA_TRY(pa_before_write(c));  // (pending "done" of the setup product; nothing inside the loop)
+        if (fuse_x) {
+          k_cg_direction_xchg<<<xgrid, PA_RED_THREADS, 0, c->stream>>>(u->d[0], r->d[0], xp.n_own, rw, d_hist, d_it, xa);
+          c->launches++;
+          PA_TRY(pa_spmv_local(A, u, cv, 1.0, 0.0, 0, u, nullptr, /*fold=*/1));  // purely local: the ghosts are in place
+          k_cg_update_fold<<<ugrid, PA_RED_THREADS, 0, c->stream>>>(x->d[0], u->d[0], r->d[0], cv->d[0], xp.n_local, xp.n_own, rw, dw, rpush,
+                                                                    d_hist, d_it, c->d_blockpart, c->d_ticket);
+          c->launches++;
+          PA_CUDA(cudaGetLastError());
+          return PA_OK;
+        }
         k_cg_direction<<<ugrid, PA_RED_THREADS, 0, c->stream>>>(u->d[0], r->d[0], xp.n_local, rw, d_hist, d_it);
         c->launches++;
         PA_TRY(pa_spmv_dot(A, u, cv, 1.0, 0.0, PA_SPMV_SKIP_GHOST_REFRESH, u, nullptr, /*fold=*/1));
@@ -422,7 +539,8 @@ extern "C" int pa_cg_precond(pa_mat *A, pa_vec *x, const pa_vec *b, pa_mg *mg, i
       if (tol <= 0.0 && maxiter >= 4 && pa_knob(c, "cg_graph", 1) != 0) {
         PA_TRY(iteration());  // iteration 0 eagerly (lazy allocations, tile tables)
         it = 1;
-        if (!(W->exec && W->exec_kind == 2)) {
+        const int kind_id = fuse_x ? 3 : 2;
+        if (!(W->exec && W->exec_kind == kind_id)) {
           if (W->exec) cudaGraphExecDestroy(W->exec);
           W->exec = nullptr;
           const int64_t l0 = c->launches;
@@ -441,7 +559,7 @@ extern "C" int pa_cg_precond(pa_mat *A, pa_vec *x, const pa_vec *b, pa_mg *mg, i
             c->pending_done.clear();
             PA_CUDA(cudaStreamSynchronize(c->stream));
           } else {
-            W->exec_kind = 2;
+            W->exec_kind = kind_id;
           }
         }
         if (W->exec) {

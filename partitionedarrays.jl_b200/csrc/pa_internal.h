@@ -104,7 +104,7 @@ struct pa_ctx {
   int64_t launches = 0;
   std::vector<pa_plan *> pending_done;  // plans whose neighbours still have to report "done reading"
   std::map<std::string, int64_t> knobs;
-  unsigned *d_cons_ticket = nullptr;    // last-CTA ticket of the fused signal+gather+done kernel
+  unsigned *d_cons_ticket = nullptr;    // [2] last-CTA tickets of the fused signal+gather+done kernels
   std::vector<CgWork *> cg_work;        // cached CG workspaces (work vectors, history, captured graph) by (A, x, b)
   uint64_t next_uid = 1;                // identity of matrices / vectors (cache keys survive address reuse)
   double cg_timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // last PA_CG_TIMING solve: ddot, waxpby, spmv, precond, total (ms), iterations
@@ -131,6 +131,9 @@ struct PlanPart {
   // assemble!: destinations (own lids) with their contributions grouped in neighbour order
   int32_t *d_asm_dst = nullptr, *d_asm_ptr = nullptr, *d_asm_slot = nullptr, *d_asm_rlid = nullptr;
   int64_t n_asm_dst = 0;
+  // the same destinations as a bitmap over the local ids (bit l set: a neighbour reads/writes local entry l): lets a
+  // streaming kernel treat the boundary entries separately (exchange fused into the producer of the vector)
+  uint32_t *d_bnd_bitmap = nullptr;
 };
 
 struct pa_plan {
@@ -164,6 +167,7 @@ struct MatPart {
   double *d_dotpart = nullptr;  // per-CTA partials of the fused dot epilogue
   unsigned *d_dot_ticket = nullptr;  // last-CTA ticket of the folded dot epilogue
   unsigned long long *d_arrive = nullptr;  // fused consistent! (SpMV MODE 4): CTAs counted in, over all launches
+  std::map<int, unsigned char *> tile_ghost;  // MODE 4: per tile size, "tile holds a ghost column" flags
   int64_t arrive_grid = 0;
   // COO pattern cache (the reference's K of sparse_matrix(...; reuse=true)): sorted permutation + segment starts
   int32_t *d_coo_perm = nullptr, *d_coo_seg = nullptr;

@@ -153,8 +153,8 @@ extern "C" int pa_ctx_create(int32_t nparts_global, int32_t nlocal, const int32_
   PA_CUDA(cudaMemsetAsync(c->d_red_epoch, 0, sizeof(unsigned long long), c->stream));
   PA_CUDA(cudaMalloc((void **)&c->d_err, sizeof(int)));
   PA_CUDA(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
-  PA_CUDA(cudaMalloc((void **)&c->d_cons_ticket, sizeof(unsigned)));
-  PA_CUDA(cudaMemsetAsync(c->d_cons_ticket, 0, sizeof(unsigned), c->stream));
+  PA_CUDA(cudaMalloc((void **)&c->d_cons_ticket, 2 * sizeof(unsigned)));
+  PA_CUDA(cudaMemsetAsync(c->d_cons_ticket, 0, 2 * sizeof(unsigned), c->stream));
   PA_CUDA(cudaHostAlloc((void **)&c->h_scal, PA_NSCAL * sizeof(double), cudaHostAllocDefault));
   PA_CUDA(cudaHostAlloc((void **)&c->h_err, sizeof(int), cudaHostAllocDefault));
   *c->h_err = 0;
@@ -749,6 +749,11 @@ extern "C" int pa_plan_commit(pa_plan *plan, int64_t sym_n_local) {
       if (!dst.empty()) PA_TRY(upload(&pp.d_asm_ptr, ptr, c->stream));
       PA_TRY(upload(&pp.d_asm_slot, s2, c->stream));
       PA_TRY(upload(&pp.d_asm_rlid, r2, c->stream));
+      if (pp.prefix && !dst.empty()) {
+        std::vector<uint32_t> bm((size_t)(pp.n_local + 31) / 32 + 1, 0u);
+        for (int32_t l : dst) bm[(size_t)l >> 5] |= 1u << (l & 31);
+        PA_TRY(upload(&pp.d_bnd_bitmap, bm, c->stream));
+      }
     }
     if (!pp.prefix) {
       PA_TRY(upload(&pp.d_own_to_local, pp.own_to_local, c->stream));
@@ -796,6 +801,7 @@ extern "C" int pa_plan_destroy(pa_plan *plan) {
     cudaFree(pp.d_asm_ptr);
     cudaFree(pp.d_asm_slot);
     cudaFree(pp.d_asm_rlid);
+    cudaFree(pp.d_bnd_bitmap);
   }
   delete plan;
   return PA_OK;

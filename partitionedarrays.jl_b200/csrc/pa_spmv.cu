@@ -45,6 +45,7 @@ struct SpmvArgs {
   int fold;
   unsigned *dot_ticket;
   RedPush push;
+  const unsigned char *tile_ghost;  // MODE 4: tile t holds a row with a ghost column (computed once per matrix and tile size)
 };
 
 // The matrix stream is read exactly once: keep it out of L1 and mark it evict-first in L2 so the
@@ -221,7 +222,7 @@ __device__ __noinline__ void spmv_wait_gather(const unsigned long long *arrive, 
 //         are counted in and read the slots through L2.  Own-block products never wait: on a banded operator only
 //         the first tiles of the persistent grid can meet the gather still in flight.
 template <typename PtrT, int MODE, int BATCH>
-__global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MODE == 1 || MODE == 4 ? 3 : 4)))) k_spmv_tma(const SpmvArgs<PtrT> a, const TmaCfg cfg) {
+__global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MODE == 1 ? 3 : 4)))) k_spmv_tma(const SpmvArgs<PtrT> a, const TmaCfg cfg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int ROWS = cfg.rows, CAP = cfg.cap, S = cfg.stages;
   // layout: val[S][CAP+2] | col[S][CAP+8] | p0[S] (int64) | full[S] | empty[S]
@@ -325,6 +326,13 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
         re_n = (int64_t)a.rowptr[rown + 1];
       }
     }
+    // MODE 4: only tiles that hold a ghost column wait for the gather (once per thread), and only they read x through the
+    // coherent path; every other tile runs the instruction stream of MODE 0
+    const bool gt = MODE == 4 && a.tile_ghost[t] != 0;
+    if (MODE == 4 && gt && !ghosts_ready) {
+      spmv_wait_gather(a.arrive, gather_target, &gather_seen);
+      ghosts_ready = true;
+    }
     mbar_wait(full + s, (uint32_t)((j / S) & 1));
     if (row < a.nrows) {
       const int64_t p0 = p0_s[s];
@@ -345,10 +353,11 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
           v[u] = vs[kk];
         }
         bool ghost = false;
-        if (MODE == 1 || MODE == 4) {
+        if (MODE == 1) {
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) ghost |= c[u] >= a.n_own_cols;
         }
+        if (MODE == 4) ghost = gt;
         if (MODE == 2) {  // own block only: ghost columns are skipped here and added, in order, by k_spmv_ghost_rows
           const int32_t last_own = (int32_t)a.n_own_cols - 1;
 #pragma unroll
@@ -356,13 +365,9 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
         } else if (MODE == 0 || !ghost) {  // straight-line: all BATCH gathers are in flight together
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) xv[u] = __ldg(a.x + c[u]);
-        } else if (MODE == 4) {  // boundary rows: the ghost slots are filled by this very kernel
-          if (!ghosts_ready) {
-            spmv_wait_gather(a.arrive, gather_target, &gather_seen);
-            ghosts_ready = true;
-          }
-#pragma unroll
-          for (int u = 0; u < BATCH; ++u) xv[u] = c[u] >= a.n_own_cols ? __ldcg(a.x + c[u]) : __ldg(a.x + c[u]);
+        } else if (MODE == 4) {  // a tile with ghost columns: the ghost slots were filled by this very kernel (and awaited above):
+#pragma unroll                  // weak loads (coherent after the acquire fence of the wait), never the read-only path
+          for (int u = 0; u < BATCH; ++u) asm volatile("ld.global.f64 %0, [%1];" : "=d"(xv[u]) : "l"(a.x + c[u]) : "memory");
         } else {  // boundary rows: ghost columns come from the owner's HBM over NVLink
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) {
@@ -434,6 +439,10 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
       }
     }
   }
+}
+
+__global__ void k_tile_ghost_flags(const int32_t *grows, int64_t n, int rows, unsigned char *flag) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) flag[grows[i] / rows] = 1;
 }
 
 // largest nnz of any ROWS-row tile (decides whether a tile fits one TMA stage)
@@ -621,6 +630,19 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, in
     }
     PA_CHECK(use_tma || (kmode != 2 && kmode != 4), PA_ESTATE, "own-block / fused-exchange modes need the TMA kernel");
     if (kmode == 4 && !m.d_arrive) PA_CUDA(cudaMalloc((void **)&m.d_arrive, sizeof(unsigned long long)));
+    const unsigned char *tile_flags = nullptr;
+    if (kmode == 4) {
+      auto it = m.tile_ghost.find(cfg.rows);
+      if (it == m.tile_ghost.end()) {
+        unsigned char *f = nullptr;
+        PA_CUDA(cudaMalloc((void **)&f, (size_t)cfg.ntiles));
+        PA_CUDA(cudaMemsetAsync(f, 0, (size_t)cfg.ntiles, c->stream));
+        if (m.n_grows) k_tile_ghost_flags<<<148 * 4, 256, 0, c->stream>>>(m.d_grows, m.n_grows, cfg.rows, f);
+        c->launches++;
+        it = m.tile_ghost.emplace(cfg.rows, f).first;
+      }
+      tile_flags = it->second;
+    }
     auto fill = [&](auto &a) {
       a.nrows = m.nrows;
       a.colval = m.d_colval;
@@ -645,6 +667,7 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, in
       a.fold = fold;
       a.dot_ticket = m.d_dot_ticket;
       if (fold) a.push = pa_red_push(c);
+      a.tile_ghost = tile_flags;
     };
     if (dotw) {
       PA_CHECK(use_tma && mode != 2 && mode != 3 && rp.prefix && alpha == 1.0 && beta == 0.0, PA_ESTATE, "dot epilogue unavailable for this configuration");
@@ -821,6 +844,7 @@ static void free_part(MatPart &m) {
   cudaFree(m.d_coo_perm);
   cudaFree(m.d_coo_seg);
   cudaFree(m.d_coo_valid);
+  for (auto &kv : m.tile_ghost) cudaFree(kv.second);
   cudaFree(m.d_dotpart);
   cudaFree(m.d_dot_ticket);
   cudaFree(m.d_arrive);
