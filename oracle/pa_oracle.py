@@ -707,6 +707,37 @@ def psparse_disassembled(I, J, V, row_partition, col_partition, local_format: st
     return PSparse(list(row_partition), cols_fa, local, oo, og, True)  # rows_fa = rows (:1737)
 
 
+def psparse_subassembled(I, J, V, row_partition, col_partition, local_format: str = "csc") -> PSparse:
+    """psparse(I,J,V,rows,cols; assemble=false) (src/p_sparse_matrix.jl:1186-1222): steps 1-2 of psparse_disassembled only.
+    `local` holds ALL local rows (own rows first, then the ghost rows) over rows_sa x cols_sa."""
+    I = [np.asarray(i, dtype=np.int64) for i in I]
+    J = [np.asarray(j, dtype=np.int64) for j in J]
+    V = [np.asarray(v, dtype=np.float64) for v in V]
+    rows_sa = [union_ghost(r, i, o) for r, i, o in zip(row_partition, I, find_owner(row_partition, I))]
+    cols_sa = [union_ghost(c, j, o) for c, j, o in zip(col_partition, J, find_owner(col_partition, J))]
+    local = []
+    for p, (r, c) in enumerate(zip(rows_sa, cols_sa)):
+        assert r.own_is_prefix() and c.own_is_prefix(), "restated for own-first local orders"
+        li = r.global_to_local(I[p]).astype(np.int64)
+        lj = c.global_to_local(J[p]).astype(np.int64)
+        li[I[p] < 1] = 0
+        lj[J[p] < 1] = 0
+        ei, ej, ev = _compress_coo(li, lj, V[p], r.n_local, c.n_local, local_format)
+        local.append(sparse_matrix_csr(ei, ej, ev, r.n_local, c.n_local, skip=False))
+    return PSparse(rows_sa, cols_sa, local, [], [], False)
+
+
+def pmul_subassembled(A: PSparse, b_vals: List[np.ndarray], c_vals: List[np.ndarray], alpha: float = 1.0, beta: float = 0.0):
+    """mul!(c,A,b,alpha,beta) for !A.assembled (src/p_sparse_matrix.jl:2105-2142): consistent!(b); own and ghost rows of c get
+    beta*c + alpha*(own block of the row, then its ghost block); assemble!(c).  With alpha = 1, beta = 0 the row sums are the
+    sequential sums of spmv_csr! over the row sorted by local column (own columns first)."""
+    consistent(b_vals, assembly_plan(A.col_partition))
+    for p in range(len(b_vals)):
+        y = spmv_csr(A.local[p], b_vals[p])
+        c_vals[p][:] = y if (alpha == 1.0 and beta == 0.0) else alpha * y + (beta * c_vals[p] if beta != 0.0 else 0.0)
+    assemble(c_vals, A.row_partition, assembly_plan(A.row_partition))
+
+
 def _entries_to_csr(ei, ej, ev, m, n) -> CSR:
     """row-major unique entries -> SparseMatrixCSR{1} arrays."""
     counts = np.bincount(ei - 1, minlength=m) if len(ei) else np.zeros(m, dtype=np.int64)

@@ -293,6 +293,7 @@ extern "C" int pa_spmv_transpose(pa_mat *A, pa_vec *b, pa_vec *cvec, double alph
     PA_CHECK(yp.n_own == cp.n_own && yp.n_local == cp.n_local && yp.prefix, PA_EINVAL,
              "pa_spmv_transpose: c does not match axes(A,2) (own and ghost ids) on part %d", c->part_ids[k] + 1);
   }
+  PA_CHECK(!A->subassembled, PA_EINVAL, "pa_spmv_transpose: needs an assembled matrix");
   PA_CUDA(cudaSetDevice(c->device));
   PA_TRY(build_transpose(A));
   PA_TRY(pa_before_write(c));

@@ -421,6 +421,7 @@ extern "C" int pa_cg_precond(pa_mat *A, pa_vec *x, const pa_vec *b, pa_mg *mg, i
                              pa_cg_result *result, double *history) {
   PA_CHECK(A && x && b && result, PA_EINVAL, "pa_cg: null argument");
   PA_CHECK(A->committed, PA_ESTATE, "pa_cg: matrix not committed");
+  PA_CHECK(!A->subassembled, PA_EINVAL, "pa_cg: needs an assembled matrix");
   PA_CHECK(maxiter >= 0, PA_EINVAL, "pa_cg: negative maxiter");
   pa_ctx *c = A->ctx;
   PA_CUDA(cudaSetDevice(c->device));

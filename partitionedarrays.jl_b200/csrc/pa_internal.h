@@ -181,6 +181,7 @@ struct pa_mat {
   pa_plan *rows = nullptr, *cols = nullptr;
   std::vector<MatPart> parts;
   bool committed = false;
+  bool subassembled = false;  // some part stores its ghost rows too (n_local rows): mul! ends with assemble!(c)
   pa_mat *T = nullptr;  // lazily built local transposes (transpose mul!)
 };
 

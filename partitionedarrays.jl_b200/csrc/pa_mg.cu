@@ -828,6 +828,7 @@ static void gs_free_part(GsPart &g) {
 
 extern "C" int pa_gs_create(pa_mat *A, pa_gs **out) {
   PA_CHECK(A && out && A->committed, PA_ESTATE, "pa_gs_create: matrix missing or not committed");
+  PA_CHECK(!A->subassembled, PA_EINVAL, "pa_gs_create: Gauss-Seidel needs an assembled matrix");
   pa_gs *g = new pa_gs();
   g->A = A;
   g->parts.resize(A->ctx->nlocal);

@@ -747,6 +747,9 @@ static int check_mul_args(pa_mat *A, pa_vec *x, pa_vec *y) {
              (long long)xp.n_own, (long long)cp.n_own, (long long)xp.n_local, (long long)cp.n_local);
     PA_CHECK(rp.n_own == yp.n_own && (rp.prefix == yp.prefix), PA_EINVAL, "pa_spmv: y does not match axes(A,1) on part %d", A->ctx->part_ids[k] + 1);
     PA_CHECK(yp.n_local >= rp.n_own, PA_EINVAL, "pa_spmv: y too short");
+    if (A->subassembled)  // matching_ghost_indices(axes(a,1), axes(c,1)) (src/p_sparse_matrix.jl:2094-2097,2109-2111)
+      PA_CHECK(y->plan == A->rows || (yp.n_local == rp.n_local && yp.signature == rp.signature), PA_EINVAL,
+               "pa_spmv: a sub-assembled matrix needs c on the row partition of A, ghost rows included (part %d)", A->ctx->part_ids[k] + 1);
   }
   return PA_OK;
 }
@@ -775,6 +778,17 @@ int pa_spmv_dot(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, uint
     tma_ok &= A->parts[k].tma_ok;
   }
   // default = the fastest measured on B200 (profiles/r01_multigpu_strategies.md): peer-load gather, then one local SpMV
+  if (A->subassembled) {
+    // !a.assembled (src/p_sparse_matrix.jl:2109-2142): own AND ghost rows are multiplied (c_local = beta*c_local + alpha*A_local*b_local,
+    // own-block entries of every row first), then assemble!(c) adds the ghost-row results to their owners and zeroes the ghosts
+    PA_CHECK(!fold, PA_ESTATE, "pa_spmv_dot: no fused dot for sub-assembled matrices");
+    PA_TRY(pa_vec_consistent(x));
+    PA_TRY(pa_before_write(c));
+    PA_TRY(pa_spmv_local(A, x, y, alpha, beta, 0, nullptr, nullptr));
+    PA_TRY(pa_vec_assemble(y));
+    if (dotw) PA_TRY(pa_reduce_dev_to(dotw, y, 0, d_out));
+    return PA_OK;
+  }
   int strategy = (flags & PA_SPMV_INLINE_PEER_LOADS) ? 1 : ((flags & PA_SPMV_OVERLAP) ? 2 : ((flags & PA_SPMV_FUSED_EXCHANGE) ? 3 : 0));
   const int64_t forced = pa_knob(c, "spmv_strategy", -1);
   if (forced >= 0 && forced <= 3) strategy = (int)forced;
@@ -913,8 +927,12 @@ static int upload_csr(pa_ctx *c, MatPart &m, int64_t nrows, int64_t ncols, const
 static int mat_part_args(pa_mat *A, int32_t k, int64_t nrows, const char *who) {
   PA_CHECK(A && !A->committed, PA_ESTATE, "%s: matrix missing or already committed", who);
   PA_CHECK(k >= 0 && k < A->ctx->nlocal, PA_EINVAL, "%s: local part %d out of range", who, k);
-  PA_CHECK(nrows == A->rows->parts[k].n_own, PA_EINVAL, "%s: %lld rows given, the row partition owns %lld", who, (long long)nrows,
-           (long long)A->rows->parts[k].n_own);
+  // own rows only (assembled matrices: the ghost-row blocks are empty, src/p_sparse_matrix.jl:1704-1705) or ALL local rows of an
+  // own-first row partition (sub-assembled matrices, psparse(...; assemble=false): blocks ghost_own / ghost_ghost stored too)
+  const PlanPart &rpp = A->rows->parts[k];
+  PA_CHECK(nrows == rpp.n_own || (rpp.prefix && nrows == rpp.n_local), PA_EINVAL,
+           "%s: %lld rows given, the row partition owns %lld (%lld local)", who, (long long)nrows, (long long)rpp.n_own, (long long)rpp.n_local);
+  if (nrows != rpp.n_own) A->subassembled = true;
   PA_CUDA(cudaSetDevice(A->ctx->device));
   return PA_OK;
 }

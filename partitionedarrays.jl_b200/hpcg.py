@@ -139,3 +139,114 @@ def smoother_name(P: "MgPreconditioner") -> str:
     if P.order == "multicolor":
         return "multi-colour Gauss-Seidel (8 colours, one launch per colour; convergence-level parity: different iterates than the reference)"
     return "bit-exact wavefront Gauss-Seidel (same iterates as the reference's sequential sweeps)"
+
+
+# ---------------------------------------------------------------------------------------------------- HPCG driver + report
+def cg_timings(backend: CUDAArray) -> dict:
+    """Device times (ms, CUDA events) of the last solve that ran with PA_CG_TIMING — the timing_data slots of
+    HPCG/src/ref_cg.jl:46-67."""
+    out = np.zeros(6, dtype=np.float64)
+    check(_capi.lib().pa_cg_timings(backend.h, ptr(out)))
+    return {"DDOT": out[0] * 1e-3, "WAXPBY": out[1] * 1e-3, "SPMV": out[2] * 1e-3, "MG": out[3] * 1e-3, "total": out[4] * 1e-3, "iters": int(out[5])}
+
+
+def report_results(np_, times: dict, levels: int, ref_max_iters: int, opt_max_iters: int, nr_cg_sets: int, norm_data, geom: dict) -> dict:
+    """report_results (HPCG/src/report_results.jl:21-152) as a dict with the reference's JSON field names: the flop and
+    byte models are the reference's own (including its sizeof(Int64) column indices in the byte model)."""
+    fniters = nr_cg_sets * opt_max_iters
+    fnrow, fnnz = geom["nrows"][levels - 1], geom["nnz"][levels - 1]
+    ddot = (3.0 * fniters + nr_cg_sets) * 2.0 * fnrow
+    waxpby = (3.0 * fniters + nr_cg_sets) * 2.0 * fnrow
+    spmv = (fniters + nr_cg_sets) * 2.0 * fnnz
+    precond = sum(fniters * 10.0 * geom["nnz"][i] for i in range(1, levels)) + fniters * 4.0 * geom["nnz"][0]
+    fnops = ddot + waxpby + spmv + precond
+    frefnops = fnops * (ref_max_iters / opt_max_iters)
+    f64, i64 = 8, 8
+    reads = (3.0 * fniters + nr_cg_sets) * 2.0 * fnrow * f64 * 2 + (fniters + nr_cg_sets) * (fnnz * (f64 + i64) + fnrow * f64)
+    writes = (3.0 * fniters + nr_cg_sets) * f64 + (3.0 * fniters + nr_cg_sets) * fnrow * f64 + (fniters + nr_cg_sets) * fnrow * f64
+    mg_data = {}
+    for i in range(1, levels):
+        nzl, nrl = geom["nnz"][i], geom["nrows"][i]
+        mg_data[f"level_{i + 1}"] = {"non_zeros": nzl, "nr_equations": nrl}
+        reads += fniters * (2.0 * nzl * (f64 + i64) + nrl * f64) * 2 + fniters * (nzl * (f64 + i64) + nrl * f64)
+        writes += 3 * fniters * nzl * f64
+    mg_data["level_1"] = {"non_zeros": geom["nnz"][0], "nr_equations": geom["nrows"][0]}
+    reads += fniters * (2.0 * geom["nnz"][0] * (f64 + i64) + geom["nrows"][0] * f64)
+    writes += fniters * geom["nrows"][0] * f64
+    t = times
+    denom = t["total"] + nr_cg_sets * (t["opt_time"] / 10.0 + t["setup"] / 10.0)
+    total_gflops = frefnops / denom / 1e9
+    safe = lambda a, b: (a / b / 1e9) if b > 0 else None
+    return {
+        "procs": np_, "main_times": dict(t), "nr_equations": fnrow, "non_zeors": fnnz, "multigrid_data": mg_data,
+        "geometry": {k: geom[k] for k in ("npx", "npy", "npz", "gnx", "gny", "gnz", "nx", "ny", "nz")},
+        "iter_data": {"ref_iters_set": ref_max_iters, "opt_iters_set": opt_max_iters, "ref_iters_total": ref_max_iters * nr_cg_sets,
+                      "opt_iters_total": opt_max_iters * nr_cg_sets},
+        "reproducibility_data": {"mean": float(np.mean(norm_data)), "var": float(np.var(norm_data, ddof=1)) if len(norm_data) > 1 else 0.0},
+        "flops": {"DDOT": ddot, "WAXPBY": waxpby, "SpMV": spmv, "MG": precond, "Total": fnops, "Total_conv": frefnops},
+        "GB/s": {"Read": reads / t["total"] / 1e9, "Write": writes / t["total"] / 1e9, "Total": (reads + writes) / t["total"] / 1e9},
+        "GFLOP/s": {"DDOT": safe(ddot, t["DDOT"]), "WAXPBY": safe(waxpby, t["WAXPBY"]), "SpMV": safe(spmv, t["SPMV"]), "MG": safe(precond, t["MG"]),
+                    "Total": fnops / t["total"] / 1e9, "Total_conv": frefnops / t["total"] / 1e9, "Total_conv_opt": total_gflops},
+        "Overview": {"GFLOP/s": total_gflops, "time": t["total"]},
+    }
+
+
+def hpcg_benchmark(backend: CUDAArray, nx: int, ny: int, nz: int, npx: int = 1, npy: int = 1, npz: int = 1, total_runtime: float = 10.0,
+                   order: str = "lexicographic", levels: int = 4, max_sets: int = 50) -> dict:
+    """hpcg_benchmark (HPCG/src/hpcg_benchmark.jl:26-100) on the CUDA backend: reference phase (2 sets of ref_cg!, 50
+    iterations, op-for-op schedule) -> reference tolerance; optimised setup phase (opt_cg! to that tolerance: the iteration
+    count that guarantees it, e.g. more than 50 with the multi-colour smoother); timing phase (sets of opt_cg! until
+    total_runtime); report with the reference's fields.  The per-operation times are device times (CUDA events)."""
+    import time as _time
+
+    t0 = _time.perf_counter()
+    S = pc_setup(backend, levels, nx, ny, nz, npx, npy, npz, order=order)
+    x = PVector(S.A.cols)
+    backend.sync()
+    t_setup = _time.perf_counter() - t0
+    ref_max_iters = 50
+    acc = {"DDOT": 0.0, "WAXPBY": 0.0, "SPMV": 0.0, "MG": 0.0, "total": 0.0}
+    tflag = _capi.PA_CG_TIMING
+
+    def add(tm):
+        for k in acc:
+            acc[k] += tm[k]
+
+    # reference phase
+    ref_time = 0.0
+    for _ in range(2):
+        x.fill_(0.0)
+        res = ref_cg_pc_(x, S.A, S.b, S, tolerance=0.0, maxiter=ref_max_iters, flags=_capi.PA_CG_REFERENCE_OPS | tflag)
+        ref_time += cg_timings(backend)["total"]
+    ref_tol = res.residual / res.residual0
+    # optimised setup phase
+    opt_n_iters, opt_worst, opt_time = ref_max_iters, 0.0, 0.0
+    for _ in range(2):
+        x.fill_(0.0)
+        res = ref_cg_pc_(x, S.A, S.b, S, tolerance=ref_tol, maxiter=10 * ref_max_iters, flags=tflag)
+        tm = cg_timings(backend)
+        opt_time += tm["total"]
+        opt_n_iters = max(opt_n_iters, res.iters)
+        opt_worst = max(opt_worst, tm["total"])
+    opt_worst = max(backend.gather_all([opt_worst]))
+    # timing phase
+    nr_sets = max(1, min(max_sets, int(np.ceil(total_runtime / max(opt_worst, 1e-9)))))
+    norm_data = []
+    for _ in range(nr_sets):
+        x.fill_(0.0)
+        res = ref_cg_pc_(x, S.A, S.b, S, tolerance=0.0, maxiter=opt_n_iters, flags=tflag)
+        add(cg_timings(backend))
+        norm_data.append(res.residual / res.residual0)
+    nnz = [int(sum(backend.gather_all([A.nnz(k) for k in range(len(backend.parts))]))) for A in S.A_vec]
+    nrows = [len(A.rows) for A in S.A_vec]
+    geom = {"nnz": nnz, "nrows": nrows, "npx": npx, "npy": npy, "npz": npz, "nx": nx, "ny": ny, "nz": nz, "gnx": npx * nx, "gny": npy * ny, "gnz": npz * nz}
+    times = {"setup": t_setup, "total": acc["total"], "DDOT": acc["DDOT"], "WAXPBY": acc["WAXPBY"], "SPMV": acc["SPMV"],
+             "allreduce": 0.0, "MG": acc["MG"], "halo_time": 0.0, "opt_time": opt_time, "ref_time": ref_time}
+    rep = report_results(backend.nparts, times, levels, ref_max_iters, opt_n_iters, nr_sets, norm_data, geom)
+    rep["smoother"] = smoother_name(S)
+    rep["reference_tolerance"] = ref_tol
+    rep["note"] = ("allreduce and halo_time are 0: the scalar all-reduces and the ghost exchange ride inside the DDOT / SPMV / MG kernels "
+                   "(no separate call to time); per-operation times are CUDA-event device times")
+    x.free()
+    S.free()
+    return rep

@@ -654,7 +654,7 @@ def _csr_to_csc(rp, cv, nz, ncols):
 
 
 def psparse(I: List, J: List, V: List, rows: PRange, cols: PRange, assembled: bool = True, split_format: bool = True,
-            local_format: str = "csr", compress: str = "host", ship: str = "host") -> PSparseMatrix:
+            local_format: str = "csr", compress: str = "host", ship: str = "host", assemble: bool = True) -> PSparseMatrix:
     """psparse([T,] I,J,V,row_partition,col_partition; assembled=true) (src/p_sparse_matrix.jl:1150-1286).
     local_format: "csr" = SparseMatrixCSR{1,Float64,Int32} local matrices; "csc" = the reference's default
     SparseMatrixCSC{Float64,Int} (converted to CSR at upload, summation order of spmv_csc! preserved).
@@ -663,6 +663,8 @@ def psparse(I: List, J: List, V: List, rows: PRange, cols: PRange, assembled: bo
     shipped to their owner first.  Ghost columns are discovered with find_owner + union_ghost (:1226-1236).
     The COO->CSR compression runs on the host at setup time (on-device compression is 'next')."""
     b = rows.backend
+    if not assembled and not assemble:
+        return _psparse_subassembled(I, J, V, rows, cols, local_format)
     if not assembled:
         return _psparse_disassembled(I, J, V, rows, cols, split_format, local_format, compress, ship)
     new_cols = []
@@ -760,6 +762,35 @@ def _ship_ghost_rows(b: CUDAArray, outgoing, ship: str):
         rcv = exchange([[np.asarray(dst[q][t], dtype=dt) for q in d] for (_, dst), d in zip(outgoing, dests)], graph)
         parts.append([np.concatenate(r).astype(dt) if r else np.zeros(0, dt) for r in rcv])
     return [tuple(parts[t][k] for t in range(3)) for k in range(len(outgoing))]
+
+
+def _psparse_subassembled(I, J, V, rows: PRange, cols: PRange, local_format: str) -> PSparseMatrix:
+    """psparse(I,J,V,rows,cols; assemble=false) (src/p_sparse_matrix.jl:1186-1222): the SUB-ASSEMBLED matrix — every part
+    compresses its own triplets over rows_sa x cols_sa = union_ghost(rows/cols, I/J) and keeps the rows it does not own as
+    ghost rows (blocks ghost_own / ghost_ghost).  mul!(c,A,b) then multiplies own and ghost rows and finishes with
+    assemble!(c) (:2109-2142); c lives on axes(A,1) (ghost rows included)."""
+    b = rows.backend
+    rsa_all, csa_all, mats = [], [], []
+    for ind_r, ind_c, i, j, v in zip(rows.indices, cols.indices, I, J, V):
+        i, j, v = np.asarray(i, dtype=np.int64), np.asarray(j, dtype=np.int64), np.asarray(v, dtype=np.float64)
+        rsa = pr.union_ghost(ind_r, i, _find_owner(rows, ind_r, i))
+        csa = pr.union_ghost(ind_c, j, _find_owner(cols, ind_c, j))
+        if not (rsa.own_is_prefix and csa.own_is_prefix):
+            raise ValueError("psparse(assemble=false): needs own-first local orders")
+        li, lj = rsa.global_to_local(i).astype(np.int64), csa.global_to_local(j).astype(np.int64)
+        li[i < 1] = 0
+        lj[j < 1] = 0
+        ei, ej, ev = _stored_entries(li, lj, v, rsa.n_local, csa.n_local, local_format)
+        # rows sorted by local column id = own-block entries first, then the ghost block: the order of mul! (:2119-2139)
+        mats.append(_coo_to_csr(ei, ej, ev, rsa.n_local, csa.n_local))
+        rsa_all.append(rsa)
+        csa_all.append(csa)
+    A = PSparseMatrix(PRange(b, rsa_all), PRange(b, csa_all))
+    for k, m in enumerate(mats):
+        A.set_csr(k, *m)
+    A.commit()
+    A.assembled = False
+    return A
 
 
 def _psparse_disassembled(I, J, V, rows: PRange, cols: PRange, split_format: bool, local_format: str, compress: str, ship: str = "host") -> PSparseMatrix:

@@ -194,3 +194,28 @@ def test_multicolor_preconditioned_cg_convergence_level_parity(pa):
     assert np.abs(np.concatenate(x.own_values()) - 1.0).max() < 1e-9  # exact solution = ones
     P.free()
     b.close()
+
+
+@pytest.mark.parametrize("order", ["lexicographic", "multicolor"])
+def test_hpcg_benchmark_driver_and_report(pa, order):
+    """hpcg_benchmark(distribute, np, nx, ny, nz; total_runtime) (HPCG/src/hpcg_benchmark.jl:26-100, called by
+    HPCG/test/hpcg_benchmark_tests.jl:43): reference phase, optimised setup phase, timing phase, report with the reference's
+    fields (report_results.jl:89-152).  np=4, 32^3 per part: the reference tolerance is the 2.88e-13 of the known answer; the
+    multi-colour smoother needs more than 50 iterations to reach it and the driver finds that count."""
+    b = pa.CUDAArray(4, arena_bytes=256 << 20)
+    rep = pa.hpcg_benchmark(b, 32, 32, 32, 2, 2, 1, total_runtime=0.2, order=order, max_sets=3)
+    assert rep["procs"] == 4 and rep["nr_equations"] == 4 * 32 ** 3
+    assert rep["geometry"]["gnx"] == 64 and rep["geometry"]["gnz"] == 32
+    assert set(rep["main_times"]) == {"setup", "total", "DDOT", "WAXPBY", "SPMV", "allreduce", "MG", "halo_time", "opt_time", "ref_time"}
+    t = rep["main_times"]
+    assert t["MG"] > 0 and t["SPMV"] > 0 and t["DDOT"] > 0 and t["WAXPBY"] > 0
+    assert abs(t["MG"] + t["SPMV"] + t["DDOT"] + t["WAXPBY"] - t["total"]) <= 1e-6 * t["total"] + 1e-9
+    if order == "lexicographic":
+        assert abs(rep["reference_tolerance"] - 2.877476184683206e-13) <= 1e-6 * 2.877476184683206e-13
+        assert rep["iter_data"]["opt_iters_set"] == 50
+    else:
+        assert 1e-12 < rep["reference_tolerance"] < 1e-10    # 1.9e-11 after 50 iterations in this order
+        assert rep["iter_data"]["opt_iters_set"] == 50       # the optimised run has to reach ITS OWN reference tolerance
+    assert rep["reproducibility_data"]["var"] == 0.0          # every set reproduces the same residual bit for bit
+    assert rep["GFLOP/s"]["Total"] > 0 and rep["flops"]["MG"] > rep["flops"]["SpMV"]
+    b.close()

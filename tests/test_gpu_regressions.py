@@ -92,3 +92,52 @@ def test_periodic_single_part_direction_consistent_and_reductions():
     for got, want in zip(v.local_values(), vo):
         assert np.array_equal(got, want)
     bk.close()
+
+
+def test_subassembled_mul_matches_the_oracle_and_the_assembled_product():
+    """psparse(I,J,V,rows,cols; assemble=false) keeps the rows a part does not own as ghost rows; mul!(c,A,b) multiplies own and
+    ghost rows and finishes with assemble!(c) (src/p_sparse_matrix.jl:2105-2142).  The 4-part matrix of
+    test/p_sparse_matrix_tests.jl:131-160 (exact in any order: small integers) and a random one against the oracle."""
+    import pa_b200 as pa
+
+    I = [[1, 2, 1, 2, 2], [3, 3, 4, 6], [5, 5, 6, 7], [9, 9, 8, 10, 6]]
+    J = [[2, 6, 1, 2, 1], [3, 9, 4, 2], [5, 6, 6, 7], [9, 3, 8, 10, 5]]
+    V = [[1.0, 2.0, 30.0, 10.0, 1.0], [10.0, 2.0, 30.0, 2.0], [10.0, 2.0, 30.0, 1.0], [10.0, 2.0, 30.0, 50.0, 2.0]]
+    n, P = 10, 4
+    rng = np.random.default_rng(2)
+    cases = [(I, J, V, n)]
+    n2 = 57
+    tab = o.global_to_owner_table(o.uniform_partition(P, n2))
+    I2 = [rng.integers(1, n2 + 1, 40) for _ in range(P)]   # rows owned anywhere: plenty of ghost rows
+    J2 = [rng.integers(1, n2 + 1, 40) for _ in range(P)]
+    V2 = [rng.standard_normal(40) for _ in range(P)]
+    cases.append((I2, J2, V2, n2))
+    for Ic, Jc, Vc, nn in cases:
+        bk = pa.CUDAArray(P, arena_bytes=8 << 20)
+        rows = pa.uniform_partition(bk, P, nn)
+        A = pa.psparse(Ic, Jc, Vc, rows, rows, assembled=False, assemble=False)
+        assert A.assembled is False
+        orows = o.uniform_partition(P, nn)
+        Ao = o.psparse_subassembled(Ic, Jc, Vc, orows, orows, local_format="csr")
+        dense = np.zeros((nn, nn))
+        for i, j, v in zip(Ic, Jc, Vc):
+            np.add.at(dense, (np.asarray(i) - 1, np.asarray(j) - 1), v)
+        xg = rng.integers(-3, 4, nn).astype(float)
+        for alpha, beta in ((1.0, 0.0), (2.0, -1.0)):
+            x = pa.pvector_from_global(xg, A.cols)
+            c = pa.pfill(1.0, A.rows)
+            pa.mul_(c, A, x, alpha, beta)
+            xo = o.pvector_from_global(xg, Ao.col_partition, ghosts=False)
+            co = [np.ones(r.n_local) for r in Ao.row_partition]
+            o.pmul_subassembled(Ao, xo, co, alpha, beta)
+            got = c.local_values()
+            for k, r in enumerate(Ao.row_partition):
+                if (alpha, beta) == (1.0, 0.0):
+                    assert np.array_equal(got[k], co[k]), k      # own entries summed, ghost entries zeroed by assemble!
+                else:
+                    np.testing.assert_allclose(got[k], co[k], rtol=1e-13, atol=1e-13)
+            # ghost rows carry beta*c_ghost too before assemble! (every ghost copy of c was 1): compare with the oracle only
+            if (alpha, beta) == (1.0, 0.0):
+                np.testing.assert_allclose(c.collect(), dense @ xg, rtol=1e-13, atol=1e-12)
+            x.free(); c.free()
+        bk.close()
