@@ -210,12 +210,11 @@ def test_hpcg_benchmark_driver_and_report(pa, order):
     t = rep["main_times"]
     assert t["MG"] > 0 and t["SPMV"] > 0 and t["DDOT"] > 0 and t["WAXPBY"] > 0
     assert abs(t["MG"] + t["SPMV"] + t["DDOT"] + t["WAXPBY"] - t["total"]) <= 1e-6 * t["total"] + 1e-9
+    assert abs(rep["reference_tolerance"] - 2.877476184683206e-13) <= 1e-6 * 2.877476184683206e-13  # reference phase = reference sweeps
     if order == "lexicographic":
-        assert abs(rep["reference_tolerance"] - 2.877476184683206e-13) <= 1e-6 * 2.877476184683206e-13
         assert rep["iter_data"]["opt_iters_set"] == 50
     else:
-        assert 1e-12 < rep["reference_tolerance"] < 1e-10    # 1.9e-11 after 50 iterations in this order
-        assert rep["iter_data"]["opt_iters_set"] == 50       # the optimised run has to reach ITS OWN reference tolerance
+        assert 55 <= rep["iter_data"]["opt_iters_set"] <= 70  # the multi-colour order pays for its parallelism in iterations
     assert rep["reproducibility_data"]["var"] == 0.0          # every set reproduces the same residual bit for bit
     assert rep["GFLOP/s"]["Total"] > 0 and rep["flops"]["MG"] > rep["flops"]["SpMV"]
     b.close()
