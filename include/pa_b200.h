@@ -65,6 +65,12 @@ int pa_ctx_stream(pa_ctx *ctx, void **stream_out);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int pa_ctx_launch_count(pa_ctx *ctx, int64_t *out);
 
+/* One process, several GPUs (the DebugArray execution model across the box): creates ndev contexts — context k holds part
+ * k+1 on devices[k] — and links them (peer access between the devices, scalar all-reduce over peer memory, no NCCL, no
+ * IPC).  Drive context k from its own host thread: every operation is collective over the contexts exactly as it is over
+ * processes in the one-process-per-GPU model.  out: ndev handles; destroy each with pa_ctx_destroy. */
+int pa_ctx_create_multi(int32_t ndev, const int32_t *devices, uint64_t arena_bytes, pa_ctx **out);
+
 /* Peer mapping of remote parts (distributed runs).  Export the 64-byte CUDA IPC handle of local
  * part k's arena, all-gather the handles on the host (torch.distributed / MPI), then import the
  * handle of every remote part.  Parts held by this process are linked automatically. */

@@ -8,7 +8,7 @@ from .hpcg import GaussSeidel, MgPreconditioner, cg_timings, hpcg_benchmark, pc_
 from .gallery import build_p_matrix, compute_optimal_shape_xyz, fill_hash, laplacian_fdm, stencil_matrix
 from .parrays import (CGResult, CUDAArray, ExchangeGraph, exchange, exchange_layout, PRange, PSparseMatrix, PVector, assemble_, consistent_, dot, mul_, mul_no_lat_, mul_transpose_, norm,
                       opt_cg_, spmv_, spmtv_, pfill, pones, psparse, pvector, pvector_from_global, pvector_from_triplets, pzeros, ref_cg_, uniform_partition,
-                      variable_partition, with_cuda)
+                      variable_partition, with_cuda, with_cuda_multi)
 from .prange import LocalIndices, local_range
 
 __all__ = [n for n in dir() if not n.startswith("_")]

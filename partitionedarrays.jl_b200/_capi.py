@@ -39,6 +39,7 @@ SIGNATURES = {
     "pa_abi_version": [],
     "pa_last_error": [],
     "pa_ctx_create": [_I32, _I32, _P, _I32, _U64, _P, _P],
+    "pa_ctx_create_multi": [_I32, _P, _U64, _P],
     "pa_ctx_destroy": [_P],
     "pa_ctx_sync": [_P],
     "pa_ctx_stream": [_P, _P],

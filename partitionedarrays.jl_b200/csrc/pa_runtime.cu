@@ -248,6 +248,42 @@ extern "C" int pa_ctx_arena_import(pa_ctx *c, int32_t part_id, const void *handl
   return PA_OK;
 }
 
+/* One PROCESS driving several GPUs (SURVEY 8b "Threading": the DebugArray execution model spanning the box): n contexts, one
+ * part and one device each, created and peer-linked here — the arenas are mapped with cudaDeviceEnablePeerAccess instead of
+ * CUDA IPC, the scalar all-reduce uses the peer-memory kernel (no NCCL).  The caller then drives context k from its own
+ * host thread (Julia: Threads.@spawn per part; Python: threading, ctypes releases the GIL): every operation stays the
+ * collective it is in the one-process-per-GPU model, so the kernels, the signalling and the results are identical. */
+extern "C" int pa_ctx_create_multi(int32_t ndev, const int32_t *devices, uint64_t arena_bytes, pa_ctx **out) {
+  PA_CHECK(ndev >= 1 && ndev <= PA_MAX_NBR && devices && out, PA_EINVAL, "pa_ctx_create_multi: bad arguments");
+  for (int i = 0; i < ndev; ++i)
+    for (int j = 0; j < i; ++j) PA_CHECK(devices[i] != devices[j], PA_EINVAL, "pa_ctx_create_multi: device %d listed twice", devices[i]);
+  for (int k = 0; k < ndev; ++k) out[k] = nullptr;
+  for (int k = 0; k < ndev; ++k) {
+    const int32_t id = k + 1;
+    int rc = pa_ctx_create(ndev, 1, &id, devices[k], arena_bytes, nullptr, &out[k]);
+    if (rc != PA_OK) {
+      for (int q = 0; q < k; ++q) pa_ctx_destroy(out[q]);
+      return rc;
+    }
+    out[k]->rank = k;
+    out[k]->world = ndev;
+  }
+  for (int k = 0; k < ndev; ++k) {
+    PA_CUDA(cudaSetDevice(devices[k]));
+    for (int q = 0; q < ndev; ++q) {
+      if (q == k) continue;
+      int can = 0;
+      PA_CUDA(cudaDeviceCanAccessPeer(&can, devices[k], devices[q]));
+      PA_CHECK(can, PA_ECUDA, "pa_ctx_create_multi: device %d cannot access device %d (no NVLink/PCIe peer path)", devices[k], devices[q]);
+      cudaError_t e = cudaDeviceEnablePeerAccess(devices[q], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return pa_cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+      cudaGetLastError();
+      out[k]->peer_base[q] = out[q]->arena[0];  // same process: the peer's arena pointer is valid here (UVA)
+    }
+  }
+  return PA_OK;
+}
+
 // ------------------------------------------------------------------ NCCL (dlopen, scalars only)
 typedef struct { char internal[128]; } nccl_uid;
 typedef int (*nccl_getuid_t)(nccl_uid *);

@@ -54,6 +54,15 @@ class CUDAArray:
         if mode == "distributed" and self.world > 1:
             self._link_peers()
 
+    @classmethod
+    def _adopt(cls, handle, nparts: int, part: int, device: int, comm: "_ThreadComm"):
+        """Backend object around one context of pa_ctx_create_multi (one process, one host thread per GPU)."""
+        self = cls.__new__(cls)
+        self.nparts, self.mode, self.group = int(nparts), "multi", None
+        self.parts, self.rank, self.world, self.device = [part], part - 1, nparts, device
+        self.h, self._comm = handle, comm
+        return self
+
     # -- distributed plumbing (torch.distributed is only used to move handles around) --
     def _link_peers(self):
         import torch.distributed as dist
@@ -78,6 +87,8 @@ class CUDAArray:
         """Objects of all parts ordered by part id (setup-time metadata only)."""
         if self.mode == "sequential" or self.world == 1:
             return list(local_objs)
+        if self.mode == "multi":
+            return [o for per_rank in self._comm.all_gather(self.rank, local_objs) for o in per_rank]
         import torch.distributed as dist
 
         out = [None] * self.world
@@ -131,6 +142,61 @@ def with_cuda(f: Callable, nparts: int = 1, **kw):
         return f(lambda ranks=None: backend)
     finally:
         backend.close()
+
+
+class _ThreadComm:
+    """All-gather of setup-time metadata between the host threads of one process (with_cuda_multi)."""
+
+    def __init__(self, n: int):
+        import threading
+
+        self.n, self.slots, self.barrier = n, [None] * n, threading.Barrier(n)
+
+    def all_gather(self, rank: int, obj):
+        self.slots[rank] = obj
+        self.barrier.wait()
+        out = list(self.slots)
+        self.barrier.wait()  # nobody overwrites a slot before everybody has read
+        return out
+
+
+def with_cuda_multi(f: Callable, devices: Sequence[int], arena_bytes: int = 1 << 30):
+    """One PROCESS driving several GPUs: the DebugArray execution model (src/debug_array.jl) spanning the box.
+    `f(backend)` runs once per device in its own host thread (SPMD, like one MPI rank per GPU, but threads of one process:
+    ctypes releases the GIL inside every library call); the contexts are created and peer-linked by pa_ctx_create_multi.
+    Returns the list of results, one per part."""
+    import threading
+
+    L = _capi.lib()
+    n = len(devices)
+    devs = i32(list(devices))
+    handles = (C.c_void_p * n)()
+    check(L.pa_ctx_create_multi(n, ptr(devs), arena_bytes, handles))
+    comm = _ThreadComm(n)
+    backends = [CUDAArray._adopt(C.c_void_p(handles[k]), n, k + 1, int(devices[k]), comm) for k in range(n)]
+    results, errors = [None] * n, [None] * n
+
+    def run(k):
+        try:
+            results[k] = f(backends[k])
+        except BaseException as e:  # noqa: BLE001 - reported after the join
+            errors[k] = e
+            comm.barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(k,)) for k in range(n)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for b in backends:
+        b.close()
+    for e in errors:
+        if e is not None and not isinstance(e, threading.BrokenBarrierError):
+            raise e
+    for e in errors:
+        if e is not None:
+            raise e
+    return results
 
 
 class PRange:
