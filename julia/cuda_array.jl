@@ -1,200 +1,355 @@
-# cuda_array.jl — a third PartitionedArrays backend next to DebugArray (src/debug_array.jl) and
-# MPIArray (src/mpi_array.jl), binding libpa_b200.so (include/pa_b200.h) with ccall.
+# cuda_array.jl — CUDAArray: a third PartitionedArrays backend next to DebugArray (src/debug_array.jl) and MPIArray
+# (src/mpi_array.jl), binding libpa_b200.so (include/pa_b200.h) with ccall.
 #
-# STATUS: written against PartitionedArrays v0.5.7 @ 8b2b2014; NOT executed in the build image
-# (no Julia toolchain there).  The same C entry points are exercised through ctypes by tests/.
+# STATUS: written against PartitionedArrays v0.5.7 @ 8b2b2014.  NOT executed in the build image (no Julia toolchain, no
+# network there); every C entry point used below is exercised through ctypes by tests/ and by examples/hpcg_cg.c.
+# julia/runtests.jl runs the reference's own test bodies against this backend when a toolchain is available.
 #
-# Model: one MPI rank (or one Julia process) per GPU holds one part, exactly like MPIArray
-# (src/mpi_array.jl:105-117).  Index metadata stays in Julia (PRange, AssemblyCache); vector and
-# matrix payloads live on the GPU behind opaque handles; mul!/consistent!/assemble!/dot/norm/
-# broadcast updates and the HPCG CG loop are forwarded to the library.
+# Shape of the backend (what src/debug_array.jl:34-255 and src/mpi_array.jl:105-117,221-239,525-614 define for theirs):
+#   * `CUDAArray{T,N} <: AbstractArray{T,N}` — the array of parts.  ONE Julia process holds all parts (the DebugArray
+#     execution model) and drives one GPU per part through pa_ctx_create_multi: context k = part k = device k.  Host-side
+#     items (index partitions, COO triplets, neighbour lists — setup-time metadata) live in `items` exactly as in
+#     DebugArray; `map`, `foreach`, `gather_impl!`, `scatter_impl`, `multicast_impl`, `scan_impl`, `reduction_impl`,
+#     `exchange_impl!`, ... operate on them sequentially, so every generic algorithm of the package runs unchanged.
+#   * device-resident payloads: `DeviceVector` (local values of one part of a PVector) and `DeviceMatrix` (local matrix of
+#     one part of a PSparseMatrix) are the per-part ITEM types.  A `PVector` / `PSparseMatrix` whose partition is a
+#     `CUDAArray` of those items dispatches to ONE library call per part and operation, issued from one task per part
+#     (Threads.@spawn): mul!, consistent!, assemble!, dot, norm, sum, fill!, copy!, rmul!, broadcast updates, ref_cg!.
+#   * `with_cuda(f) = f(distribute_with_cuda)` mirrors with_debug (src/debug_array.jl:7-9); `to_device(v)` / `to_device(A)`
+#     move a host PVector / PSparseMatrix built by the package's own constructors onto the GPUs.
 module PartitionedArraysB200
 
-using PartitionedArrays, SparseMatricesCSR, LinearAlgebra, MPI
-import PartitionedArrays: partition, local_values, own_values, ghost_values, consistent!, assemble!
+using PartitionedArrays, SparseArrays, SparseMatricesCSR, LinearAlgebra
+import PartitionedArrays: partition, local_values, own_values, ghost_values, consistent!, assemble!, linear_indices, cartesian_indices,
+    gather_impl!, scatter_impl, scatter_impl!, multicast_impl, multicast_impl!, scan_impl, reduction_impl, is_consistent,
+    allocate_exchange_impl, setup_exchange_impl, exchange_impl!, scalar_indexing_action, getany, i_am_main, ExchangeGraph, @fake_async
+
+export CUDAArray, with_cuda, distribute_with_cuda, to_device, to_host, DeviceVector, DeviceMatrix, ref_cg!
 
 const LIB = get(ENV, "PA_B200_LIB", "libpa_b200.so")
 
 pa_error() = unsafe_string(ccall((:pa_last_error, LIB), Cstring, ()))
-macro pacall(ex)   # @pacall ccall(...)  -> throws like the reference's @assert/@boundscheck failures
-    :(rc = $(esc(ex)); rc == 0 || error("pa_b200: ", pa_error()); nothing)
-end
+"Turns a status code into a Julia error, like the reference's @assert / @boundscheck failures (src/p_sparse_matrix.jl:2091-2093)."
+check(rc) = rc == 0 ? nothing : error("pa_b200: ", pa_error())
 
-# ---------------------------------------------------------------- backend instance (with_cuda)
-mutable struct CUDABackend
-    h::Ptr{Cvoid}
-    comm::MPI.Comm
-    rank::Int32
-    nparts::Int32
-end
-
-"with_cuda(f) = f(distribute) — mirrors with_mpi (src/mpi_array.jl:64-83)."
-function with_cuda(f; comm=MPI.COMM_WORLD, arena_bytes::UInt64=UInt64(8) << 30)
-    MPI.Initialized() || MPI.Init()
-    rank, np = MPI.Comm_rank(comm), MPI.Comm_size(comm)
-    h = Ref{Ptr{Cvoid}}()
-    ids = Int32[rank + 1]
-    dev = Int32(parse(Int, get(ENV, "LOCAL_RANK", string(rank))))
-    @pacall ccall((:pa_ctx_create, LIB), Cint, (Int32, Int32, Ptr{Int32}, Int32, UInt64, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}),
-                  np, 1, ids, dev, arena_bytes, C_NULL, h)
-    b = CUDABackend(h[], comm, rank, np)
-    if np > 1
-        # peer-map every arena (CUDA IPC) and create the NCCL communicator used for scalar all-reduces
-        handle = zeros(UInt8, 64)
-        @pacall ccall((:pa_ctx_arena_export, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{UInt8}), b.h, 0, handle)
-        all = MPI.Allgather(handle, comm)
-        for q in 0:np-1
-            q == rank && continue
-            @pacall ccall((:pa_ctx_arena_import, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{UInt8}), b.h, q + 1, all[64q+1:64q+64])
-        end
-        uid = zeros(UInt8, 128)
-        rank == 0 && @pacall ccall((:pa_nccl_unique_id, LIB), Cint, (Ptr{UInt8},), uid)
-        MPI.Bcast!(uid, 0, comm)
-        @pacall ccall((:pa_ctx_nccl_init, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), b.h, uid, rank, np)
+# ------------------------------------------------------------------------------------------ the set of device contexts
+mutable struct Contexts
+    h::Vector{Ptr{Cvoid}}     # pa_ctx* of part k (device k)
+    function Contexts(devices::Vector{Int32}; arena_bytes::UInt64 = UInt64(8) << 30)
+        h = Vector{Ptr{Cvoid}}(undef, length(devices))
+        check(ccall((:pa_ctx_create_multi, LIB), Cint, (Int32, Ptr{Int32}, UInt64, Ptr{Ptr{Cvoid}}), length(devices), devices, arena_bytes, h))
+        c = new(h)
+        finalizer(x -> foreach(p -> ccall((:pa_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), p), x.h), c)
     end
+end
+const CTX = Ref{Union{Nothing,Contexts}}(nothing)
+contexts() = something(CTX[])
+
+"One task per part: every library call is collective over the parts (the device-side waits of part k need part q's call to be enqueued)."
+function foreach_part(f, n::Integer)
+    tasks = [Threads.@spawn f(k) for k in 1:n]
+    foreach(wait, tasks)
+end
+
+# ------------------------------------------------------------------------------------------ the array of parts
+"""
+    CUDAArray{T,N} <: AbstractArray{T,N}
+
+Array of parts of the CUDA backend (cf. `DebugArray`, src/debug_array.jl:34-52).  Scalar indexing is disallowed
+(`scalar_indexing_action`, src/primitives.jl:4-11); the array is immutable like `DebugArray`.
+"""
+struct CUDAArray{T,N} <: AbstractArray{T,N}
+    items::Array{T,N}
+    CUDAArray{T,N}(a) where {T,N} = new{T,N}(convert(Array{T,N}, a))
+    CUDAArray(a) = new{eltype(a),ndims(a)}(convert(Array{eltype(a),ndims(a)}, a))
+end
+Base.size(a::CUDAArray) = size(a.items)
+Base.IndexStyle(::Type{<:CUDAArray}) = IndexLinear()
+Base.getindex(a::CUDAArray, i::Int) = (scalar_indexing_action(a); a.items[i])
+Base.setindex!(a::CUDAArray, v, i::Int) = error("CUDAArray is inmutable for performance reasons")
+Base.similar(a::CUDAArray, ::Type{T}, dims::Dims) where T = error("CUDAArray is inmutable for performance reasons")
+Base.copyto!(b::CUDAArray, a::CUDAArray) = error("CUDAArray is inmutable for performance reasons")
+Base.map!(f, r::CUDAArray, args::CUDAArray...) = error("CUDAArray is inmutable for performance reasons")
+linear_indices(a::CUDAArray) = CUDAArray(collect(LinearIndices(a)))
+cartesian_indices(a::CUDAArray) = CUDAArray(collect(CartesianIndices(a)))
+Base.map(f, args::CUDAArray...) = CUDAArray(map(f, map(i -> i.items, args)...))
+Base.foreach(f, args::CUDAArray...) = (foreach(f, map(i -> i.items, args)...); nothing)
+Base.all(a::CUDAArray) = reduce(&, a; init = true)
+Base.all(p::Function, a::CUDAArray) = all(map(p, a))
+Base.reduce(op, a::CUDAArray; kwargs...) = reduce(op, a.items; kwargs...)
+Base.sum(a::CUDAArray) = reduce(+, a)
+Base.collect(a::CUDAArray) = collect(a.items)
+getany(a::CUDAArray) = first(a.items)
+i_am_main(::CUDAArray) = true
+function Base.show(io::IO, k::MIME"text/plain", data::CUDAArray)
+    println(io, "$(length(data))-element CUDAArray (one part per GPU):")
+    for (i, item) in enumerate(data.items)
+        println(io, "[$i] = ", item)
+    end
+end
+Base.show(io::IO, data::CUDAArray) = print(io, "CUDAArray(", data.items, ")")
+
+# primitives on host items: delegated to the sequential implementations, like DebugArray (src/debug_array.jl:138-255)
+gather_impl!(rcv::CUDAArray, snd::CUDAArray, destination, ::Type{T}) where T = gather_impl!(rcv.items, snd.items, destination, T)
+scatter_impl(snd::CUDAArray, source) = CUDAArray(scatter_impl(snd.items, source))
+scatter_impl!(rcv::CUDAArray, snd::CUDAArray, source, ::Type{T}) where T = scatter_impl!(rcv.items, snd.items, source, T)
+multicast_impl(snd::CUDAArray, source) = CUDAArray(multicast_impl(snd.items, source))
+multicast_impl!(rcv::CUDAArray, snd::CUDAArray, source, ::Type{T}) where T = multicast_impl!(rcv.items, snd.items, source, T)
+scan_impl(op, a::CUDAArray, init, type) = CUDAArray(scan_impl(op, a.items, init, type))
+reduction_impl(op, a::CUDAArray, destination; kwargs...) = CUDAArray(reduction_impl(op, a.items, destination; kwargs...))
+is_consistent(graph::ExchangeGraph{<:CUDAArray}) = is_consistent(ExchangeGraph(graph.snd.items, graph.rcv.items))
+allocate_exchange_impl(snd::CUDAArray, graph::ExchangeGraph{<:CUDAArray}) =
+    CUDAArray(allocate_exchange_impl(snd.items, ExchangeGraph(graph.snd.items, graph.rcv.items)))
+setup_exchange_impl(rcv::CUDAArray, snd::CUDAArray, graph::ExchangeGraph{<:CUDAArray}) =
+    setup_exchange_impl(rcv.items, snd.items, ExchangeGraph(graph.snd.items, graph.rcv.items))
+function exchange_impl!(rcv::CUDAArray, snd::CUDAArray, graph::ExchangeGraph{<:CUDAArray}, setup)
+    exchange_impl!(rcv.items, snd.items, ExchangeGraph(graph.snd.items, graph.rcv.items), setup)
+    @fake_async rcv
+end
+
+"`distribute_with_cuda(a)`: the backend's `distribute` (cf. distribute_with_debug, src/debug_array.jl:24-31)."
+distribute_with_cuda(a) = CUDAArray(collect(a))
+
+"""
+    with_cuda(f; devices = 0:ngpus-1, arena_bytes)
+
+`with_cuda(f) = f(distribute_with_cuda)` (cf. with_debug, src/debug_array.jl:7-9): creates one device context per part.
+"""
+function with_cuda(f; devices = nothing, arena_bytes::UInt64 = UInt64(8) << 30)
+    devs = devices === nothing ? Int32.(0:parse(Int, get(ENV, "PA_B200_NGPUS", "1"))-1) : Int32.(collect(devices))
+    CTX[] = Contexts(devs; arena_bytes)
     try
-        # index metadata keeps using the MPI backend of the reference; payloads go to the GPU
-        f(a -> distribute_with_mpi(a; comm), b)
+        f(distribute_with_cuda)
     finally
-        ccall((:pa_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), b.h)
+        finalize(CTX[]); CTX[] = nothing
     end
 end
 
-# ---------------------------------------------------------------- plan: PRange + VectorAssemblyCache
+# ------------------------------------------------------------------------------------------ plan: PRange + VectorAssemblyCache
 mutable struct DevicePlan
-    h::Ptr{Cvoid}
+    h::Vector{Ptr{Cvoid}}   # pa_plan* per part
 end
+const PLANS = IdDict{Any,DevicePlan}()   # memoised per partition object, like assembly_cache (src/p_range.jl:354-376)
 
 "Upload the exchange plan of `index_partition` (assembly_neighbors / assembly_local_indices, src/p_range.jl:417-531)."
-function DevicePlan(b::CUDABackend, index_partition)
-    h = Ref{Ptr{Cvoid}}()
-    @pacall ccall((:pa_plan_create, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), b.h, h)
-    nsnd, nrcv = assembly_neighbors(index_partition)
-    lsnd, lrcv = assembly_local_indices(index_partition, nsnd, nrcv)
-    # neighbour-side local ids (one exchange of the lid lists, like the gid exchange at src/p_range.jl:517-518)
-    graph = ExchangeGraph(nsnd, nrcv)
-    rl_snd = exchange_fetch(lrcv, reverse(graph))   # for my snd entries: the neighbour's rcv lids
-    rl_rcv = exchange_fetch(lsnd, graph)            # for my rcv entries: the neighbour's snd lids
-    map(index_partition, nsnd, nrcv, lsnd, lrcv, rl_snd, rl_rcv) do ids, ns, nr, ls, lr, rs, rr
-        o2l = collect(Int32, own_to_local(ids)); g2l = collect(Int32, ghost_to_local(ids))
-        @pacall ccall((:pa_plan_set_part, LIB), Cint,
-            (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Int32}, Ptr{Int32},
-             Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32},
-             Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
-            h[], 0, local_length(ids), own_length(ids), o2l, g2l,
-            length(ns), collect(Int32, ns), ls.ptrs, ls.data, rs.data,
-            length(nr), collect(Int32, nr), lr.ptrs, lr.data, rr.data)
-    end
-    sym = reduction(max, map(local_length, index_partition); destination=:all, init=0)
-    @pacall ccall((:pa_plan_commit, LIB), Cint, (Ptr{Cvoid}, Int64), h[], PartitionedArrays.getany(sym))
-    p = DevicePlan(h[])
-    finalizer(x -> ccall((:pa_plan_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), p)
-end
-
-# ---------------------------------------------------------------- PVector payload on the GPU
-mutable struct DeviceVector
-    h::Ptr{Cvoid}
-    plan::DevicePlan
-    n_local::Int
-end
-function DeviceVector(plan::DevicePlan, n_local)
-    h = Ref{Ptr{Cvoid}}()
-    @pacall ccall((:pa_vec_create, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), plan.h, h)
-    v = DeviceVector(h[], plan, n_local)
-    finalizer(x -> ccall((:pa_vec_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), v)   # symmetric heap: free in SPMD order
-end
-upload!(v::DeviceVector, a::Vector{Float64}) = @pacall ccall((:pa_vec_upload, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64), v.h, 0, a, length(a))
-download!(a::Vector{Float64}, v::DeviceVector) = @pacall ccall((:pa_vec_download, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64), v.h, 0, a, length(a))
-
-Base.fill!(v::DeviceVector, a) = (@pacall ccall((:pa_vec_fill, LIB), Cint, (Ptr{Cvoid}, Float64), v.h, a); v)                       # src/p_vector.jl:816-821
-Base.copy!(d::DeviceVector, s::DeviceVector) = (@pacall ccall((:pa_vec_copy, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), d.h, s.h); d)      # :800-814
-LinearAlgebra.rmul!(v::DeviceVector, a::Number) = (@pacall ccall((:pa_vec_scale, LIB), Cint, (Ptr{Cvoid}, Float64), v.h, a); v)       # :1194-1199
-"y .= a.*x .+ b.*y  (broadcast materialize!, src/p_vector.jl:1208-1277)"
-axpby!(a, x::DeviceVector, b, y::DeviceVector) = (@pacall ccall((:pa_vec_axpby, LIB), Cint, (Ptr{Cvoid}, Float64, Ptr{Cvoid}, Float64), y.h, a, x.h, b); y)
-function LinearAlgebra.dot(x::DeviceVector, y::DeviceVector)                                                                          # :1189-1192
-    r = Ref{Float64}(); @pacall ccall((:pa_vec_dot, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}), x.h, y.h, r); r[]
-end
-function LinearAlgebra.norm(x::DeviceVector)                                                                                           # :1201-1206
-    r = Ref{Float64}(); @pacall ccall((:pa_vec_norm2, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), x.h, r); sqrt(r[])
-end
-struct DeviceTask; ctx::Ptr{Cvoid}; end
-Base.wait(t::DeviceTask) = @pacall ccall((:pa_ctx_sync, LIB), Cint, (Ptr{Cvoid},), t.ctx)
-consistent!(v::DeviceVector, b::CUDABackend) = (@pacall ccall((:pa_vec_consistent, LIB), Cint, (Ptr{Cvoid},), v.h); DeviceTask(b.h))  # :747-755
-assemble!(v::DeviceVector, b::CUDABackend) = (@pacall ccall((:pa_vec_assemble, LIB), Cint, (Ptr{Cvoid},), v.h); DeviceTask(b.h))      # :695-708
-# assemble!(op, v) (:699-708); insert(a,b) = b (:755)
-const PA_OP = Dict{Any,Int32}(+ => 0, max => 1, min => 2, PartitionedArrays.insert => 6)
-assemble!(op, v::DeviceVector, b::CUDABackend) = (@pacall ccall((:pa_vec_assemble_op, LIB), Cint, (Ptr{Cvoid}, Int32), v.h, PA_OP[op]); DeviceTask(b.h))
-"reduce(op, a) (src/p_vector.jl:1178-1183): the per-part reduction runs on the device; the reduction over parts is the backend's `reduce`"
-function reduce_own(op, v::DeviceVector)
-    r = Ref{Float64}(); @pacall ccall((:pa_vec_reduce_parts, LIB), Cint, (Ptr{Cvoid}, Int32, Float64, Ptr{Float64}), v.h, PA_OP[op], 0.0, r); r[]
-end
-"norm(a,p) (:1201-1206): sum over parts of norm(own,p)^p, then ^(1/p)  (op 3 = sum|x|, op 5 = sum|x|^p)"
-function norm_p_own(v::DeviceVector, p::Real)
-    r = Ref{Float64}(); @pacall ccall((:pa_vec_reduce_parts, LIB), Cint, (Ptr{Cvoid}, Int32, Float64, Ptr{Float64}), v.h, p == 1 ? Int32(3) : Int32(5), Float64(p), r); r[]
-end
-
-# ---------------------------------------------------------------- exchange!(rcv, snd, graph) with device-resident buffers
-# exchange_impl!(rcv, snd, graph, setup, ::Type{<:AbstractVector}) (src/primitives.jl:1020-1042; src/mpi_array.jl:525-614):
-# snd/rcv are JaggedArrays of 8-byte elements; the receiver pulls its segments from the senders' HBM.
-mutable struct DeviceExchange
-    h::Ptr{Cvoid}
-end
-function DeviceExchange(b::CUDABackend, graph::ExchangeGraph, snd_ptrs::Vector{Int64}, rcv_ptrs::Vector{Int64}, rcv_src_offsets::Vector{Int64}, sym_snd_len)
-    h = Ref{Ptr{Cvoid}}()
-    @pacall ccall((:pa_xchg_create, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), b.h, h)
-    map(graph.snd, graph.rcv) do s, r   # one part per process: a single item
-        @pacall ccall((:pa_xchg_set_part, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Ptr{Int64}, Int32, Ptr{Int32}, Ptr{Int64}, Ptr{Int64}),
-                      h[], 0, length(s), Int32.(s), snd_ptrs, length(r), Int32.(r), rcv_ptrs, rcv_src_offsets)
-    end
-    @pacall ccall((:pa_xchg_commit, LIB), Cint, (Ptr{Cvoid}, Int64), h[], sym_snd_len)
-    x = DeviceExchange(h[])
-    finalizer(y -> ccall((:pa_xchg_destroy, LIB), Cint, (Ptr{Cvoid},), y.h), x)
-end
-function exchange!(rcv::Vector{T}, snd::Vector{T}, x::DeviceExchange, b::CUDABackend) where T<:Union{Float64,Int64}
-    @pacall ccall((:pa_xchg_upload_snd, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int64), x.h, 0, snd, length(snd))
-    @pacall ccall((:pa_xchg_exchange, LIB), Cint, (Ptr{Cvoid},), x.h)
-    @pacall ccall((:pa_xchg_download_rcv, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int64), x.h, 0, rcv, length(rcv))   # = fetch(t)
-    rcv
-end
-
-# ---------------------------------------------------------------- PSparseMatrix payload on the GPU
-mutable struct DeviceMatrix
-    h::Ptr{Cvoid}
-end
-"Upload an assembled PSparseMatrix whose local matrices are SparseMatrixCSR{1,Float64,Ti} (split or not)."
-function DeviceMatrix(A::PSparseMatrix, rows::DevicePlan, cols::DevicePlan)
-    h = Ref{Ptr{Cvoid}}()
-    @pacall ccall((:pa_mat_create, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), rows.h, cols.h, h)
-    map(partition(A)) do a
-        if a isa PartitionedArrays.AbstractSplitMatrix      # src/p_sparse_matrix.jl:588-593
-            oo, oh = a.blocks.own_own, a.blocks.own_ghost
-            Ti = eltype(oo.rowptr); bits = Int32(8sizeof(Ti))
-            @pacall ccall((:pa_mat_set_csr_split, LIB), Cint,
-                (Ptr{Cvoid}, Int32, Int64, Int32, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}),
-                h[], 0, size(oo, 1), 1, bits, bits, oo.rowptr, oo.colval, oo.nzval, oh.rowptr, oh.colval, oh.nzval)
-        else                                                  # HPCG layout (HPCG/src/sparse_matrix.jl:115-121)
-            Ti = eltype(a.rowptr); bits = Int32(8sizeof(Ti))
-            @pacall ccall((:pa_mat_set_csr, LIB), Cint,
-                (Ptr{Cvoid}, Int32, Int64, Int64, Int32, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}),
-                h[], 0, size(a, 1), size(a, 2), 1, bits, bits, a.rowptr, a.colval, a.nzval)
+function device_plan(index_partition::CUDAArray)
+    get!(PLANS, index_partition) do
+        ctx = contexts()
+        np = length(index_partition)
+        nsnd, nrcv = assembly_neighbors(index_partition)
+        lsnd, lrcv = assembly_local_indices(index_partition, nsnd, nrcv)
+        graph = ExchangeGraph(nsnd, nrcv)
+        # neighbour-side local ids: one exchange of the lid lists (as the gid exchange at src/p_range.jl:517-518)
+        rl_snd = exchange(lrcv, reverse(graph)) |> fetch    # for my snd entries: the neighbour's rcv lids
+        rl_rcv = exchange(lsnd, graph) |> fetch             # for my rcv entries: the neighbour's snd lids
+        sym = maximum(map(local_length, index_partition).items)
+        h = Vector{Ptr{Cvoid}}(undef, np)
+        for k in 1:np
+            r = Ref{Ptr{Cvoid}}()
+            check(ccall((:pa_plan_create, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), ctx.h[k], r)); h[k] = r[]
+            ids = index_partition.items[k]
+            o2l = collect(Int32, own_to_local(ids)); g2l = collect(Int32, ghost_to_local(ids))
+            ls, lr, rs, rr = lsnd.items[k], lrcv.items[k], rl_snd.items[k], rl_rcv.items[k]
+            ns, nr = collect(Int32, nsnd.items[k]), collect(Int32, nrcv.items[k])
+            check(ccall((:pa_plan_set_part, LIB), Cint,
+                (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32},
+                 Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
+                h[k], 0, local_length(ids), own_length(ids), o2l, g2l, length(ns), ns, ls.ptrs, ls.data, rs.data,
+                length(nr), nr, lr.ptrs, lr.data, rr.data))
+            check(ccall((:pa_plan_commit, LIB), Cint, (Ptr{Cvoid}, Int64), h[k], sym))
         end
+        p = DevicePlan(h)
+        finalizer(x -> foreach(q -> ccall((:pa_plan_destroy, LIB), Cint, (Ptr{Cvoid},), q), x.h), p)
     end
-    @pacall ccall((:pa_mat_commit, LIB), Cint, (Ptr{Cvoid},), h[])
-    m = DeviceMatrix(h[])
-    finalizer(x -> ccall((:pa_mat_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), m)
 end
 
-"mul!(c,A,b[,α,β]) (src/p_sparse_matrix.jl:2090-2142) and HPCG mul_no_lat! (HPCG/src/hpcg_utils.jl:6-17)"
-LinearAlgebra.mul!(c::DeviceVector, A::DeviceMatrix, b::DeviceVector, α::Number=1.0, β::Number=0.0) =
-    (@pacall ccall((:pa_spmv, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64, UInt32), A.h, b.h, c.h, α, β, 0); c)
+# ------------------------------------------------------------------------------------------ device items
+"Local values of one part of a PVector, resident in that part's HBM (the item type of a device PVector's partition)."
+mutable struct DeviceVector <: AbstractVector{Float64}
+    h::Ptr{Cvoid}
+    part::Int
+    n::Int
+end
+Base.size(v::DeviceVector) = (v.n,)
+Base.getindex(v::DeviceVector, i::Int) = error("scalar indexing of a DeviceVector: use to_host(v)")
+"Local matrix of one part of a PSparseMatrix (own rows x local columns, CSR) in that part's HBM."
+mutable struct DeviceMatrix <: AbstractMatrix{Float64}
+    h::Ptr{Cvoid}
+    part::Int
+    dims::Tuple{Int,Int}
+end
+Base.size(a::DeviceMatrix) = a.dims
+Base.getindex(a::DeviceMatrix, i::Int, j::Int) = error("scalar indexing of a DeviceMatrix")
+
+const DevicePVector = PVector{DeviceVector}
+const DevicePSparseMatrix = PSparseMatrix{DeviceMatrix}
+handles(v::PVector) = map(i -> i.h, partition(v).items)
+nparts(v) = length(partition(v))
+
+"PVector(undef, index_partition) on the device (src/p_vector.jl:334-344)."
+function device_pvector(index_partition::CUDAArray)
+    plan = device_plan(index_partition)
+    items = map(1:length(index_partition)) do k
+        r = Ref{Ptr{Cvoid}}()
+        check(ccall((:pa_vec_create, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), plan.h[k], r))
+        v = DeviceVector(r[], k, local_length(index_partition.items[k]))
+        finalizer(x -> ccall((:pa_vec_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), v)   # symmetric heap: freed in creation order per part
+    end
+    PVector(CUDAArray(items), index_partition)
+end
+Base.similar(v::DevicePVector) = device_pvector(partition(axes(v, 1)))
+
+"Move a host PVector (Vector{Float64} items) onto the GPUs / back."
+function to_device(v::PVector)
+    d = device_pvector(partition(axes(v, 1)))
+    foreach_part(nparts(d)) do k
+        a = partition(v).items[k]
+        check(ccall((:pa_vec_upload, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64), partition(d).items[k].h, 0, a, length(a)))
+    end
+    d
+end
+function to_host(d::DevicePVector)
+    items = map(i -> zeros(Float64, i.n), partition(d).items)
+    foreach_part(nparts(d)) do k
+        check(ccall((:pa_vec_download, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64), partition(d).items[k].h, 0, items[k], length(items[k])))
+    end
+    PVector(CUDAArray(items), partition(axes(d, 1)))
+end
+
+"Upload an assembled PSparseMatrix (SparseMatrixCSR{1}/CSC local matrices, split or not) — src/p_sparse_matrix.jl:971-991."
+function to_device(A::PSparseMatrix)
+    rows, cols = device_plan(partition(axes(A, 1))), device_plan(partition(axes(A, 2)))
+    items = map(1:length(partition(A))) do k
+        r = Ref{Ptr{Cvoid}}()
+        check(ccall((:pa_mat_create, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), rows.h[k], cols.h[k], r))
+        a = partition(A).items[k]
+        upload_local!(r[], a)
+        check(ccall((:pa_mat_commit, LIB), Cint, (Ptr{Cvoid},), r[]))
+        m = DeviceMatrix(r[], k, size(a))
+        finalizer(x -> ccall((:pa_mat_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), m)
+    end
+    PSparseMatrix(CUDAArray(items), partition(axes(A, 1)), partition(axes(A, 2)), A.assembled)
+end
+bits(::Type{T}) where T = Int32(8sizeof(T))
+function upload_local!(h, a::PartitionedArrays.AbstractSplitMatrix)            # src/p_sparse_matrix.jl:588-593
+    oo, oh = a.blocks.own_own, a.blocks.own_ghost
+    upload_split!(h, oo, oh)
+end
+upload_split!(h, oo::SparseMatrixCSR{Bi,Float64,Ti}, oh::SparseMatrixCSR{Bi,Float64,Ti}) where {Bi,Ti} =
+    check(ccall((:pa_mat_set_csr_split, LIB), Cint,
+        (Ptr{Cvoid}, Int32, Int64, Int32, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}),
+        h, 0, size(oo, 1), Bi, bits(Ti), bits(Ti), oo.rowptr, oo.colval, oo.nzval, oh.rowptr, oh.colval, oh.nzval))
+upload_split!(h, oo::SparseMatrixCSC{Float64,Ti}, oh::SparseMatrixCSC{Float64,Ti}) where Ti =
+    check(ccall((:pa_mat_set_csc_split, LIB), Cint,
+        (Ptr{Cvoid}, Int32, Int64, Int32, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}),
+        h, 0, size(oo, 1), 1, bits(Ti), bits(Ti), oo.colptr, oo.rowval, oo.nzval, oh.colptr, oh.rowval, oh.nzval))
+upload_local!(h, a::SparseMatrixCSR{Bi,Float64,Ti}) where {Bi,Ti} =       # HPCG layout (HPCG/src/sparse_matrix.jl:115-121)
+    check(ccall((:pa_mat_set_csr, LIB), Cint, (Ptr{Cvoid}, Int32, Int64, Int64, Int32, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}),
+        h, 0, size(a, 1), size(a, 2), Bi, bits(Ti), bits(Ti), a.rowptr, a.colval, a.nzval))
+upload_local!(h, a::SparseMatrixCSC{Float64,Ti}) where Ti =
+    check(ccall((:pa_mat_set_csc, LIB), Cint, (Ptr{Cvoid}, Int32, Int64, Int64, Int32, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}),
+        h, 0, size(a, 1), size(a, 2), 1, bits(Ti), bits(Ti), a.colptr, a.rowval, a.nzval))
+
+# ------------------------------------------------------------------------------------------ PVector / PSparseMatrix level overloads
+struct DeviceTask; n::Int; end
+function Base.wait(t::DeviceTask)
+    ctx = contexts()
+    foreach_part(k -> check(ccall((:pa_ctx_sync, LIB), Cint, (Ptr{Cvoid},), ctx.h[k])), t.n)
+end
+Base.fetch(t::DeviceTask) = wait(t)
+
+each(f, v::DevicePVector) = foreach_part(k -> check(f(partition(v).items[k].h)), nparts(v))
+
+Base.fill!(v::DevicePVector, a) = (each(h -> ccall((:pa_vec_fill, LIB), Cint, (Ptr{Cvoid}, Float64), h, a), v); v)           # src/p_vector.jl:816-821
+LinearAlgebra.rmul!(v::DevicePVector, a::Number) = (each(h -> ccall((:pa_vec_scale, LIB), Cint, (Ptr{Cvoid}, Float64), h, a), v); v)  # :1194-1199
+function Base.copy!(d::DevicePVector, s::DevicePVector)                                                                     # :800-814
+    foreach_part(k -> check(ccall((:pa_vec_copy, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), partition(d).items[k].h, partition(s).items[k].h)), nparts(d)); d
+end
+Base.copyto!(d::DevicePVector, s::DevicePVector) = copy!(d, s)
+"consistent!(v) (src/p_vector.jl:747-755) / assemble!([op,] v) (:695-708): peer-load kernels; returns a waitable like the reference's task."
+consistent!(v::DevicePVector) = (each(h -> ccall((:pa_vec_consistent, LIB), Cint, (Ptr{Cvoid},), h), v); DeviceTask(nparts(v)))
+const PA_OP = IdDict{Any,Int32}(+ => 0, max => 1, min => 2, PartitionedArrays.insert => 6)
+assemble!(v::DevicePVector) = assemble!(+, v)
+assemble!(op, v::DevicePVector) = (each(h -> ccall((:pa_vec_assemble_op, LIB), Cint, (Ptr{Cvoid}, Int32), h, PA_OP[op]), v); DeviceTask(nparts(v)))
+
+function reduce_scalar(sym::Symbol, x::DevicePVector, y = nothing)
+    out = zeros(Float64, nparts(x))
+    foreach_part(nparts(x)) do k
+        r = Ref{Float64}()
+        hx = partition(x).items[k].h
+        rc = y === nothing ? ccall((sym, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), hx, r) :
+                             ccall((sym, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}), hx, partition(y).items[k].h, r)
+        check(rc); out[k] = r[]
+    end
+    out[1]   # every part holds the all-reduced value (part order sum, bitwise identical on all parts)
+end
+LinearAlgebra.dot(a::DevicePVector, b::DevicePVector) = reduce_scalar(:pa_vec_dot, a, b)                                    # :1189-1192
+Base.sum(a::DevicePVector) = reduce_scalar(:pa_vec_sum, a)                                                                  # :1178-1187
+function LinearAlgebra.norm(a::DevicePVector, p::Real = 2)                                                                  # :1201-1206
+    p == 2 && return sqrt(reduce_scalar(:pa_vec_norm2, a))
+    out = zeros(Float64, nparts(a))
+    foreach_part(nparts(a)) do k
+        r = Ref{Float64}()
+        check(ccall((:pa_vec_reduce_parts, LIB), Cint, (Ptr{Cvoid}, Int32, Float64, Ptr{Float64}), partition(a).items[k].h, p == 1 ? Int32(3) : Int32(5), Float64(p), r))
+        out[k] = r[]
+    end
+    sum(out)^(1 / p)
+end
+function Base.reduce(op, a::DevicePVector; kwargs...)                                                                        # :1178-1183
+    out = zeros(Float64, nparts(a))
+    foreach_part(nparts(a)) do k
+        r = Ref{Float64}()
+        check(ccall((:pa_vec_reduce_parts, LIB), Cint, (Ptr{Cvoid}, Int32, Float64, Ptr{Float64}), partition(a).items[k].h, PA_OP[op], 0.0, r))
+        out[k] = r[]
+    end
+    reduce(op, out; kwargs...)
+end
+Base.maximum(a::DevicePVector) = reduce(max, a)
+Base.minimum(a::DevicePVector) = reduce(min, a)
+
+"w .= a.*x .+ b.*y — the broadcast updates of the CG loop (materialize!, src/p_vector.jl:1208-1277; own AND ghost entries when the partitions are identical)."
+function waxpby!(w::DevicePVector, a::Number, x::DevicePVector, b::Number, y::DevicePVector)
+    foreach_part(nparts(w)) do k
+        check(ccall((:pa_vec_waxpby, LIB), Cint, (Ptr{Cvoid}, Float64, Ptr{Cvoid}, Float64, Ptr{Cvoid}),
+                    partition(w).items[k].h, a, partition(x).items[k].h, b, partition(y).items[k].h))
+    end
+    w
+end
+LinearAlgebra.axpy!(a::Number, x::DevicePVector, y::DevicePVector) = waxpby!(y, a, x, 1.0, y)
+LinearAlgebra.axpby!(a::Number, x::DevicePVector, b::Number, y::DevicePVector) = waxpby!(y, a, x, b, y)
+
+"mul!(c,A,b[,α,β]) (src/p_sparse_matrix.jl:2090-2142; sub-assembled matrices end with assemble!(c)) and HPCG mul_no_lat! (HPCG/src/hpcg_utils.jl:6-17)."
+function LinearAlgebra.mul!(c::DevicePVector, A::DevicePSparseMatrix, b::DevicePVector, α::Number = 1.0, β::Number = 0.0)
+    foreach_part(nparts(c)) do k
+        check(ccall((:pa_spmv, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64, UInt32),
+                    partition(A).items[k].h, partition(b).items[k].h, partition(c).items[k].h, α, β, 0))
+    end
+    c
+end
+function LinearAlgebra.mul!(c::DevicePVector, At::Transpose{T,<:DevicePSparseMatrix} where T, b::DevicePVector, α::Number = 1.0, β::Number = 0.0)   # :2144-2162
+    A = At.parent
+    foreach_part(nparts(c)) do k
+        check(ccall((:pa_spmv_transpose, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64),
+                    partition(A).items[k].h, partition(b).items[k].h, partition(c).items[k].h, α, β))
+    end
+    c
+end
+function Base.:*(A::DevicePSparseMatrix, b::DevicePVector)                                                                   # :2042-2049
+    c = device_pvector(partition(axes(A, 1))); mul!(c, A, b); c
+end
+LinearAlgebra.fillstored!(A::DevicePSparseMatrix, a) =
+    (foreach_part(k -> check(ccall((:pa_mat_fill_stored, LIB), Cint, (Ptr{Cvoid}, Float64), partition(A).items[k].h, a)), length(partition(A))); A)
 
 struct PaCgResult; iters::Int32; converged::Int32; residual0::Float64; residual::Float64; end
-"ref_cg!(x,A,b; tolerance, maxiter, Pl=Identity) (HPCG/src/ref_cg.jl:119-134) — the whole loop on the device"
-function ref_cg!(x::DeviceVector, A::DeviceMatrix, b::DeviceVector; tolerance=0.0, maxiter=50)
-    res = Ref{PaCgResult}(); hist = zeros(Float64, maxiter + 1)
-    @pacall ccall((:pa_cg, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Float64, UInt32, Ptr{PaCgResult}, Ptr{Float64}),
-                  A.h, x.h, b.h, maxiter, tolerance, 0, res, hist)
-    x, hist, res[].residual0, res[].residual, res[].iters
+"ref_cg!(x,A,b; tolerance, maxiter, Pl=Identity) (HPCG/src/ref_cg.jl:119-134) — the whole loop on the devices (3 launches per iteration)."
+function ref_cg!(x::DevicePVector, A::DevicePSparseMatrix, b::DevicePVector; tolerance = 0.0, maxiter = length(b))
+    np = nparts(x)
+    res = [Ref{PaCgResult}() for _ in 1:np]; hist = [zeros(Float64, maxiter + 1) for _ in 1:np]
+    foreach_part(np) do k
+        check(ccall((:pa_cg, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Float64, UInt32, Ptr{PaCgResult}, Ptr{Float64}),
+                    partition(A).items[k].h, partition(x).items[k].h, partition(b).items[k].h, maxiter, tolerance, 0, res[k], hist[k]))
+    end
+    x, hist[1][1:res[1][].iters+1], res[1][].residual0, res[1][].residual, res[1][].iters
 end
 
 end # module

@@ -708,7 +708,6 @@ __global__ void __launch_bounds__(GS_THREADS, (MODE == 1 ? 2 : 3)) k_gs_sell(con
               *a.err = 3;
               break;
             }
-            __nanosleep(40);  // 32 lanes polling 32 different sectors flat out saturate the SM's LSU and starve the rows that can run
           }
           xv[u] = __longlong_as_double((long long)((w1[u] << 32) | (w0[u] & 0xffffffffull)));
         }
@@ -732,6 +731,162 @@ __global__ void __launch_bounds__(GS_THREADS, (MODE == 1 ? 2 : 3)) k_gs_sell(con
         gs_fence_acq_rel();
         asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(a.done + lev) : "memory");
       }
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------ the SELL dataflow kernel of the lexicographic order
+// One thread per row, one warp per slice, like k_gs_sell, but with everything that does not depend on the rows of
+// earlier levels done BEFORE the warp waits:
+//   before the gate  the slice's entries are read (coalesced, L2-prefetched one slice ahead) and parked in shared memory
+//                    ([slot][lane]: conflict-free); entries whose column is NOT updated earlier in this sweep (later
+//                    levels, ghosts, the diagonal) are multiplied with x right away — nobody writes those x before this
+//                    row publishes — and parked as products; the slots that need a NEW value are listed;
+//   the gate         lane 0 polls the completion counter of the previous level with relaxed loads — NO fence: the counter
+//                    only keeps 31 of 32 lanes (and all their sector requests) out of the polling; whether a NEW value has
+//                    really arrived is decided by its (value, sweep epoch) pair, written as one 16-byte store;
+//   behind the gate  the NEW values are gathered (pairs verified, re-read in the rare case the counter ran ahead of the
+//                    data), multiplied and parked; then the ordered chain s -= product[k], k = 0..W-1 in CSR order, on
+//                    all 32 lanes at once; s += d*x_old; s /= d; publish (pair + plain x); relaxed increment of the level.
+// Critical path per level: gather of the NEW pairs + W dependent subtractions + divide + publish — no fence, no
+// matrix load.  Same arithmetic and order as k_gs_flow (bit-identical sweeps, tests/test_gpu_hpcg_mg.py).
+#define GSF_WARPS (GS_THREADS / 32)
+#define GSF_WARP_BYTES(W) ((size_t)(W) * 32 * (8 + 4 + 1))
+
+template <int W>
+__global__ void __launch_bounds__(GS_THREADS, 2) k_gs_sell_flow(const GsSellArgs a) {
+  extern __shared__ __align__(16) unsigned char gsf_smem[];
+  constexpr int B = W == 27 ? 9 : (W == 7 ? 7 : 8);
+  const int WD = W ? W : a.W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *sval = reinterpret_cast<double *>(gsf_smem + (size_t)warp * GSF_WARP_BYTES(WD)) + lane;   // [slot][lane]
+  int32_t *scode = reinterpret_cast<int32_t *>(gsf_smem + (size_t)warp * GSF_WARP_BYTES(WD) + (size_t)WD * 32 * 8) + lane;
+  unsigned char *slist = gsf_smem + (size_t)warp * GSF_WARP_BYTES(WD) + (size_t)WD * 32 * 12 + lane;
+  const int64_t nw = (int64_t)gridDim.x * GSF_WARPS;
+  const int64_t w = (int64_t)blockIdx.x * GSF_WARPS + warp;
+  const unsigned epoch = (unsigned)a.epoch;
+  const uint64_t pol = gs_stream_policy(), keep = gs_keep_policy(1);
+  for (int64_t i = a.g0 + w; i < a.g1; i += nw) {
+    const int64_t g = a.backward ? a.ngroups - 1 - i : i;
+    const int32_t row = a.rows[g * 32 + lane];
+    const int32_t *cp = a.cols + g * WD * 32 + lane;
+    const double *vp = a.vals + g * WD * 32 + lane;
+    {  // the next slice of this warp: start its HBM reads now
+      const int64_t inext = i + nw;
+      if (inext < a.g1) {
+        const int64_t gn = a.backward ? a.ngroups - 1 - inext : inext;
+        const char *nv = reinterpret_cast<const char *>(a.vals + gn * WD * 32), *nc = reinterpret_cast<const char *>(a.cols + gn * WD * 32);
+        for (int l = lane; l < 2 * WD; l += 32) gs_prefetch_l2(nv + (size_t)l * 128);
+        if (lane < WD) gs_prefetch_l2(nc + (size_t)lane * 128);
+      }
+    }
+    // ---- before the gate
+    double bval = 0.0, xold = 0.0, d = 0.0;
+    int nf = 0;
+    if (row >= 0) {
+      bval = __ldg(a.b + row);
+      if (!a.zero_guess) xold = gs_ld_x(a.x + row, keep);
+    }
+#pragma unroll 1
+    for (int k0 = 0; k0 < WD; k0 += B) {
+      int32_t code[B];
+      double v[B], xv[B];
+#pragma unroll
+      for (int u = 0; u < B; ++u) {
+        const bool in = (W ? (k0 + u < W) : (k0 + u < WD)) && row >= 0;
+        code[u] = in ? gs_ld_stream(cp + (k0 + u) * 32, pol) : -1;
+        v[u] = in ? gs_ld_stream(vp + (k0 + u) * 32, pol) : 0.0;
+      }
+      bool fresh[B], use[B];
+#pragma unroll
+      for (int u = 0; u < B; ++u) {
+        const bool valid = code[u] >= 0;
+        const int32_t c = code[u] & GS_COL_MASK;
+        const bool ff = valid && (code[u] & GS_COL_FRESH), own = valid && (code[u] & GS_COL_OWN);
+        fresh[u] = a.backward ? (own && !ff && c != row) : ff;
+        use[u] = valid && (!a.zero_guess || ff);
+        xv[u] = (use[u] && !fresh[u]) ? gs_ld_x(a.x + c, keep) : 0.0;  // OLD values, ghosts, the diagonal: final until this row publishes
+        if (valid && c == row) d = v[u];
+      }
+#pragma unroll
+      for (int u = 0; u < B; ++u) {
+        if (W ? (k0 + u < W) : (k0 + u < WD)) {
+          const int k = k0 + u;
+          if (fresh[u]) {
+            sval[k * 32] = v[u];
+            scode[k * 32] = code[u] & GS_COL_MASK;
+            slist[nf * 32] = (unsigned char)k;
+            ++nf;
+          } else {
+            sval[k * 32] = use[u] ? __dmul_rn(v[u], xv[u]) : 0.0;  // unused slots contribute +0.0: s - (+0.0) == s bit for bit
+          }
+        }
+      }
+    }
+    // ---- the gate (relaxed counter, no fence: it only spares the polling; the pairs below carry the proof)
+    {
+      const int lev = a.slice_lev[g];
+      const int glev = a.backward ? lev + 1 : lev - 1;
+      if (glev >= 0 && glev < a.nlev) {
+        if (lane == 0) {
+          const unsigned long long target = a.sweep * (unsigned long long)a.lev_n[glev];
+          long long t0 = 0;
+          while (gs_ld_relaxed(a.done + glev) < target) {
+            if (!t0) {
+              t0 = clock64();
+            } else if (clock64() - t0 > GS_SPIN_LIMIT) {
+              *a.err = 3;
+              break;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      // ---- behind the gate: the NEW values
+      for (int j0 = 0; j0 < nf; j0 += 7) {
+        unsigned long long w0[7], w1[7];
+        int kk[7];
+#pragma unroll
+        for (int u = 0; u < 7; ++u) {
+          kk[u] = j0 + u < nf ? (int)slist[(j0 + u) * 32] : -1;
+          w0[u] = w1[u] = 0ull;
+          if (kk[u] >= 0)
+            asm volatile("ld.relaxed.gpu.global.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(w0[u]), "=l"(w1[u]) : "l"(a.xe + scode[kk[u] * 32]), "l"(keep) : "memory");
+        }
+#pragma unroll
+        for (int u = 0; u < 7; ++u) {
+          if (kk[u] >= 0) {
+            long long t0 = 0;
+            while ((unsigned)(w0[u] >> 32) != epoch || (unsigned)(w1[u] >> 32) != epoch) {
+              asm volatile("ld.relaxed.gpu.global.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(w0[u]), "=l"(w1[u]) : "l"(a.xe + scode[kk[u] * 32]), "l"(keep) : "memory");
+              if (!t0) {
+                t0 = clock64();
+              } else if (clock64() - t0 > GS_SPIN_LIMIT) {
+                *a.err = 3;
+                break;
+              }
+            }
+            const double xn = __longlong_as_double((long long)((w1[u] << 32) | (w0[u] & 0xffffffffull)));
+            sval[kk[u] * 32] = __dmul_rn(sval[kk[u] * 32], xn);
+          }
+        }
+      }
+      // ---- the ordered chain, all lanes at once
+      if (row >= 0) {
+        double s = bval;
+        if (W) {
+#pragma unroll
+          for (int k = 0; k < W; ++k) s = __dsub_rn(s, sval[k * 32]);  // s -= a*x[col], in CSR order
+        } else {
+          for (int k = 0; k < WD; ++k) s = __dsub_rn(s, sval[k * 32]);
+        }
+        if (!a.zero_guess) s = __dadd_rn(s, __dmul_rn(d, xold));  // s += d*x[row]
+        s = __ddiv_rn(s, d);
+        gs_publish(a.xe + row, a.x + row, s, epoch, keep);
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(a.done + lev) : "memory");
     }
   }
 }
@@ -1175,17 +1330,20 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
           c->launches++;
         }
       } else {
-        // gs_sell_mode 2 (default): level gate; 1: per-row dataflow
-        const bool gate = pa_knob(c, "gs_sell_mode", 2) == 2;
-        void (*kern)(const GsSellArgs) = gate ? (o->W == 27 ? k_gs_sell<27, 2> : (o->W == 7 ? k_gs_sell<7, 2> : k_gs_sell<0, 2>))
-                                              : (o->W == 27 ? k_gs_sell<27, 1> : (o->W == 7 ? k_gs_sell<7, 1> : k_gs_sell<0, 1>));
+        // gs_sell_mode 3 (default): staged dataflow kernel (relaxed level gate + per-row pairs); 2: fenced level gate; 1: per-row pairs only
+        const int mode = (int)pa_knob(c, "gs_sell_mode", 3);
+        void (*kern)(const GsSellArgs) = mode == 3 ? (o->W == 27 ? k_gs_sell_flow<27> : (o->W == 7 ? k_gs_sell_flow<7> : k_gs_sell_flow<0>))
+                                       : mode == 2 ? (o->W == 27 ? k_gs_sell<27, 2> : (o->W == 7 ? k_gs_sell<7, 2> : k_gs_sell<0, 2>))
+                                                   : (o->W == 27 ? k_gs_sell<27, 1> : (o->W == 7 ? k_gs_sell<7, 1> : k_gs_sell<0, 1>));
         a.slice_lev = o->d_slice_lev;
         a.lev_n = o->d_lev_n;
         a.done = o->d_done;
-        a.sweep = gate ? ++o->sweeps : 0;  // every gated sweep advances every level counter by its slice count, once
+        a.sweep = mode == 1 ? 0 : ++o->sweeps;  // every gated sweep advances every level counter by its slice count, once
         a.nlev = o->nlev;
+        const size_t smem = mode == 3 ? GSF_WARPS * GSF_WARP_BYTES(o->W) : 0;
+        if (smem) PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int ctas_per_sm = 0;
-        PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, GS_THREADS, 0));
+        PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, GS_THREADS, smem));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
         const int64_t cap = pa_knob(c, "gs_ctas", 0);
         if (cap > 0 && cap < ctas_per_sm) ctas_per_sm = (int)cap;
@@ -1193,7 +1351,7 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
         a.g1 = a.ngroups;
         // all CTAs co-resident: a waiting row only waits for rows of earlier slices, held by running warps
         const int64_t grid = std::min<int64_t>((a.ngroups + wpc - 1) / wpc, (int64_t)nsm * ctas_per_sm);
-        kern<<<(unsigned)grid, GS_THREADS, 0, c->stream>>>(a);
+        kern<<<(unsigned)grid, GS_THREADS, smem, c->stream>>>(a);
         c->launches++;
       }
       continue;

@@ -22,18 +22,18 @@ def _vec(pa, rows, vals):
 
 # every variant of the sweep kernel: default choice, warp-per-row dataflow kernel with 0 (any row length) / 4 / 8 / 16 / 32 lanes per
 # row, and the batch kernel (32 rows of one level per warp) with and without the L2 prefetch
-@pytest.mark.parametrize("lanes", [None, "sell-dataflow", 0, 4, 8, 16, 32, "batch", "batch-noprefetch"])
+@pytest.mark.parametrize("lanes", [None, "sell-rows", "sell-gate", 0, 4, 8, 16, 32, "batch", "batch-noprefetch"])
 @pytest.mark.parametrize("npd,nloc,hint", [((2, 2, 1), (8, 6, 4), True), ((1, 2, 2), (4, 4, 6), False), ((1, 1, 1), (10, 9, 8), True),
                                            ((2, 1, 1), (40, 32, 24), True)])
 def test_symmetric_gauss_seidel_is_bit_exact(pa, npd, nloc, hint, lanes):
     """smooth! (smoothers.jl:98-125): wavefront sweeps == the reference's sequential per-part sweeps, bit for bit."""
-    if nloc[0] >= 40 and lanes not in (None, "sell-dataflow", 16, "batch", "batch-noprefetch"):
+    if nloc[0] >= 40 and lanes not in (None, "sell-rows", "sell-gate", 16, "batch", "batch-noprefetch"):
         pytest.skip("the large case runs the default, the 16-lane and the batch kernels")
     lev = hpcg_mg.Level(*nloc, npd)
     P = len(lev.part)
     b = pa.CUDAArray(P, arena_bytes=32 << 20)
-    if lanes == "sell-dataflow":  # the SELL kernel with per-row flags instead of the level gate (the default, lanes=None)
-        b.set_knob("gs_sell_mode", 1)
+    if lanes in ("sell-rows", "sell-gate"):  # SELL kernel variants: per-row pairs only / fenced level gate (default, lanes=None: staged dataflow)
+        b.set_knob("gs_sell_mode", 1 if lanes == "sell-rows" else 2)
     elif isinstance(lanes, str):
         b.set_knob("gs_kernel", 1)
         b.set_knob("gs_prefetch", 0 if lanes.endswith("noprefetch") else 1)
