@@ -68,9 +68,12 @@ struct GsOrder {
   std::vector<int64_t> lev_group;  // first slice of every level, size nlev + 1 (one launch per colour)
   // level-gated sweeps (MODE 2): level of every slice, slices per level, slices finished per level summed over all sweeps
   int32_t *d_slice_lev = nullptr;
-  uint32_t *d_lev_n = nullptr;
-  unsigned long long *d_done = nullptr;
-  unsigned long long sweeps = 0;
+  uint32_t *d_lev_n = nullptr;            // [nlev * GS_SUB] slices counting into every sub-counter
+  unsigned long long *d_done = nullptr;   // [nlev * GS_SUB]
+  int64_t *d_lev_first = nullptr;         // [nlev + 1]
+  uint32_t *d_lev_tot = nullptr;          // [nlev] (fenced gate variant)
+  unsigned long long *d_done2 = nullptr;  // [nlev]
+  unsigned long long sweeps = 0, sweeps2 = 0;
 };
 #define GS_COL_FRESH (1 << 30)
 #define GS_COL_OWN (1 << 29)
@@ -609,6 +612,10 @@ struct GsSellArgs {
   unsigned long long *done;
   unsigned long long sweep;
   int nlev;
+  const int64_t *lev_first;  // first slice of every level (k_gs_sell_flow: which sub-counter a slice counts into)
+  int gate, trace;
+  const uint32_t *lev_tot;   // MODE 2: slices per level, one counter per level
+  unsigned long long *done2;
 };
 
 // minBlocksPerSM is explicit: with maxThreads alone ptxas aims at full occupancy and sinks every load next to its use,
@@ -650,9 +657,9 @@ __global__ void __launch_bounds__(GS_THREADS, (MODE == 1 ? 2 : 3)) k_gs_sell(con
       const int glev = a.backward ? lev + 1 : lev - 1;  // the level whose completion opens this one (and, by induction, all before it)
       if (glev >= 0 && glev < a.nlev) {
         if (lane == 0) {
-          const unsigned long long target = a.sweep * (unsigned long long)a.lev_n[glev];
+          const unsigned long long target = a.sweep * (unsigned long long)a.lev_tot[glev];
           long long t0 = 0;
-          while (gs_ld_relaxed(a.done + glev) < target) {
+          while (gs_ld_relaxed(a.done2 + glev) < target) {
             if (!t0) {
               t0 = clock64();
             } else if (clock64() - t0 > GS_SPIN_LIMIT) {
@@ -729,7 +736,7 @@ __global__ void __launch_bounds__(GS_THREADS, (MODE == 1 ? 2 : 3)) k_gs_sell(con
       __syncwarp();
       if (lane == 0) {
         gs_fence_acq_rel();
-        asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(a.done + lev) : "memory");
+        asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(a.done2 + lev) : "memory");
       }
     }
   }
@@ -752,6 +759,8 @@ __global__ void __launch_bounds__(GS_THREADS, (MODE == 1 ? 2 : 3)) k_gs_sell(con
 // Critical path per level: gather of the NEW pairs + W dependent subtractions + divide + publish — no fence, no
 // matrix load.  Same arithmetic and order as k_gs_flow (bit-identical sweeps, tests/test_gpu_hpcg_mg.py).
 #define GSF_WARPS (GS_THREADS / 32)
+#define GS_SUB 32  // completion sub-counters per level (slice s of a level counts into s & 31): 1172 increments of ONE address per
+                   // level serialise in L2 (~27 cycles each = 17 us per level at 512^3); 32 addresses polled by the 32 lanes do not
 #define GSF_WARP_BYTES(W) ((size_t)(W) * 32 * (8 + 4 + 1))
 
 template <int W>
@@ -782,6 +791,8 @@ __global__ void __launch_bounds__(GS_THREADS, 2) k_gs_sell_flow(const GsSellArgs
       }
     }
     // ---- before the gate
+    long long tpre = 0;
+    if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) tpre = clock64();
     double bval = 0.0, xold = 0.0, d = 0.0;
     int nf = 0;
     if (row >= 0) {
@@ -828,21 +839,22 @@ __global__ void __launch_bounds__(GS_THREADS, 2) k_gs_sell_flow(const GsSellArgs
     {
       const int lev = a.slice_lev[g];
       const int glev = a.backward ? lev + 1 : lev - 1;
-      if (glev >= 0 && glev < a.nlev) {
-        if (lane == 0) {
-          const unsigned long long target = a.sweep * (unsigned long long)a.lev_n[glev];
-          long long t0 = 0;
-          while (gs_ld_relaxed(a.done + glev) < target) {
-            if (!t0) {
-              t0 = clock64();
-            } else if (clock64() - t0 > GS_SPIN_LIMIT) {
-              *a.err = 3;
-              break;
-            }
+      if (a.gate && glev >= 0 && glev < a.nlev) {
+        // lane l polls sub-counter l of the previous level (one coalesced 256-byte read per poll)
+        const unsigned long long target = a.sweep * (unsigned long long)a.lev_n[glev * GS_SUB + lane];
+        long long t0 = 0;
+        while (gs_ld_relaxed(a.done + glev * GS_SUB + lane) < target) {
+          if (!t0) {
+            t0 = clock64();
+          } else if (clock64() - t0 > GS_SPIN_LIMIT) {
+            *a.err = 3;
+            break;
           }
         }
         __syncwarp();
       }
+      long long tg = 0;
+      if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) tg = clock64();
       // ---- behind the gate: the NEW values
       for (int j0 = 0; j0 < nf; j0 += 7) {
         unsigned long long w0[7], w1[7];
@@ -886,7 +898,9 @@ __global__ void __launch_bounds__(GS_THREADS, 2) k_gs_sell_flow(const GsSellArgs
         gs_publish(a.xe + row, a.x + row, s, epoch, keep);
       }
       __syncwarp();
-      if (lane == 0) asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(a.done + lev) : "memory");
+      if (lane == 0 && a.gate) asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(a.done + lev * GS_SUB + (int)((g - a.lev_first[lev]) & (GS_SUB - 1))) : "memory");
+      if (a.trace && blockIdx.x == 0 && threadIdx.x == 0 && i < a.g0 + 40 * nw)
+        printf("gs-flow slice %lld lev %d nf %d: pre-gate+wait %lld post-gate %lld cycles\n", (long long)g, lev, nf, tg - tpre, clock64() - tg);
     }
   }
 }
@@ -965,6 +979,9 @@ static void gs_free_order(GsOrder *&o) {
   cudaFree(o->d_slice_lev);
   cudaFree(o->d_lev_n);
   cudaFree(o->d_done);
+  cudaFree(o->d_lev_first);
+  cudaFree(o->d_lev_tot);
+  cudaFree(o->d_done2);
   delete o;
   o = nullptr;
 }
@@ -1053,17 +1070,26 @@ static int gs_build_sell(pa_ctx *c, const MatPart &m, GsPart &p, const int32_t *
   {  // level of every slice, slices per level, completion counters (level-gated sweeps)
     const int64_t ng = o->npad / 32;
     std::vector<int32_t> sl((size_t)ng);
-    std::vector<uint32_t> ln((size_t)nlev);
+    std::vector<uint32_t> ln((size_t)nlev * GS_SUB, 0u), lt((size_t)nlev);
     for (int l = 0; l < nlev; ++l) {
-      ln[l] = (uint32_t)(o->lev_group[l + 1] - o->lev_group[l]);
-      for (int64_t q = o->lev_group[l]; q < o->lev_group[l + 1]; ++q) sl[(size_t)q] = l;
+      lt[l] = (uint32_t)(o->lev_group[l + 1] - o->lev_group[l]);
+      for (int64_t q = o->lev_group[l]; q < o->lev_group[l + 1]; ++q) {
+        sl[(size_t)q] = l;
+        ln[(size_t)l * GS_SUB + (size_t)((q - o->lev_group[l]) & (GS_SUB - 1))]++;
+      }
     }
     PA_CUDA(cudaMalloc((void **)&o->d_slice_lev, std::max<int64_t>(ng, 1) * sizeof(int32_t)));
-    PA_CUDA(cudaMalloc((void **)&o->d_lev_n, (size_t)nlev * sizeof(uint32_t)));
-    PA_CUDA(cudaMalloc((void **)&o->d_done, (size_t)nlev * sizeof(unsigned long long)));
+    PA_CUDA(cudaMalloc((void **)&o->d_lev_n, ln.size() * sizeof(uint32_t)));
+    PA_CUDA(cudaMalloc((void **)&o->d_done, ln.size() * sizeof(unsigned long long)));
+    PA_CUDA(cudaMalloc((void **)&o->d_lev_first, (size_t)(nlev + 1) * sizeof(int64_t)));
+    PA_CUDA(cudaMalloc((void **)&o->d_lev_tot, (size_t)nlev * sizeof(uint32_t)));
+    PA_CUDA(cudaMalloc((void **)&o->d_done2, (size_t)nlev * sizeof(unsigned long long)));
     PA_CUDA(cudaMemcpyAsync(o->d_slice_lev, sl.data(), (size_t)ng * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    PA_CUDA(cudaMemcpyAsync(o->d_lev_n, ln.data(), (size_t)nlev * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    PA_CUDA(cudaMemsetAsync(o->d_done, 0, (size_t)nlev * sizeof(unsigned long long), c->stream));
+    PA_CUDA(cudaMemcpyAsync(o->d_lev_n, ln.data(), ln.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    PA_CUDA(cudaMemcpyAsync(o->d_lev_first, o->lev_group.data(), (size_t)(nlev + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    PA_CUDA(cudaMemcpyAsync(o->d_lev_tot, lt.data(), (size_t)nlev * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    PA_CUDA(cudaMemsetAsync(o->d_done, 0, ln.size() * sizeof(unsigned long long), c->stream));
+    PA_CUDA(cudaMemsetAsync(o->d_done2, 0, (size_t)nlev * sizeof(unsigned long long), c->stream));
     PA_CUDA(cudaStreamSynchronize(c->stream));
   }
   PA_CUDA(cudaStreamSynchronize(c->stream));
@@ -1313,6 +1339,10 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
       a.done = nullptr;
       a.sweep = 0;
       a.nlev = o->nlev;
+      a.lev_first = nullptr;
+      a.gate = a.trace = 0;
+      a.lev_tot = nullptr;
+      a.done2 = nullptr;
       int nsm = 148;
       cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
       const int wpc = GS_THREADS / 32;
@@ -1338,7 +1368,13 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
         a.slice_lev = o->d_slice_lev;
         a.lev_n = o->d_lev_n;
         a.done = o->d_done;
-        a.sweep = mode == 1 ? 0 : ++o->sweeps;  // every gated sweep advances every level counter by its slice count, once
+        a.gate = (int)pa_knob(c, "gs_gate", 1);
+        a.trace = (int)pa_knob(c, "gs_trace", 0);
+        a.lev_first = o->d_lev_first;
+        a.lev_tot = o->d_lev_tot;
+        a.done2 = o->d_done2;
+        // every gated sweep advances every (sub-)counter by its slice count, once: the target is sweep number x count
+        a.sweep = mode == 3 ? (a.gate ? ++o->sweeps : 0) : (mode == 2 ? ++o->sweeps2 : 0);
         a.nlev = o->nlev;
         const size_t smem = mode == 3 ? GSF_WARPS * GSF_WARP_BYTES(o->W) : 0;
         if (smem) PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

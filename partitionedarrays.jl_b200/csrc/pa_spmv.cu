@@ -366,8 +366,8 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) xv[u] = __ldg(a.x + c[u]);
         } else if (MODE == 4) {  // a tile with ghost columns: the ghost slots were filled by this very kernel (and awaited above):
-#pragma unroll                  // weak loads (coherent after the acquire fence of the wait), never the read-only path
-          for (int u = 0; u < BATCH; ++u) asm volatile("ld.global.f64 %0, [%1];" : "=d"(xv[u]) : "l"(a.x + c[u]) : "memory");
+#pragma unroll                  // plain (weak) loads through the writable alias of x: coherent after the acquire fence of the wait, never
+          for (int u = 0; u < BATCH; ++u) xv[u] = a.xw[c[u]];  // the read-only (.nc) path; no asm barrier: the BATCH loads stay in flight together
         } else {  // boundary rows: ghost columns come from the owner's HBM over NVLink
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) {
