@@ -1248,13 +1248,17 @@ extern "C" int pa_gs_commit(pa_gs *g) {
       return PA_OK;
     };
     PA_TRY(padded_list(8, &p.d_rows, &p.npad));
-    // the sweep-ordered SELL copy of the default (wavefront) order; gs_kernel = 0 keeps the dataflow kernel on the CSR
-    if (gs_sell_ok(p, m, g->A->cols->parts[k].n_local) && pa_knob(c, "gs_kernel", 2) == 2) {
+    // gs_kernel = 2: sweep-ordered SELL copy of the wavefront order + thread-per-row kernels.  NOT the default: measured on
+    // B200 (27-pt 512^3, symmetric sweep) 76-99 ms against 58 ms of the warp-per-row dataflow kernel on the CSR — with one
+    // thread per row a lane collects its 13 NEW values itself (two dependent L2 round trips behind the gate, ~6500 cycles per
+    // level, profiles/r02_gs_sell_trace.log) where the dataflow kernel spreads them over 8 lanes that are already polling.
+    // The SELL copy is what the multi-colour order runs on (no waiting at all there: 27.8 ms).
+    if (gs_sell_ok(p, m, g->A->cols->parts[k].n_local) && pa_knob(c, "gs_kernel", 0) == 2) {
       PA_TRY(gs_build_sell(c, m, p, d_lev, d_lev2, d_rows1, cnt, p.nlev, &p.ord[0]));
     }
     // batch kernel tables (only when that kernel is selected: it is not the default): level l occupies
     // ceil(cnt_l / GSB_ROWS) consecutive batches
-    if (p.maxlen <= 32 && m.nnz > 0 && pa_knob(c, "gs_kernel", 2) == 1) {
+    if (p.maxlen <= 32 && m.nnz > 0 && pa_knob(c, "gs_kernel", 0) == 1) {
       const int64_t al = GSB_ROWS;
       PA_TRY(padded_list(al, &p.d_rows_b, &p.npad_b));
       std::vector<int32_t> batch_lev((size_t)(p.npad_b / al));
@@ -1317,7 +1321,7 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
     const MatPart &m = g->A->parts[k];
     if (p.n == 0) continue;
     p.epoch += 1;
-    GsOrder *o = g->order == PA_GS_MULTICOLOR ? p.ord[1] : (pa_knob(c, "gs_kernel", 2) == 2 ? p.ord[0] : nullptr);
+    GsOrder *o = g->order == PA_GS_MULTICOLOR ? p.ord[1] : (pa_knob(c, "gs_kernel", 0) == 2 ? p.ord[0] : nullptr);
     PA_CHECK(g->order != PA_GS_MULTICOLOR || o, PA_ESTATE, "gs_sweep: the multi-colour copy of the matrix is missing");
     if (o) {
       PA_CHECK(!(zero_guess && backward), PA_ESTATE, "gs_sweep: the zero-guess sweep is a forward sweep");
@@ -1414,7 +1418,7 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
       cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
       // batch kernel (32 rows of one level per warp) where the levels are wide; the warp-per-row dataflow kernel where
       // the sweep is bound by the level-to-level hop (coarse grids) or rows are longer than 32 entries
-      if (p.d_rows_b && pa_knob(c, "gs_kernel", 2) == 1) {
+      if (p.d_rows_b && pa_knob(c, "gs_kernel", 0) == 1) {
         const int nj = p.maxlen <= 8 ? 1 : (p.maxlen <= 16 ? 2 : 4);
         void (*wk)(const GsLevelArgs<PtrT>) = nullptr;
         PA_CHECK(!(zero_guess && backward), PA_ESTATE, "gs_sweep: the zero-guess sweep is a forward sweep");
