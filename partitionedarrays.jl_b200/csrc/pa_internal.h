@@ -87,7 +87,7 @@ struct pa_ctx {
   std::vector<char *> arena;      // per local part (device memory, cudaMalloc, IPC exportable)
   std::vector<char *> peer_base;  // per global part: arena base in this process' address space
   std::vector<bool> peer_ipc;
-  std::map<uint64_t, std::vector<uint64_t>> freelist;  // symmetric offsets by size
+  std::map<uint64_t, uint64_t> freeblocks;  // symmetric arena: free blocks (offset -> bytes), coalesced; first fit
   // reductions
   double *d_scal = nullptr;       // [PA_NSCAL]
   double *d_partial = nullptr;    // [nlocal]
@@ -209,6 +209,7 @@ void pa_mark_pending_done(pa_plan *plan);  // the neighbours' "done" for the cur
 int pa_before_write(pa_ctx *ctx);         // wait until nobody is still reading my vectors
 PeerPtrs pa_peer_ptrs(const pa_vec *v, int k);
 int pa_arena_alloc(pa_ctx *ctx, uint64_t bytes, uint64_t *off);  // symmetric offset (same sequence of calls on every process)
+void pa_arena_free(pa_ctx *ctx, uint64_t off, uint64_t bytes);
 int pa_reduce_finish(pa_ctx *ctx, double *d_out);  // sum local partials (+ NCCL all-reduce) into *d_out
 int pa_read_scalars(pa_ctx *ctx, int first, int count, double *out);  // synchronises
 int pa_check_device_error(pa_ctx *ctx);

@@ -159,7 +159,7 @@ extern "C" int pa_xchg_destroy(pa_xchg *x) {
   if (x->committed) {
     pa_before_write(c);  // the slot may be handed out again: every reader must be finished
     cudaStreamSynchronize(c->stream);
-    c->freelist[x->snd_bytes].push_back(x->snd_off);
+    pa_arena_free(c, x->snd_off, x->snd_bytes);
   }
   for (auto &p : x->parts) {
     cudaFree(p.d_rcv_ptrs);

@@ -2,16 +2,25 @@
 // reductions, and the consistent!/assemble! peer-pull kernels.
 // Reference: src/p_vector.jl:587-612 (assemble_impl!), :695-708 (assemble!), :747-755 (consistent!),
 // :800-821 (copy!/fill!), :1178-1206 (sum/dot/norm), :1194-1199 (rmul!), :1208-1277 (broadcast).
+#include <iterator>
+
 #include "pa_device.cuh"
 #include "pa_internal.h"
 
 // ------------------------------------------------------------------ symmetric arena
+// Deterministic first-fit allocator with coalescing: every process performs the same sequence of allocations and releases
+// (SPMD) with the same sizes (sizes derive from the job-wide symmetric lengths), so the offsets agree on all parts — the
+// NVSHMEM symmetric-heap rule — whatever mixture of vector sizes the caller creates and frees.
 int pa_arena_alloc(pa_ctx *c, uint64_t bytes, uint64_t *off) {
-  auto it = c->freelist.find(bytes);
-  if (it != c->freelist.end() && !it->second.empty()) {
-    *off = it->second.back();
-    it->second.pop_back();
-    return PA_OK;
+  for (auto it = c->freeblocks.begin(); it != c->freeblocks.end(); ++it) {
+    if (it->second >= bytes) {
+      *off = it->first;
+      const uint64_t rest = it->second - bytes;
+      const uint64_t at = it->first + bytes;
+      c->freeblocks.erase(it);
+      if (rest) c->freeblocks[at] = rest;
+      return PA_OK;
+    }
   }
   PA_CHECK(c->bump + bytes <= c->arena_bytes, PA_ENOMEM,
            "vector arena exhausted (%.2f GiB in use of %.2f GiB): pass a larger arena_bytes to pa_ctx_create",
@@ -19,6 +28,27 @@ int pa_arena_alloc(pa_ctx *c, uint64_t bytes, uint64_t *off) {
   *off = c->bump;
   c->bump += bytes;
   return PA_OK;
+}
+
+void pa_arena_free(pa_ctx *c, uint64_t off, uint64_t bytes) {
+  auto it = c->freeblocks.emplace(off, bytes).first;
+  auto nx = std::next(it);
+  if (nx != c->freeblocks.end() && it->first + it->second == nx->first) {  // merge with the block behind
+    it->second += nx->second;
+    c->freeblocks.erase(nx);
+  }
+  if (it != c->freeblocks.begin()) {  // merge with the block in front
+    auto pv = std::prev(it);
+    if (pv->first + pv->second == it->first) {
+      pv->second += it->second;
+      c->freeblocks.erase(it);
+      it = pv;
+    }
+  }
+  if (it->first + it->second == c->bump) {  // the top of the heap: give it back
+    c->bump = it->first;
+    c->freeblocks.erase(it);
+  }
 }
 
 extern "C" int pa_vec_create(pa_plan *plan, pa_vec **out) {
@@ -43,7 +73,7 @@ extern "C" int pa_vec_destroy(pa_vec *v) {
   // the slot may be handed out again: every earlier reader (local or remote) must be finished
   cudaSetDevice(c->device);
   pa_before_write(c);
-  c->freelist[v->plan->vec_bytes].push_back(v->offset);
+  pa_arena_free(c, v->offset, v->plan->vec_bytes);
   delete v;
   return PA_OK;
 }
