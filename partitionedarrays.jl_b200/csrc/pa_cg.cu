@@ -188,17 +188,25 @@ __global__ void __launch_bounds__(PA_RED_THREADS)
     pa_st_release_sys(xa.arrive_dst.p[threadIdx.x], e);
   }
   // ---- B: the bulk of the own entries (boundary entries are skipped)
-  for (int64_t j = tid * 2; j < n_own; j += nth * 2) {
-    const unsigned bits = xa.bitmap ? ((xa.bitmap[j >> 5] >> (j & 31)) & 3u) : 0u;  // j is even: both bits in one word
-    if (bits == 0u && j + 1 < n_own) {
-      double2 rv = *reinterpret_cast<const double2 *>(r + j), uv = *reinterpret_cast<double2 *>(u + j);
-      uv.x = __dadd_rn(__dmul_rn(1.0, rv.x), __dmul_rn(beta, uv.x));
-      uv.y = __dadd_rn(__dmul_rn(1.0, rv.y), __dmul_rn(beta, uv.y));
+  // (the loads do not wait for the bitmap word: r and u are read for every pair, only the STORE of a boundary entry is
+  // suppressed — a boundary entry of u read here may be the old or the new value, it is not used)
+  int64_t j = tid * 2;
+  for (; j + 1 < n_own; j += nth * 2) {
+    const unsigned bits = xa.bitmap ? ((__ldg(xa.bitmap + (j >> 5)) >> (j & 31)) & 3u) : 0u;  // j is even: both bits in one word
+    const double2 rv = *reinterpret_cast<const double2 *>(r + j);
+    double2 uv = *reinterpret_cast<double2 *>(u + j);
+    uv.x = __dadd_rn(__dmul_rn(1.0, rv.x), __dmul_rn(beta, uv.x));
+    uv.y = __dadd_rn(__dmul_rn(1.0, rv.y), __dmul_rn(beta, uv.y));
+    if (bits == 0u) {
       *reinterpret_cast<double2 *>(u + j) = uv;
     } else {
-      if (!(bits & 1u)) u[j] = __dadd_rn(__dmul_rn(1.0, r[j]), __dmul_rn(beta, u[j]));
-      if (j + 1 < n_own && !(bits & 2u)) u[j + 1] = __dadd_rn(__dmul_rn(1.0, r[j + 1]), __dmul_rn(beta, u[j + 1]));
+      if (!(bits & 1u)) u[j] = uv.x;
+      if (!(bits & 2u)) u[j + 1] = uv.y;
     }
+  }
+  if (j < n_own) {
+    const unsigned bit = xa.bitmap ? ((xa.bitmap[j >> 5] >> (j & 31)) & 1u) : 0u;
+    if (!bit) u[j] = __dadd_rn(__dmul_rn(1.0, r[j]), __dmul_rn(beta, u[j]));
   }
   // ---- C: the ghost values
   if ((int)threadIdx.x < xa.nnbr) pa_spin_until(xa.arrive_src.p[threadIdx.x], e, xa.err);

@@ -194,21 +194,21 @@ __device__ __forceinline__ void keep_live(const double (&x)[N]) {
   if (N >= 32) keep_live16(x + 16);
 }
 
-// MODE 4: wait until every CTA of this launch has stored its share of the ghost values (out of line: rare path).
-// The first thread of a CTA that gets here polls the global counter (relaxed loads, then ONE acquire fence: an
-// acquire load would invalidate the SM's L1 on every poll) and leaves a CTA-wide flag behind for the others.
-__device__ __noinline__ void spmv_wait_gather(const unsigned long long *arrive, unsigned long long target, int *cta_ready) {
-  int seen;
-  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(seen) : "r"((uint32_t)__cvta_generic_to_shared(cta_ready)) : "memory");
-  if (seen) return;
-  unsigned long long got;
-  const long long t0 = clock64();
-  for (;;) {
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(got) : "l"(arrive) : "memory");
-    if (got >= target || clock64() - t0 > 20000000000LL) break;  // (~10 s: never hang the GPU)
+// MODE 4: wait until every CTA of this launch has stored its share of the ghost values.  ONE thread per CTA polls the global
+// counter (relaxed loads, then one acquire fence; 150 000 threads polling one L2 line would starve the very atomics they wait
+// for) and the consumers meet at a named barrier — they reach a tile together anyway.
+__device__ __forceinline__ void spmv_wait_gather(const unsigned long long *arrive, unsigned long long target, int tid, int rows) {
+  if (tid == 0) {
+    unsigned long long got;
+    const long long t0 = clock64();
+    for (;;) {
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(got) : "l"(arrive) : "memory");
+      if (got >= target || clock64() - t0 > 20000000000LL) break;  // (~10 s: never hang the GPU)
+      __nanosleep(100);
+    }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
-  asm volatile("fence.acq_rel.gpu;" ::: "memory");
-  asm volatile("st.release.cta.shared.s32 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(cta_ready)) : "memory");
+  asm volatile("bar.sync 2, %0;" ::"r"(rows) : "memory");
 }
 
 // minBlocksPerSM is stated explicitly: with maxThreads alone ptxas squeezes the kernel into 32 registers
@@ -233,9 +233,7 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
   uint64_t *empty = full + S;
   const int tid = threadIdx.x;
   __shared__ unsigned long long gather_target;
-  __shared__ int gather_seen;  // MODE 4: some thread of this CTA has seen the gather complete
   if (tid == 0) {
-    gather_seen = 0;
     for (int s = 0; s < S; ++s) {
       mbar_init(full + s, 1);
       mbar_init(empty + s, ROWS);
@@ -330,7 +328,7 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
     // coherent path; every other tile runs the instruction stream of MODE 0
     const bool gt = MODE == 4 && a.tile_ghost[t] != 0;
     if (MODE == 4 && gt && !ghosts_ready) {
-      spmv_wait_gather(a.arrive, gather_target, &gather_seen);
+      spmv_wait_gather(a.arrive, gather_target, tid, ROWS);
       ghosts_ready = true;
     }
     mbar_wait(full + s, (uint32_t)((j / S) & 1));
