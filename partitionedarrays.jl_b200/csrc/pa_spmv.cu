@@ -355,17 +355,20 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) ghost |= c[u] >= a.n_own_cols;
         }
-        if (MODE == 4) ghost = gt;
         if (MODE == 2) {  // own block only: ghost columns are skipped here and added, in order, by k_spmv_ghost_rows
           const int32_t last_own = (int32_t)a.n_own_cols - 1;
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) xv[u] = __ldg(a.x + min(c[u], last_own));
+        } else if (MODE == 4) {
+          // every tile reads x with plain (weak) loads through the writable alias — never the read-only (.nc) path: the ghost
+          // slots are written by this very kernel.  Tiles that hold a ghost column have waited above (acquire fence: the SM's
+          // L1 is invalidated after the last gather store), the others never touch a ghost slot.  No branch per batch: the
+          // instruction stream is that of MODE 0 (a per-batch test cost 9.6 % more instructions = 8.6 % more time, ncu).
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u) xv[u] = a.xw[c[u]];
         } else if (MODE == 0 || !ghost) {  // straight-line: all BATCH gathers are in flight together
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) xv[u] = __ldg(a.x + c[u]);
-        } else if (MODE == 4) {  // a tile with ghost columns: the ghost slots were filled by this very kernel (and awaited above):
-#pragma unroll                  // plain (weak) loads through the writable alias of x: coherent after the acquire fence of the wait, never
-          for (int u = 0; u < BATCH; ++u) xv[u] = a.xw[c[u]];  // the read-only (.nc) path; no asm barrier: the BATCH loads stay in flight together
         } else {  // boundary rows: ghost columns come from the owner's HBM over NVLink
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) {
