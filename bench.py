@@ -12,7 +12,9 @@ A "step" is one ref_cg!(x,A,b; maxiter=ITERS, Pl=Identity) call (HPCG/src/ref_cg
   value  = HPCG-model GFLOP/s of the CG loop, whole job, operands resident in HBM
            ((2*nnz + 12*n) flop per iteration — HPCG/src/report_results.jl:27-29 — x iterations / time)
   e2e    = same metric through the public API with HOST buffers: every step uploads b from pinned host memory, sets
-           x0 = 0 (fill!), solves, and downloads x and the residual history inside the timed region
+           x0 = 0 (fill!), solves, and downloads x and the residual history inside the timed region; the transfers of
+           neighbouring steps overlap with the running solve (two buffer pairs, copy streams); the strictly serial
+           upload -> solve -> download figure is printed beside it (e2e.serial_value)
   roofline = the SpMV kernel (dominant): algorithmic bytes / CUDA-event time vs measured HBM peak
   cpu_baseline = the CPU oracle (C twin of the reference loops, one part per host thread) on a bounded sample
 Secondary sections (same JSON line): hpcg27 (27-pt 512^3 per GPU: SpMV, CG, 4-level MG-preconditioned CG — configs[3],
@@ -384,7 +386,7 @@ def run_ours(args):
     gn = (n, n, n) if args.strong else (n * shape[0], n * shape[1], n * shape[2])  # --strong: fixed global grid
     stream = torch.cuda.Stream()
     vec_bytes = (n + 2) ** 3 * 8
-    backend = pa.CUDAArray(N, mode="distributed" if world > 1 else "sequential", device=local_rank, arena_bytes=10 * vec_bytes + (64 << 20),
+    backend = pa.CUDAArray(N, mode="distributed" if world > 1 else "sequential", device=local_rank, arena_bytes=14 * vec_bytes + (64 << 20),
                            stream=stream.cuda_stream, group=meta)
 
     def barrier():
@@ -482,24 +484,61 @@ def run_ours(args):
     ms_ref_ops, w = timed(lambda: step_resident(pa.PA_CG_REFERENCE_OPS))
     windows.append(w)
 
-    # --- e2e: host buffers in, host buffers out, every step (b uploaded from pinned memory, x0 = 0 set on the device —
-    # the caller's x0 is the zero vector —, x and the residual history downloaded)
-    hb = torch.empty(n_local, dtype=torch.float64).pin_memory()
-    hx = torch.empty(n_local, dtype=torch.float64).pin_memory()
-    hb.numpy()[:] = b.local_values()[0]
-    def step_e2e():
-        pa._capi.check(L.pa_vec_upload(b.h, 0, hb.data_ptr(), n_local))
+    # --- e2e: host buffers in, host buffers out, every step: b uploaded from pinned host memory, x0 = 0 set on the device (the
+    # caller's x0 is the zero vector), x and the residual history downloaded.  Serial: upload -> solve -> download, one after
+    # the other.  Pipelined (the headline e2e): two (x, b) buffer pairs; the upload of the NEXT right-hand side and the
+    # download of the PREVIOUS solution run on their own copy streams while the current solve occupies the SMs (PCIe is full
+    # duplex); every step's copies still happen inside the timed region, the last download included.
+    hbuf = [(torch.empty(n_local, dtype=torch.float64).pin_memory(), torch.empty(n_local, dtype=torch.float64).pin_memory()) for _ in range(2)]
+    for hb_, _ in hbuf:
+        hb_.numpy()[:] = b.local_values()[0]
+    def step_e2e_serial():
+        hb_, hx_ = hbuf[0]
+        pa._capi.check(L.pa_vec_upload(b.h, 0, hb_.data_ptr(), n_local))
         x.fill_(0.0)
         r = pa.ref_cg_(x, A, b, tolerance=0.0, maxiter=args.iters)
-        pa._capi.check(L.pa_vec_download(x.h, 0, hx.data_ptr(), n_local))
+        pa._capi.check(L.pa_vec_download(x.h, 0, hx_.data_ptr(), n_local))
         return r
-    step_e2e()
-    ms_e2e, w = timed(lambda: [step_e2e() for _ in range(args.steps)])
+    step_e2e_serial()
+    ms_e2e_serial, w = timed(lambda: [step_e2e_serial() for _ in range(args.steps)])
     windows.append(w)
+    err = float(np.abs(hbuf[0][1].numpy()[:n_rows] - 1.0).max())
+    x2, b2 = pa.pzeros(A.cols), pa.PVector(A.cols)
+    pairs = [(x, b), (x2, b2)]
+    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+    def e2e_pipelined(K):
+        ev_up, ev_down = [None, None], [None, None]
+        def upload(sidx):
+            q = sidx % 2
+            pa._capi.check(L.pa_vec_upload_async(pairs[q][1].h, 0, hbuf[q][0].data_ptr(), n_local, s_h2d.cuda_stream))
+            ev_up[q] = torch.cuda.Event(); ev_up[q].record(s_h2d)
+        s_h2d.wait_stream(stream)  # the buffers are idle: everything enqueued so far has to finish first
+        s_d2h.wait_stream(stream)
+        upload(0)
+        for sidx in range(K):
+            q = sidx % 2
+            if sidx + 1 < K:
+                upload(sidx + 1)  # b of the other pair: its last reader (solve sidx-1) has returned; overlaps with the solve below
+            stream.wait_event(ev_up[q])
+            if ev_down[q] is not None:
+                stream.wait_event(ev_down[q])  # x of this pair is free again once its previous solution has been read out
+            pairs[q][0].fill_(0.0)
+            pa.ref_cg_(pairs[q][0], A, pairs[q][1], tolerance=0.0, maxiter=args.iters)  # returns when the solve is complete
+            pa._capi.check(L.pa_vec_download_async(pairs[q][0].h, 0, hbuf[q][1].data_ptr(), n_local, s_d2h.cuda_stream))
+            ev_down[q] = torch.cuda.Event(); ev_down[q].record(s_d2h)
+        stream.wait_stream(s_d2h)  # the last solution has to be on the host inside the timed region
+        stream.wait_stream(s_h2d)
+    e2e_pipelined(2)
+    ms_e2e, w = timed(lambda: e2e_pipelined(args.steps))
+    windows.append(w)
+    torch.cuda.synchronize()
+    err = max(err, float(np.abs(hbuf[(args.steps - 1) % 2][1].numpy()[:n_rows] - 1.0).max()))
     e2e_value = flops_iter * args.iters / (ms_e2e / args.steps * 1e-3) / 1e9
+    e2e_serial_value = flops_iter * args.iters / (ms_e2e_serial / args.steps * 1e-3) / 1e9
     h2d, d2h = n_local * 8, n_local * 8 + (args.iters + 1) * 8
-    err = float(np.abs(hx.numpy()[:n_rows] - 1.0).max())
-    del hb, hx
+    for v in (x2, b2):
+        v.free()
+    del hbuf
 
     extra = {"reference_ops": {"cg_iters_per_sec": args.iters / (ms_ref_ops * 1e-3), "gflops": flops_iter * args.iters / ms_ref_ops / 1e6,
                                "note": "PA_CG_REFERENCE_OPS: one kernel per operation of ref_cg.jl:46-67 (3 reductions, 8 passes); the headline is the fused "
@@ -582,7 +621,9 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_spmv_tma", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": B, "traffic": traffic, "traffic_source": traffic_src,
                          "cg_iter_bytes_model": B + 120 * n_rows, "cg_frac_of_peak": (B + 120 * n_rows) * args.iters / (ms_step * 1e-3) / 1e9 / peak},
-            "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                    "schedule": "pipelined: upload of the next b and download of the previous x on copy streams, overlapped with the running solve",
+                    "serial_value": e2e_serial_value, "serial_ms_per_step": ms_e2e_serial / args.steps},
             "gpu_launches": int(launches), "launches_per_cg_iteration": launches / (args.steps * args.iters), "spmv_region_launches": int(spmv_launches),
             "clocks": clocks, "cpu_baseline": cpu,
         }

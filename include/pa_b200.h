@@ -111,6 +111,11 @@ int pa_vec_destroy(pa_vec *v);
 int pa_vec_upload(pa_vec *v, int32_t k, const double *host, int64_t n);
 /* host <- local_values(v)[k]; synchronises. */
 int pa_vec_download(const pa_vec *v, int32_t k, double *host, int64_t n);
+/* The same copies on a caller-chosen stream (pinned host memory; returns at once): lets a caller overlap the upload of the next
+ * right-hand side and the download of the previous solution with the running solve.  The caller orders them against the
+ * context's stream with events; the vector must not take part in an exchange that is in flight. */
+int pa_vec_upload_async(pa_vec *v, int32_t k, const double *host_pinned, int64_t n, void *stream);
+int pa_vec_download_async(const pa_vec *v, int32_t k, double *host_pinned, int64_t n, void *stream);
 /* fill!(v,a) (src/p_vector.jl:816-821), copy!(dst,src) (:800-814), rmul!(v,a) (:1194-1199) —
  * all local entries (own and ghost). */
 int pa_vec_fill(pa_vec *v, double a);

@@ -56,6 +56,8 @@ SIGNATURES = {
     "pa_vec_destroy": [_P],
     "pa_vec_upload": [_P, _I32, _P, _I64],
     "pa_vec_download": [_P, _I32, _P, _I64],
+    "pa_vec_upload_async": [_P, _I32, _P, _I64, _P],
+    "pa_vec_download_async": [_P, _I32, _P, _I64, _P],
     "pa_vec_fill": [_P, _D],
     "pa_vec_copy": [_P, _P],
     "pa_vec_scale": [_P, _D],

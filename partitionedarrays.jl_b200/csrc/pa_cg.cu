@@ -342,8 +342,18 @@ static int cg_get_work(pa_ctx *c, pa_mat *A, pa_vec *x, const pa_vec *b, int max
   for (CgWork *q : c->cg_work)
     if (q->a_uid == A->uid && q->x_uid == x->uid && q->b_uid == b->uid && q->plan == x->plan) w = q;
   if (!w) {
-    // one workspace per matrix: a solve with other vectors replaces it (the arena holds 3 vectors per workspace)
-    pa_cg_drop_work(c, A, nullptr, false);
+    // at most two workspaces per matrix (a caller that alternates between two (x, b) pairs to overlap transfers with solves
+    // keeps both graphs); a third pair replaces the older one — the arena holds 3 vectors per workspace
+    int cnt = 0;
+    for (CgWork *q : c->cg_work) cnt += q->a_uid == A->uid;
+    if (cnt >= 2) {
+      for (size_t i = 0; i < c->cg_work.size(); ++i)
+        if (c->cg_work[i]->a_uid == A->uid) {
+          cg_free_work(c->cg_work[i]);
+          c->cg_work.erase(c->cg_work.begin() + i);
+          break;
+        }
+    }
     w = new CgWork();
     w->a_uid = A->uid;
     w->x_uid = x->uid;

@@ -108,6 +108,26 @@ extern "C" int pa_vec_download(const pa_vec *v, int32_t k, double *host, int64_t
   return pa_check_device_error(c);
 }
 
+/* Copies on a caller-chosen stream (pinned host memory), for pipelines that overlap the transfer of the NEXT right-hand side
+ * and of the PREVIOUS solution with the running solve.  No ordering is added here: the caller orders the copy against the
+ * context's stream with events (the vector must not take part in an exchange that is in flight). */
+extern "C" int pa_vec_upload_async(pa_vec *v, int32_t k, const double *host, int64_t n, void *stream) {
+  PA_CHECK(v && host && stream, PA_EINVAL, "pa_vec_upload_async: null argument");
+  pa_ctx *c = v->plan->ctx;
+  PA_CHECK(k >= 0 && k < c->nlocal && n == v->plan->parts[k].n_local, PA_EINVAL, "pa_vec_upload_async: length mismatch");
+  PA_CUDA(cudaSetDevice(c->device));
+  PA_CUDA(cudaMemcpyAsync(v->d[k], host, n * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return PA_OK;
+}
+extern "C" int pa_vec_download_async(const pa_vec *v, int32_t k, double *host, int64_t n, void *stream) {
+  PA_CHECK(v && host && stream, PA_EINVAL, "pa_vec_download_async: null argument");
+  pa_ctx *c = v->plan->ctx;
+  PA_CHECK(k >= 0 && k < c->nlocal && n == v->plan->parts[k].n_local, PA_EINVAL, "pa_vec_download_async: length mismatch");
+  PA_CUDA(cudaSetDevice(c->device));
+  PA_CUDA(cudaMemcpyAsync(host, v->d[k], n * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return PA_OK;
+}
+
 // ------------------------------------------------------------------ elementwise kernels
 // All updates are written as separate IEEE multiply and add (no FMA contraction) so that they are
 // bit-identical to the reference's Julia broadcasts (a.*x .+ b.*y evaluates mul, mul, add).
