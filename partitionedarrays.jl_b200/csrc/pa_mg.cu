@@ -24,6 +24,9 @@
 #ifndef GS_MINB8
 #define GS_MINB8 4  // resident CTAs per SM of the 8-lanes-per-row kernel: 64 registers (4 bytes of spill); 3 CTAs = 76 registers
 #endif
+#ifndef GS_COLOR_MINB
+#define GS_COLOR_MINB 4  // resident CTAs per SM of the multi-colour kernel (64 registers)
+#endif
 #define GS_SPIN_LIMIT (20000000000LL)  // ~10 s of SM cycles, then give up and flag an error instead of hanging
 
 struct GsPart {
@@ -625,7 +628,7 @@ struct GsSellArgs {
 //         stored; one lane per warp polls one hot line, the other lanes cost nothing while they wait, and the NEW values
 //         are then simply what x holds (no per-row flags, no 16-byte pairs)
 template <int W, int MODE>
-__global__ void __launch_bounds__(GS_THREADS, (MODE == 1 ? 2 : 3)) k_gs_sell(const GsSellArgs a) {
+__global__ void __launch_bounds__(GS_THREADS, (MODE == 1 ? 2 : (MODE == 0 ? GS_COLOR_MINB : 3))) k_gs_sell(const GsSellArgs a) {
   constexpr bool SYNC = MODE == 1;
   constexpr int B = W == 27 ? 9 : (W == 7 ? 7 : 8);  // slots per batch: loads of a batch are in flight together
   const int WD = W ? W : a.W;

@@ -364,8 +364,11 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
           // slots are written by this very kernel.  Tiles that hold a ghost column have waited above (acquire fence: the SM's
           // L1 is invalidated after the last gather store), the others never touch a ghost slot.  No branch per batch: the
           // instruction stream is that of MODE 0 (a per-batch test cost 9.6 % more instructions = 8.6 % more time, ncu).
+          // (a non-volatile asm without memory clobber: the compiler schedules it like __ldg — with the C++ load through the
+          // writable alias it gave up the 128-bit shared-memory reads of the row, 2688 instead of 1600 SASS instructions; the
+          // load cannot move above the wait: its address comes from the tile, which is read behind the mbarrier wait)
 #pragma unroll
-          for (int u = 0; u < BATCH; ++u) xv[u] = a.xw[c[u]];
+          for (int u = 0; u < BATCH; ++u) asm("ld.global.f64 %0, [%1];" : "=d"(xv[u]) : "l"(a.x + c[u]));
         } else if (MODE == 0 || !ghost) {  // straight-line: all BATCH gathers are in flight together
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) xv[u] = __ldg(a.x + c[u]);
