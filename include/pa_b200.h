@@ -175,7 +175,9 @@ int pa_vec_fill_hash_box(pa_vec *v, int32_t k, const int64_t *gn, const int64_t 
 
 /* ------------------------------------------------------------------ PSparseMatrix -----------
  * PSparseMatrix (src/p_sparse_matrix.jl:971-991).  Row plan / column plan = partition(axes(A,1)),
- * partition(axes(A,2)).  Only assembled matrices (ghost-row blocks empty, :1704-1705). */
+ * partition(axes(A,2)).  A part stores either its own rows only (assembled matrices: the ghost-row blocks are empty,
+ * :1704-1705) or ALL local rows of an own-first row partition (sub-assembled matrices, psparse(...; assemble=false)): mul!
+ * then multiplies own and ghost rows and finishes with assemble!(c) (:2109-2142). */
 int pa_mat_create(pa_plan *rows, pa_plan *cols, pa_mat **out);
 int pa_mat_destroy(pa_mat *A);
 /* Unsplit local CSR, the HPCG layout (HPCG/src/sparse_matrix.jl:115-121): n_own_rows x n_local_cols,
@@ -216,6 +218,8 @@ int pa_mat_set_stencil(pa_mat *A, int32_t k, int32_t kind, const int64_t *gn, co
                        const int32_t *ghost_id_of_sorted, pa_vec *rhs);
 int pa_mat_commit(pa_mat *A);
 int pa_mat_nnz(const pa_mat *A, int32_t k, int64_t *out);
+/* stored rows of part k: the own rows, or all local rows for a sub-assembled matrix */
+int pa_mat_nrows(const pa_mat *A, int32_t k, int64_t *out);
 /* Copy the device CSR of part k back (0-based, int64 rowptr; any pointer may be NULL). */
 int pa_mat_download_csr(const pa_mat *A, int32_t k, int64_t *rowptr, int32_t *colval, double *nzval);
 /* LinearAlgebra.fillstored!(A,a) (used by test/p_sparse_matrix_tests.jl:285). */
@@ -251,6 +255,16 @@ int pa_spmv(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, uint32_t
  * axes(A,2): c_own = beta*c_own + alpha*A_oo^T b_own + the ghost contributions alpha*A_oh^T b_own shipped to their owners
  * by assemble!; c's ghost entries are zero on return.  The local transposes are built once on the device. */
 int pa_spmv_transpose(pa_mat *A, pa_vec *b, pa_vec *c, double alpha, double beta);
+
+/* Sparse x sparse products (spmm / spmtm / rap, src/p_sparse_matrix.jl:2212-2307; what AMG needs).
+ * pa_mat_spmm_local: D_k = A_k * C_k for every local part on the device (expand - stable sort - in-order compression: sums
+ * in ascending local k, one rounding per product and per addition).  C holds one row per LOCAL column of A: the own rows of
+ * B followed by the rows of B that A's ghost columns refer to (C = consistent(B, axes(A,2)), :2243; built by the host mirror
+ * with exchange!).  D: created on (axes(A,1), axes(C,2)), not committed.
+ * pa_mat_transpose_local: T_k = (A_k)^T as a matrix on (axes(A,2), axes(A,1)) — with pa_mat_spmm_local(T, B, D) the local
+ * product of spmtm (transpose(A)*B, :2276-2290), whose ghost rows then travel to their owners (assemble). */
+int pa_mat_spmm_local(pa_mat *A, pa_mat *C, pa_mat *D);
+int pa_mat_transpose_local(pa_mat *A, pa_mat *T);
 
 typedef struct {
   int32_t iters;

@@ -89,8 +89,11 @@ SIGNATURES = {
     "pa_mat_set_stencil": [_P, _I32, _I32, _P, _P, _P, _I64, _P, _P, _P],
     "pa_mat_commit": [_P],
     "pa_mat_nnz": [_P, _I32, _P],
+    "pa_mat_nrows": [_P, _I32, _P],
     "pa_mat_download_csr": [_P, _I32, _P, _P, _P],
     "pa_mat_fill_stored": [_P, _D],
+    "pa_mat_spmm_local": [_P, _P, _P],
+    "pa_mat_transpose_local": [_P, _P],
     "pa_spmv": [_P, _P, _P, _D, _D, _U32],
     "pa_spmv_transpose": [_P, _P, _P, _D, _D],
     "pa_cg": [_P, _P, _P, _I32, _D, _U32, _P, _P],

@@ -50,7 +50,7 @@ __global__ void k_coo_sum(const double *V, const int32_t *perm, const unsigned c
     double acc = 0.0;
     for (int64_t s = a; s < b; ++s) {
       const int32_t p = perm[s];
-      if (valid[p]) acc = __dadd_rn(acc, V[p]);  // A_nz[k] += v, input order
+      if (!valid || valid[p]) acc = __dadd_rn(acc, V[p]);  // A_nz[k] += v, input order
     }
     nz[u] = acc;
   }
@@ -307,4 +307,164 @@ extern "C" int pa_spmv_transpose(pa_mat *A, pa_vec *b, pa_vec *cvec, double alph
   // c_local = beta*c_local + alpha * A_local^T b_own (ghost rows start from zero)
   PA_TRY(pa_spmv_local(A->T, b, cvec, alpha, beta, 0, nullptr, nullptr));
   return pa_vec_assemble(cvec);
+}
+
+
+// ------------------------------------------------------------------ local sparse x sparse product (spmm / spmtm / rap)
+// D_k = A_k * C_k on the device for every local part (src/p_sparse_matrix.jl:2237-2262: `spmm(partition(A), partition(C))` after
+// C = consistent(B, axes(A,2)) brought the rows of B that A's ghost columns refer to).  A_k: rows of part k x local columns of
+// axes(A,2); C_k: one row per LOCAL column of A (own rows of B first, then the fetched ghost rows) x local columns of C.
+// Expand - sort - compress: every product a_ik * c_kj becomes a triplet (i, j, a*c), generated row by row of A with k in the
+// stored (ascending local id) order; a stable radix sort by (i, j) keeps that order inside every output entry, and one thread
+// per output entry adds its products in that order — the order of a Gustavson product over the local matrices (and of
+// SparseArrays' CSC product: ascending k), with one rounding per product and per addition, no FMA.
+__device__ __forceinline__ int64_t rp_at(const void *rp, int is64, int64_t i) {
+  return is64 ? reinterpret_cast<const int64_t *>(rp)[i] : (int64_t)reinterpret_cast<const int32_t *>(rp)[i];
+}
+__global__ void k_spgemm_count(const int32_t *colA, int64_t nnzA, const void *rpC, int c64, int64_t *cnt) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p <= nnzA; p += (int64_t)gridDim.x * blockDim.x)
+    cnt[p] = p < nnzA ? rp_at(rpC, c64, colA[p] + 1) - rp_at(rpC, c64, colA[p]) : 0;
+}
+__global__ void k_spgemm_expand(const int32_t *rowidxA, const int32_t *colA, const double *nzA, int64_t nnzA, const int64_t *off, const void *rpC,
+                                int c64, const int32_t *colC, const double *nzC, uint64_t *key, int32_t *pos, double *val) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnzA; p += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t hi = ((uint64_t)(uint32_t)rowidxA[p]) << 32;
+    const double a = nzA[p];
+    int64_t o = off[p];
+    for (int64_t q = rp_at(rpC, c64, colA[p]); q < rp_at(rpC, c64, colA[p] + 1); ++q, ++o) {
+      key[o] = hi | (uint64_t)(uint32_t)colC[q];
+      val[o] = __dmul_rn(a, nzC[q]);
+      pos[o] = (int32_t)o;
+    }
+  }
+}
+
+/* D = A * C, part by part (see above).  D: created on (axes(A,1), axes(C,2)), not committed; C must hold one row per local
+ * column of A.  Entries of D are sorted by column inside every row; explicit zeros are kept (like the reference's product). */
+extern "C" int pa_mat_spmm_local(pa_mat *A, pa_mat *C, pa_mat *D) {
+  PA_CHECK(A && C && D && A->committed && C->committed && !D->committed, PA_ESTATE, "pa_mat_spmm_local: A and C must be committed, D must not");
+  pa_ctx *c = A->ctx;
+  PA_CHECK(C->ctx == c && D->ctx == c, PA_EINVAL, "pa_mat_spmm_local: matrices live on different backends");
+  PA_CUDA(cudaSetDevice(c->device));
+  const int g = 148 * 8;
+  for (int k = 0; k < c->nlocal; ++k) {
+    const MatPart &a = A->parts[k], &cm = C->parts[k];
+    MatPart &d = D->parts[k];
+    PA_CHECK(cm.nrows == a.ncols, PA_EINVAL, "pa_mat_spmm_local: part %d: C has %lld rows, A has %lld local columns", c->part_ids[k] + 1,
+             (long long)cm.nrows, (long long)a.ncols);
+    PA_CHECK(D->rows->parts[k].n_own == a.nrows || (D->rows->parts[k].prefix && D->rows->parts[k].n_local == a.nrows), PA_EINVAL,
+             "pa_mat_spmm_local: D's row partition does not match A's rows");
+    PA_CHECK(D->cols->parts[k].n_local == cm.ncols && D->cols->parts[k].prefix, PA_EINVAL, "pa_mat_spmm_local: D's column partition does not match C's");
+    PA_CHECK(a.nnz < (1ll << 31), PA_EINVAL, "pa_mat_spmm_local: A too large");
+    cudaFree(d.d_rowptr); cudaFree(d.d_colval); cudaFree(d.d_nzval);
+    d = MatPart();
+    d.nrows = a.nrows;
+    d.ncols = cm.ncols;
+    if (a.nrows != D->rows->parts[k].n_own) D->subassembled = true;
+    int64_t *d_cnt = nullptr, *d_off = nullptr, *d_rowcount = nullptr, *d_rp64 = nullptr;
+    int32_t *rowidx = nullptr, *epos = nullptr;
+    const int64_t na = std::max<int64_t>(a.nnz, 1);
+    PA_CUDA(cudaMalloc((void **)&d_cnt, (na + 1) * 8));
+    PA_CUDA(cudaMalloc((void **)&d_off, (na + 1) * 8));
+    PA_CUDA(cudaMalloc((void **)&rowidx, na * 4));
+    PA_CUDA(cudaMalloc((void **)&epos, na * 4));
+    PA_CUDA(cudaMalloc((void **)&d_rowcount, (a.nrows + 1) * 8));
+    PA_CUDA(cudaMalloc((void **)&d_rp64, (a.nrows + 1) * 8));
+    PA_CUDA(cudaMemsetAsync(d_rowcount, 0, (a.nrows + 1) * 8, c->stream));
+    int64_t T = 0, nuniq = 0;
+    if (a.nnz) {
+      k_row_of_entry<<<g, 256, 0, c->stream>>>(a.ptr64 ? nullptr : (const int32_t *)a.d_rowptr, a.ptr64 ? (const int64_t *)a.d_rowptr : nullptr, a.nrows, rowidx, epos);
+      k_spgemm_count<<<g, 256, 0, c->stream>>>(a.d_colval, a.nnz, cm.d_rowptr, cm.ptr64 ? 1 : 0, d_cnt);
+      size_t tb = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tb, d_cnt, d_off, (int)(a.nnz + 1), c->stream);
+      void *tmp = nullptr;
+      PA_CUDA(cudaMalloc(&tmp, tb ? tb : 1));
+      PA_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, d_cnt, d_off, (int)(a.nnz + 1), c->stream));
+      PA_CUDA(cudaMemcpyAsync(&T, d_off + a.nnz, 8, cudaMemcpyDeviceToHost, c->stream));
+      PA_CUDA(cudaStreamSynchronize(c->stream));
+      cudaFree(tmp);
+      c->launches += 3;
+    }
+    PA_CHECK(T < (1ll << 31), PA_EINVAL, "pa_mat_spmm_local: %lld products in part %d: too many for one pass", (long long)T, c->part_ids[k] + 1);
+    if (T) {
+      uint64_t *key = nullptr, *key2 = nullptr;
+      int32_t *pos = nullptr, *perm = nullptr, *head = nullptr, *incl = nullptr, *seg = nullptr;
+      double *val = nullptr;
+      PA_CUDA(cudaMalloc((void **)&key, T * 8)); PA_CUDA(cudaMalloc((void **)&key2, T * 8)); PA_CUDA(cudaMalloc((void **)&val, T * 8));
+      PA_CUDA(cudaMalloc((void **)&pos, T * 4)); PA_CUDA(cudaMalloc((void **)&perm, T * 4));
+      PA_CUDA(cudaMalloc((void **)&head, T * 4)); PA_CUDA(cudaMalloc((void **)&incl, T * 4));
+      k_spgemm_expand<<<g, 256, 0, c->stream>>>(rowidx, a.d_colval, a.d_nzval, a.nnz, d_off, cm.d_rowptr, cm.ptr64 ? 1 : 0, cm.d_colval, cm.d_nzval, key, pos, val);
+      size_t tb = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tb, key, key2, pos, perm, (int)T, 0, 64, c->stream);
+      void *tmp = nullptr;
+      PA_CUDA(cudaMalloc(&tmp, tb ? tb : 1));
+      PA_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, key, key2, pos, perm, (int)T, 0, 64, c->stream));  // stable
+      k_coo_heads<<<g, 256, 0, c->stream>>>(key2, T, head);
+      size_t tb2 = 0;
+      cub::DeviceScan::InclusiveSum(nullptr, tb2, head, incl, (int)T, c->stream);
+      void *tmp2 = nullptr;
+      PA_CUDA(cudaMalloc(&tmp2, tb2 ? tb2 : 1));
+      PA_CUDA(cub::DeviceScan::InclusiveSum(tmp2, tb2, head, incl, (int)T, c->stream));
+      int32_t last = 0;
+      PA_CUDA(cudaMemcpyAsync(&last, incl + T - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+      PA_CUDA(cudaStreamSynchronize(c->stream));
+      nuniq = last;
+      PA_CUDA(cudaMalloc((void **)&d.d_colval, (nuniq + PA_MAT_PAD) * 4));
+      PA_CUDA(cudaMalloc((void **)&d.d_nzval, (nuniq + PA_MAT_PAD) * 8));
+      PA_CUDA(cudaMalloc((void **)&seg, (nuniq + 1) * 4));
+      k_coo_unique<<<g, 256, 0, c->stream>>>(key2, head, incl, T, d.d_colval, seg, d_rowcount);
+      k_coo_sum<<<g, 256, 0, c->stream>>>(val, perm, nullptr, seg, nuniq, T, d.d_nzval);
+      PA_CUDA(cudaStreamSynchronize(c->stream));
+      cudaFree(tmp); cudaFree(tmp2); cudaFree(key); cudaFree(key2); cudaFree(val); cudaFree(pos); cudaFree(perm); cudaFree(head); cudaFree(incl); cudaFree(seg);
+      c->launches += 6;
+    } else {
+      PA_CUDA(cudaMalloc((void **)&d.d_colval, 16 * 4));
+      PA_CUDA(cudaMalloc((void **)&d.d_nzval, 16 * 8));
+    }
+    size_t tb3 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb3, d_rowcount, d_rp64, (int)(a.nrows + 1), c->stream);
+    void *tmp3 = nullptr;
+    PA_CUDA(cudaMalloc(&tmp3, tb3 ? tb3 : 1));
+    PA_CUDA(cub::DeviceScan::ExclusiveSum(tmp3, tb3, d_rowcount, d_rp64, (int)(a.nrows + 1), c->stream));
+    PA_CUDA(cudaMalloc(&d.d_rowptr, (a.nrows + 1) * sizeof(int32_t)));
+    k_narrow64<<<148, 256, 0, c->stream>>>(d_rp64, (int32_t *)d.d_rowptr, a.nrows + 1);
+    PA_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(tmp3); cudaFree(d_cnt); cudaFree(d_off); cudaFree(rowidx); cudaFree(epos); cudaFree(d_rowcount); cudaFree(d_rp64);
+    d.nnz = nuniq;
+    d.ptr64 = false;
+    d.rows_per_cta = nuniq <= 8 * d.nrows ? 256 : (nuniq <= 16 * d.nrows ? 128 : (nuniq <= 32 * d.nrows ? 64 : 32));
+    d.set = true;
+  }
+  return PA_OK;
+}
+
+/* The local transposes of an assembled matrix as a matrix of their own: T_k = (A_k)^T, one row per LOCAL column of A (own, then
+ * ghost) x own rows of A — the left factor of spmtm (transpose(A)*B, src/p_sparse_matrix.jl:2276-2290).  T: created on
+ * (axes(A,2), axes(A,1)), not committed; its ghost rows make it a sub-assembled matrix. */
+extern "C" int pa_mat_transpose_local(pa_mat *A, pa_mat *T) {
+  PA_CHECK(A && T && A->committed && !T->committed && !A->subassembled, PA_ESTATE, "pa_mat_transpose_local: A must be committed and assembled, T not committed");
+  pa_ctx *c = A->ctx;
+  PA_CUDA(cudaSetDevice(c->device));
+  PA_TRY(build_transpose(A));
+  for (int k = 0; k < c->nlocal; ++k) {
+    const MatPart &t = A->T->parts[k];
+    MatPart &o = T->parts[k];
+    PA_CHECK(T->rows->parts[k].prefix && T->rows->parts[k].n_local == t.nrows && T->cols->parts[k].n_own == t.ncols, PA_EINVAL,
+             "pa_mat_transpose_local: T must live on (axes(A,2), axes(A,1))");
+    cudaFree(o.d_rowptr); cudaFree(o.d_colval); cudaFree(o.d_nzval);
+    o = MatPart();
+    o.nrows = t.nrows; o.ncols = T->cols->parts[k].n_local; o.nnz = t.nnz; o.ptr64 = false; o.rows_per_cta = t.rows_per_cta;
+    PA_CUDA(cudaMalloc(&o.d_rowptr, (t.nrows + 1) * 4));
+    PA_CUDA(cudaMalloc((void **)&o.d_colval, (t.nnz + PA_MAT_PAD) * 4));
+    PA_CUDA(cudaMalloc((void **)&o.d_nzval, (t.nnz + PA_MAT_PAD) * 8));
+    PA_CUDA(cudaMemcpyAsync(o.d_rowptr, t.d_rowptr, (t.nrows + 1) * 4, cudaMemcpyDeviceToDevice, c->stream));
+    if (t.nnz) {
+      PA_CUDA(cudaMemcpyAsync(o.d_colval, t.d_colval, t.nnz * 4, cudaMemcpyDeviceToDevice, c->stream));
+      PA_CUDA(cudaMemcpyAsync(o.d_nzval, t.d_nzval, t.nnz * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    PA_CUDA(cudaStreamSynchronize(c->stream));
+    if (t.nrows != T->rows->parts[k].n_own) T->subassembled = true;
+    o.set = true;
+  }
+  return PA_OK;
 }

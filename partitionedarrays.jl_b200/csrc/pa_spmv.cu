@@ -1081,6 +1081,12 @@ extern "C" int pa_mat_nnz(const pa_mat *A, int32_t k, int64_t *out) {
   return PA_OK;
 }
 
+extern "C" int pa_mat_nrows(const pa_mat *A, int32_t k, int64_t *out) {
+  PA_CHECK(A && out && k >= 0 && k < A->ctx->nlocal && A->parts[k].set, PA_EINVAL, "pa_mat_nrows: bad arguments");
+  *out = A->parts[k].nrows;
+  return PA_OK;
+}
+
 __global__ void k_narrow(const int64_t *in, int32_t *out, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int32_t)in[i];
 }

@@ -626,6 +626,15 @@ class PSparseMatrix:
         check(_capi.lib().pa_mat_download_csr(self.h, k, ptr(rp), ptr(cv), ptr(nz)))
         return rp, cv, nz
 
+    def download_csr_all(self, k: int):
+        """All stored rows of part k (own rows, and the ghost rows of a sub-assembled matrix): 0-based rowptr / colval."""
+        nnz = self.nnz(k)
+        nrows = C.c_int64()
+        check(_capi.lib().pa_mat_nrows(self.h, k, C.byref(nrows)))
+        rp, cv, nz = np.zeros(nrows.value + 1, np.int64), np.zeros(nnz, np.int32), np.zeros(nnz, np.float64)
+        check(_capi.lib().pa_mat_download_csr(self.h, k, ptr(rp), ptr(cv), ptr(nz)))
+        return rp, cv, nz
+
     def fillstored_(self, a: float):
         check(_capi.lib().pa_mat_fill_stored(self.h, float(a)))
         return self
@@ -999,3 +1008,124 @@ def ref_cg_(x: PVector, A: PSparseMatrix, b: PVector, tolerance: float = 0.0, ma
 def opt_cg_(x, A, b, **kw):
     """opt_cg! forwards to ref_cg! in the reference (HPCG/src/opt_cg.jl:25-32); here it is the fused schedule."""
     return ref_cg_(x, A, b, **kw)
+
+
+# ---------------------------------------------------------------------------------------------------- spmm / spmtm / rap
+def _remove_ghost(r: PRange) -> PRange:
+    """remove_ghost on every part (src/p_range.jl:1404-1410): the own ids only."""
+    out = []
+    for ind in r.indices:
+        if ind.block is not None and ind.own_is_prefix:
+            out.append(pr.LocalIndices(ind.n_global, ind.part, block=ind.block, n_own=ind.n_own))
+        else:
+            out.append(pr.LocalIndices(ind.n_global, ind.part, ind.own_to_global, np.full(ind.n_own, ind.part, dtype=np.int32)))
+    return PRange(r.backend, out)
+
+
+def consistent_matrix(B: PSparseMatrix, rows_co: PRange) -> PSparseMatrix:
+    """C = consistent(B, rows_co) (src/p_sparse_matrix.jl:2243 and the consistent(::PSparseMatrix, rows_co) it calls): a
+    matrix with one row per LOCAL id of rows_co — the own rows of B plus, for every ghost id of rows_co, the row of B its
+    owner holds.  The ghost rows travel with exchange! on the device (row lengths, global column ids, values: each receiver
+    pulls its segments from the owners' HBM); the index bookkeeping (which rows, local numbering of the new ghost columns)
+    is setup-time host work, as in the reference."""
+    b = B.backend
+    rows_co.plan  # builds rows_co.plans
+    snd_to, payload = [], [[], [], []]
+    parts_csr = []
+    for k, (ind_b, ind_c, pl) in enumerate(zip(B.cols.indices, rows_co.indices, rows_co.plans)):
+        if not (ind_c.own_is_prefix and ind_b.own_is_prefix):
+            raise ValueError("consistent(B, rows_co): needs own-first local orders")
+        if B.rows.indices[k].n_own != ind_c.n_own:
+            raise ValueError("consistent(B, rows_co): the own rows of B and of rows_co differ")
+        rp, cv, nz = B.download_csr(k)
+        l2g = ind_b.local_to_global
+        parts_csr.append((rp, cv, nz, l2g))
+        snd_to.append([int(q) for q in pl.nbr_rcv])
+        lens, gids, vals = [], [], []
+        for i in range(len(pl.nbr_rcv)):
+            rows = pl.rcv_lids[pl.rcv_ptrs[i] - 1 : pl.rcv_ptrs[i + 1] - 1].astype(np.int64) - 1  # my own rows this neighbour needs
+            cnt = rp[rows + 1] - rp[rows]
+            take = np.concatenate([np.arange(rp[r], rp[r + 1]) for r in rows]) if len(rows) and cnt.sum() else np.zeros(0, np.int64)
+            lens.append(cnt.astype(np.int64)); gids.append(l2g[cv[take]].astype(np.int64)); vals.append(nz[take])
+        payload[0].append(lens); payload[1].append(gids); payload[2].append(vals)
+    graph = ExchangeGraph(b, snd_to)
+    got = [exchange(p, graph) for p in payload]
+    new_cols, locals_ = [], []
+    for k, (ind_b, ind_c, pl) in enumerate(zip(B.cols.indices, rows_co.indices, rows_co.plans)):
+        rp, cv, nz, l2g = parts_csr[k]
+        if [int(q) for q in graph.rcv[k]] != [int(q) for q in pl.nbr_snd]:
+            raise RuntimeError("consistent(B, rows_co): exchange graph and ghost owners disagree")
+        n_own, n_loc = ind_c.n_own, ind_c.n_local
+        row_len = np.zeros(n_loc, dtype=np.int64)
+        row_len[:n_own] = np.diff(rp)
+        ghost_rows = {}
+        all_g = []
+        for i in range(len(pl.nbr_snd)):
+            lids = pl.snd_lids[pl.snd_ptrs[i] - 1 : pl.snd_ptrs[i + 1] - 1].astype(np.int64) - 1  # my ghost rows owned by this neighbour
+            lens_i, g_i, v_i = got[0][k][i].astype(np.int64), got[1][k][i].astype(np.int64), got[2][k][i].astype(np.float64)
+            cuts = np.concatenate([[0], np.cumsum(lens_i)])
+            for t, L in enumerate(lids):
+                ghost_rows[int(L)] = (g_i[cuts[t] : cuts[t + 1]], v_i[cuts[t] : cuts[t + 1]])
+            row_len[lids] = lens_i
+            all_g.append(g_i)
+        all_g = np.concatenate(all_g) if all_g else np.zeros(0, np.int64)
+        cC = pr.union_ghost(ind_b, all_g, _find_owner(B.cols, ind_b, all_g))
+        new_cols.append(cC)
+        rp2 = np.zeros(n_loc + 1, dtype=np.int64)
+        np.cumsum(row_len, out=rp2[1:])
+        cv2 = np.zeros(int(rp2[-1]), dtype=np.int32)
+        nz2 = np.zeros(int(rp2[-1]), dtype=np.float64)
+        cv2[: len(cv)] = cv  # the own rows keep B's local column ids (cC appends its new ghosts behind B's)
+        nz2[: len(nz)] = nz
+        for L, (g, v) in ghost_rows.items():
+            lc = cC.global_to_local(g).astype(np.int64) - 1
+            o = np.argsort(lc, kind="stable")
+            cv2[rp2[L] : rp2[L + 1]] = lc[o]
+            nz2[rp2[L] : rp2[L + 1]] = v[o]
+        locals_.append((rp2, cv2, nz2))
+    C = PSparseMatrix(rows_co, PRange(b, new_cols))
+    for k, (rp2, cv2, nz2) in enumerate(locals_):
+        C.set_csr(k, rp2, cv2, nz2, index_base=0)
+    return C.commit()
+
+
+def spmm(A: PSparseMatrix, B: PSparseMatrix) -> PSparseMatrix:
+    """spmm(A, B) = A*B (src/p_sparse_matrix.jl:2237-2262): C = consistent(B, axes(A,2)), then the local products
+    D_k = A_k * C_k on the device (pa_mat_spmm_local); D is assembled on (axes(A,1), axes(C,2))."""
+    if not (A.assembled and B.assembled):
+        raise ValueError("spmm: both matrices must be assembled")
+    Cm = consistent_matrix(B, A.cols)
+    D = PSparseMatrix(A.rows, Cm.cols)
+    check(_capi.lib().pa_mat_spmm_local(A.h, Cm.h, D.h))
+    D.commit()
+    Cm.free()
+    return D
+
+
+def spmtm(A: PSparseMatrix, B: PSparseMatrix) -> PSparseMatrix:
+    """spmtm(A, B) = transpose(A)*B (src/p_sparse_matrix.jl:2276-2290): local products (A_k)^T * B_k on the device give a
+    sub-assembled matrix on (axes(A,2), axes(B,2)) whose ghost rows then travel to their owners (assemble)."""
+    if not (A.assembled and B.assembled):
+        raise ValueError("spmtm: both matrices must be assembled")
+    b = A.backend
+    T = PSparseMatrix(A.cols, A.rows)
+    check(_capi.lib().pa_mat_transpose_local(A.h, T.h))
+    T.commit()
+    Ds = PSparseMatrix(A.cols, B.cols)
+    check(_capi.lib().pa_mat_spmm_local(T.h, B.h, Ds.h))
+    Ds.commit()
+    I, J, V = [], [], []
+    for k, (ir, ic) in enumerate(zip(A.cols.indices, B.cols.indices)):
+        rp, cv, nz = Ds.download_csr_all(k)
+        rowid = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+        I.append(ir.local_to_global[rowid]); J.append(ic.local_to_global[cv]); V.append(nz)
+    T.free(); Ds.free()
+    return psparse(I, J, V, _remove_ghost(A.cols), _remove_ghost(B.cols), assembled=False, compress="device")
+
+
+def rap(R: PSparseMatrix, A: PSparseMatrix, P: PSparseMatrix) -> PSparseMatrix:
+    """rap(R, A, P) = R*A*P (src/p_sparse_matrix.jl:2212-2218)."""
+    RA = spmm(R, A)
+    out = spmm(RA, P)
+    RA.free()
+    return out
