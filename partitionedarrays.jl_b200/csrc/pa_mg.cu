@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <array>
 
+#include "pa_device.cuh"
 #include "pa_internal.h"
 
 #define GS_THREADS 256
@@ -746,6 +747,108 @@ __global__ void __launch_bounds__(GS_THREADS, (MODE == 1 ? 2 : (MODE == 0 ? GS_C
 }
 
 
+// ------------------------------------------------------------------ the multi-colour kernel: SELL slices through a TMA ring
+// One launch per colour, like k_gs_sell<W, 0>, but the matrix never passes through registers on its way in: the slices
+// of a colour are contiguous in the SELL copy, so a persistent CTA streams tiles of NW slices (values + column words,
+// NW*W*384 bytes) HBM -> shared memory with cp.async.bulk (TMA engine, L2 evict-first) into a ring of S stages, exactly
+// like k_spmv_tma; NW consumer warps (one thread per row) read their slots from shared memory ([slot][lane]: conflict
+// free), gather x and run the ordered chain.  Only the x gathers, b and the row ids go through the LSU.
+// Rows of a colour never read a value another row of the colour writes, so x is read with plain loads and the slices are
+// walked in ascending order in both sweep directions (the order inside a colour is immaterial: same bits either way).
+template <int W, int B>
+__global__ void __launch_bounds__(288, 2) k_gs_color_tma(const GsSellArgs a, const int NW, const int S) {
+  extern __shared__ __align__(128) unsigned char gsc_smem[];
+  const int WD = W ? W : a.W;
+  const int tile_e = NW * WD * 32;  // entries per stage
+  double *val_s = reinterpret_cast<double *>(gsc_smem);
+  int32_t *col_s = reinterpret_cast<int32_t *>(val_s + (size_t)S * tile_e);
+  uint64_t *full = reinterpret_cast<uint64_t *>(col_s + (size_t)S * tile_e);
+  uint64_t *empty = full + S;
+  const int tid = threadIdx.x, nthr_c = NW * 32;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, nthr_c);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t nsl = a.g1 - a.g0, ntiles = (nsl + NW - 1) / NW;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int64_t nloc = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
+  if (tid >= nthr_c) {
+    if (tid == nthr_c) {  // producer: one elected lane drives the ring
+      const uint64_t pol = gs_stream_policy();
+      int s = 0;
+      uint32_t ph = 1;  // parity of the consumers' release of stage s, one lap behind
+      for (int64_t j = 0; j < nloc; ++j, ++s) {
+        if (s == S) { s = 0; ph ^= 1u; }
+        if (j >= S) mbar_wait(empty + s, ph);
+        const int64_t g = a.g0 + (first + j * stride) * NW;
+        const uint32_t ne = (uint32_t)(min((int64_t)NW, a.g1 - g) * WD * 32);
+        mbar_expect_tx(full + s, ne * 12u);
+        tma_load_1d(val_s + (size_t)s * tile_e, a.vals + g * WD * 32, ne * 8u, full + s, pol);
+        tma_load_1d(col_s + (size_t)s * tile_e, a.cols + g * WD * 32, ne * 4u, full + s, pol);
+      }
+    }
+    return;
+  }
+  const int lane = tid & 31, wrp = tid >> 5;
+  // row ids two tiles ahead, right-hand side one tile ahead: none of the three dependent reads waits inside the loop
+  auto slice_row = [&](int64_t j) -> int32_t {
+    if (j >= nloc) return -1;
+    const int64_t g = a.g0 + (first + j * stride) * NW + wrp;
+    return g < a.g1 ? __ldg(a.rows + g * 32 + lane) : -1;
+  };
+  int32_t row = slice_row(0), row_n = slice_row(1);
+  double bv = row >= 0 ? __ldg(a.b + row) : 0.0;
+  int s = 0;
+  uint32_t ph = 0;
+  for (int64_t j = 0; j < nloc; ++j, ++s) {
+    if (s == S) { s = 0; ph ^= 1u; }
+    const int32_t row_nn = slice_row(j + 2);
+    const double bv_n = row_n >= 0 ? __ldg(a.b + row_n) : 0.0;
+    mbar_wait(full + s, ph);
+    if (row >= 0) {
+      const double *vs = val_s + (size_t)s * tile_e + wrp * WD * 32 + lane;
+      const int32_t *cs = col_s + (size_t)s * tile_e + wrp * WD * 32 + lane;
+      double sum = bv, d = 0.0, xo = 0.0;
+#pragma unroll 1
+      for (int k0 = 0; k0 < WD; k0 += B) {
+        int32_t code[B];
+        double v[B], xv[B];
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+          const int kk = W ? min(k0 + u, W - 1) : min(k0 + u, WD - 1);  // past the end: a redundant read of the last slot
+          code[u] = cs[kk * 32];
+          v[u] = vs[kk * 32];
+        }
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+          const int32_t c = code[u] >= 0 ? (code[u] & GS_COL_MASK) : row;  // empty slot: any valid address
+          asm("ld.global.f64 %0, [%1];" : "=d"(xv[u]) : "l"(a.x + c));  // scheduled like __ldg, but never the read-only path
+        }
+#pragma unroll
+        for (int u = 0; u < B; ++u) {  // s -= a*x[col], in CSR order
+          const bool in = (W ? (k0 + u < W) : (k0 + u < WD)) && code[u] >= 0;
+          const bool use = in && (!a.zero_guess || (code[u] & GS_COL_FRESH));
+          const double t = __dsub_rn(sum, __dmul_rn(v[u], xv[u]));
+          sum = use ? t : sum;
+          const bool dg = in && (code[u] & GS_COL_MASK) == row;
+          d = dg ? v[u] : d;
+          xo = dg ? xv[u] : xo;
+        }
+      }
+      mbar_arrive(empty + s);
+      if (!a.zero_guess) sum = __dadd_rn(sum, __dmul_rn(d, xo));  // s += d*x[row]
+      a.x[row] = __ddiv_rn(sum, d);
+    } else {
+      mbar_arrive(empty + s);
+    }
+    row = row_n; row_n = row_nn; bv = bv_n;
+  }
+}
+
 // ------------------------------------------------------------------ the SELL dataflow kernel of the lexicographic order
 // One thread per row, one warp per slice, like k_gs_sell, but with everything that does not depend on the rows of
 // earlier levels done BEFORE the warp waits:
@@ -1356,10 +1459,39 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
       if (g->order == PA_GS_MULTICOLOR) {
         // one launch per colour, in sweep order; within a colour the rows are independent
         void (*kern)(const GsSellArgs) = o->W == 27 ? k_gs_sell<27, 0> : (o->W == 7 ? k_gs_sell<7, 0> : k_gs_sell<0, 0>);
+        // gs_color_kernel 1 (default): the slices stream through a TMA ring (k_gs_color_tma); 0: every lane loads its own entries
+        const bool ring = pa_knob(c, "gs_color_kernel", 1) != 0;
+        const int batch = (int)pa_knob(c, "gs_color_batch", 14);
+        void (*tk)(const GsSellArgs, int, int) = o->W == 27 ? (batch >= 27 ? k_gs_color_tma<27, 27> : (batch >= 14 ? k_gs_color_tma<27, 14> : k_gs_color_tma<27, 9>))
+                                                 : (o->W == 7 ? k_gs_color_tma<7, 7> : k_gs_color_tma<0, 8>);
+        int NW = (int)pa_knob(c, "gs_color_slices", 2), S = (int)pa_knob(c, "gs_color_stages", 2);
+        NW = std::max(1, std::min(NW, 8));
+        S = std::max(2, std::min(S, 8));
+        size_t smem = 0;
+        int per_sm = 1;
+        if (ring) {
+          while ((smem = (size_t)S * ((size_t)NW * o->W * 32 * 12 + 16)) > 200 * 1024 && (NW > 1 || S > 2)) {
+            if (NW > 1) NW /= 2; else --S;
+          }
+          PA_CHECK(smem <= 220 * 1024, PA_ESTATE, "gs_sweep: a slice of the multi-colour copy does not fit shared memory");
+          PA_CUDA(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tk, NW * 32 + 32, smem));
+          const int64_t cap = pa_knob(c, "gs_color_ctas", 0);
+          if (cap > 0 && cap < per_sm) per_sm = (int)cap;
+          if (per_sm < 1) per_sm = 1;
+        }
         for (int q = 0; q < o->nlev; ++q) {
           const int l = backward ? o->nlev - 1 - q : q;
           const int64_t s0 = o->lev_group[l], s1 = o->lev_group[l + 1];
           if (s1 == s0) continue;
+          if (ring) {
+            a.g0 = s0;
+            a.g1 = s1;
+            const int64_t grid = std::min<int64_t>((s1 - s0 + NW - 1) / NW, (int64_t)nsm * per_sm);
+            tk<<<(unsigned)grid, NW * 32 + 32, smem, c->stream>>>(a, NW, S);
+            c->launches++;
+            continue;
+          }
           a.g0 = backward ? a.ngroups - s1 : s0;
           a.g1 = backward ? a.ngroups - s0 : s1;
           const int64_t grid = std::min<int64_t>((s1 - s0 + wpc - 1) / wpc, (int64_t)nsm * 16);

@@ -157,8 +157,11 @@ def test_gauss_seidel_on_short_rows_is_bit_exact(pa, case, kernel):
     b.close()
 
 
+# colour kernel: "lanes" = every lane loads its own entries (k_gs_sell<W,0>); (slices per tile, stages, batch) = the slices
+# stream through a TMA ring (k_gs_color_tma, the default: 2 slices, 2 stages, batches of 14)
+@pytest.mark.parametrize("ckern", ["lanes", (2, 2, 14), (1, 3, 9), (4, 2, 27), (3, 4, 14)])
 @pytest.mark.parametrize("npd,nloc", [((2, 2, 1), (8, 6, 4)), ((1, 1, 1), (10, 9, 8)), ((2, 1, 1), (40, 32, 24))])
-def test_multicolor_gauss_seidel_matches_the_oracle_order(pa, npd, nloc):
+def test_multicolor_gauss_seidel_matches_the_oracle_order(pa, npd, nloc, ckern):
     """The opt-in multi-colour order (8 colours, one launch per colour): same per-row arithmetic as the reference's
     sweep, rows visited colour by colour — bit-identical to the oracle's sweep in that order, and switching back to the
     lexicographic order gives the reference's iterates again."""
@@ -166,6 +169,7 @@ def test_multicolor_gauss_seidel_matches_the_oracle_order(pa, npd, nloc):
     lev.order, lev.kind = "multicolor", 27
     P = len(lev.part)
     b = pa.CUDAArray(P, arena_bytes=32 << 20)
+    _set_color_kernel(b, ckern)
     gn = tuple(a * c for a, c in zip(npd, nloc))
     A, rhs = pa.stencil_matrix(27, gn, npd, b)
     gs = pa.GaussSeidel(A, kind=27).set_order("multicolor")
@@ -173,6 +177,40 @@ def test_multicolor_gauss_seidel_matches_the_oracle_order(pa, npd, nloc):
     gs.set_order("lexicographic")
     lev.order = "lexicographic"
     _smooth_and_compare(pa, lev, A, gs, 8)
+    gs.free()
+    b.close()
+
+
+def _set_color_kernel(b, ckern):
+    if ckern == "lanes":
+        b.set_knob("gs_color_kernel", 0)
+    else:
+        b.set_knob("gs_color_kernel", 1)
+        for key, val in zip(("gs_color_slices", "gs_color_stages", "gs_color_batch"), ckern):
+            b.set_knob(key, val)
+
+
+@pytest.mark.parametrize("ckern", ["lanes", (2, 2, 14), (8, 3, 14)])
+@pytest.mark.parametrize("case", ["fdm7-redblack", "fdm27-thin"])
+def test_multicolor_gauss_seidel_other_row_widths(pa, case, ckern):
+    """Red/black order of the 7-pt gallery operator (rows of <= 7 entries) and the 8-colour order on a box one cell thick
+    (rows of <= 9 entries: the generic-width instantiation of the colour kernels), against the oracle's sweep in that order."""
+    if case == "fdm7-redblack":
+        gn, npd, kind = (14, 12, 10), (2, 1, 2), 7
+        I, J, V, rows, cols = o.laplacian_fdm(gn, npd)
+        Ao = o.psparse(I, J, V, rows, cols, assembled=True, local_format="csr")
+        lev = hpcg_mg.Level.from_psparse(Ao)
+        b = pa.CUDAArray(4, arena_bytes=16 << 20)
+        A, _ = pa.stencil_matrix(7, gn, npd, b)
+    else:
+        npd, nloc, kind = (2, 1, 1), (12, 10, 1), 27
+        lev = hpcg_mg.Level(*nloc, npd)
+        b = pa.CUDAArray(2, arena_bytes=16 << 20)
+        A, _ = pa.stencil_matrix(27, tuple(a * c for a, c in zip(npd, nloc)), npd, b)
+    _set_color_kernel(b, ckern)
+    lev.order, lev.kind = "multicolor", kind
+    gs = pa.GaussSeidel(A, kind=kind).set_order("multicolor")
+    _smooth_and_compare(pa, lev, A, gs, 9)
     gs.free()
     b.close()
 
