@@ -152,7 +152,7 @@ int pa_vec_reduce_parts(const pa_vec *x, int32_t op, double p, double *out);
 
 /* ------------------------------------------------------------------ exchange!(rcv, snd, graph) ----------
  * ExchangeGraph (src/primitives.jl:728-741) + the vector-payload exchange (exchange!/exchange_impl! :992-1042;
- * src/debug_array.jl:250-255, src/mpi_array.jl:525-614) for 8-byte elements (Float64 / Int64 payloads).
+ * src/debug_array.jl:250-255, src/mpi_array.jl:525-614) for 1/2/4/8-byte elements (Float64 / Int64 by default; Int32, Float32, ...).
  * snd_ids / rcv_ids: 1-based part ids (graph.snd[p], graph.rcv[p]); snd_ptrs / rcv_ptrs: the 1-based JaggedArray ptrs
  * of the send / receive buffers (n+1 entries; what allocate_exchange_impl computes, :921-947).
  * rcv_src_offsets (nullable): for every source i the 0-based position of the segment addressed to this part inside the
@@ -160,6 +160,9 @@ int pa_vec_reduce_parts(const pa_vec *x, int32_t op, double p, double *out);
  * The send buffers live in the symmetric arena: a receiver reads its segment straight from the sender's HBM. */
 typedef struct pa_xchg pa_xchg;
 int pa_xchg_create(pa_ctx *ctx, pa_xchg **out);
+/* bytes per payload element: 8 (default), 4 (the reference's Int32 index lists, src/p_range.jl:489-531; Float32), 2 or 1;
+ * before pa_xchg_commit.  ptrs, offsets and the n of upload/download count elements. */
+int pa_xchg_set_elem_size(pa_xchg *x, int32_t bytes);
 int pa_xchg_set_part(pa_xchg *x, int32_t k, int32_t n_snd, const int32_t *snd_ids, const int64_t *snd_ptrs, int32_t n_rcv,
                      const int32_t *rcv_ids, const int64_t *rcv_ptrs, const int64_t *rcv_src_offsets);
 /* sym_snd_len: longest send buffer over ALL parts of the job (0 = over the local parts; only when every part is local) */

@@ -71,6 +71,7 @@ SIGNATURES = {
     "pa_vec_assemble_op": [_P, _I32],
     "pa_vec_reduce_parts": [_P, _I32, _D, _P],
     "pa_xchg_create": [_P, _P],
+    "pa_xchg_set_elem_size": [_P, _I32],
     "pa_xchg_set_part": [_P, _I32, _I32, _P, _P, _I32, _P, _P, _P],
     "pa_xchg_commit": [_P, _I64],
     "pa_xchg_destroy": [_P],

@@ -1642,6 +1642,80 @@ __global__ void k_prolong(double *xf, const double *xc, int64_t nc, int64_t cx, 
   }
 }
 
+// mul_no_lat!(Axf, A, x) followed by restrict! reads Axf only at the injection points (one fine row in eight): this
+// kernel computes exactly those rows — r_c[i] = b_f[v] - (A x)[v], v = f2c[i] — with the arithmetic of spmv_csr!
+// (acc += a*x[col] in CSR order, separate multiply and add), so r_c has the bits of the two-step reference sequence while
+// 7/8 of the residual SpMV's matrix traffic is never read.  One warp per coarse row: lane k loads entry k (one coalesced
+// read of the row), multiplies, and the products are added in column order by passing them to lane 0.
+template <typename PtrT>
+__global__ void __launch_bounds__(256, 4) k_residual_restrict(double *rc, const double *bf, const double *x, const PtrT *rowptr, const int32_t *colval,
+                                                           const double *nzval, int64_t nc, int64_t cx, int64_t cy, int64_t fx, int64_t fy) {
+  constexpr int R = 4;  // coarse rows in flight per warp: the three dependent reads (row pointer, entries, x) of R rows overlap
+  __shared__ double rr_prod[8 * R * 33];
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const uint32_t ucx = (uint32_t)cx, ucy = (uint32_t)cy;
+  for (int64_t i0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R; i0 < nc; i0 += nw * R) {
+    int64_t f[R], p0[R];
+    int len[R];
+    bool shortrows = true;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const uint32_t i = (uint32_t)min(i0 + r, nc - 1);  // (rows < 2^31: pa_gs_commit)
+      const uint32_t ix = i % ucx, t = i / ucx, iy = t % ucy, iz = t / ucy;
+      f[r] = 2 * (int64_t)ix + fx * (2 * (int64_t)iy + fy * 2 * (int64_t)iz);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      p0[r] = (int64_t)rowptr[f[r]];
+      len[r] = (int)((int64_t)rowptr[f[r] + 1] - p0[r]);
+      shortrows &= len[r] <= 32;
+    }
+    if (shortrows) {
+      double v[R], xv[R];
+      int32_t c[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const bool in = lane < len[r];
+        v[r] = in ? nzval[p0[r] + lane] : 0.0;
+        c[r] = in ? colval[p0[r] + lane] : 0;
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) xv[r] = x[c[r]];
+      // products parked in shared memory, then lane r adds row r's products in column order (R chains side by side)
+      double *sp = rr_prod + (size_t)(threadIdx.x >> 5) * (R * 33);
+#pragma unroll
+      for (int r = 0; r < R; ++r) sp[r * 33 + lane] = __dmul_rn(v[r], xv[r]);
+      __syncwarp();
+      if (lane < R) {
+        int mylen = len[0];
+        int64_t myf = f[0];
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+          mylen = lane == r ? len[r] : mylen;
+          myf = lane == r ? f[r] : myf;
+        }
+        const double bv = bf[myf];
+        double acc = 0.0;
+        for (int k = 0; k < mylen; ++k) acc = __dadd_rn(acc, sp[lane * 33 + k]);
+        if (i0 + lane < nc) rc[i0 + lane] = __dsub_rn(bv, acc);
+      }
+      __syncwarp();
+    } else {
+      for (int r = 0; r < R && i0 + r < nc; ++r) {  // rows of any length: 32 entries per trip, the chain continues across trips
+        double acc = 0.0;
+        for (int64_t q = p0[r]; q < p0[r] + len[r]; q += 32) {
+          const int n = (int)min((int64_t)32, p0[r] + len[r] - q);
+          double prod = 0.0;
+          if (lane < n) prod = __dmul_rn(nzval[q + lane], x[colval[q + lane]]);
+          for (int k = 0; k < n; ++k) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, prod, k));
+        }
+        if (lane == 0) rc[i0 + r] = __dsub_rn(bf[f[r]], acc);
+      }
+    }
+  }
+}
+
 /* Mg_preconditioner (mg_preconditioner.jl:44-63): levels[0] = coarsest ... levels[n-1] = finest.
  * dims: nlevels x nlocal x 3 local box dims (x fastest); each level halves the one above. */
 extern "C" int pa_mg_create(int32_t nlevels, pa_mat **A, pa_gs **gs, const int64_t *dims, pa_mg **out) {
@@ -1705,13 +1779,27 @@ static int pc_solve(pa_mg *M, pa_vec *x, const pa_vec *b, int l, int zero_guess)
   pa_ctx *c = M->ctx;
   PA_TRY(pa_gs_smooth(M->gs[l], x, b, zero_guess));  // bottom solve / pre-smoother
   if (l == 0) return PA_OK;
-  PA_TRY(pa_spmv(M->A[l], x, M->Axf[l], 1.0, 0.0, PA_SPMV_DEFAULT));  // mul_no_lat!(Axf, A, x)
+  // mg_fused_restrict 1 (default): residual at the injection points only (k_residual_restrict); 0: the reference's two steps
+  const bool fused = pa_knob(c, "mg_fused_restrict", 1) != 0 && !M->A[l]->subassembled;
+  if (fused) PA_TRY(pa_vec_consistent(x));  // mul_no_lat! = consistent!(x), then the local product
+  else PA_TRY(pa_spmv(M->A[l], x, M->Axf[l], 1.0, 0.0, PA_SPMV_DEFAULT));  // mul_no_lat!(Axf, A, x)
   PA_TRY(pa_before_write(c));
   for (int k = 0; k < c->nlocal; ++k) {
     const auto &dc = M->dims[l - 1][k], &df = M->dims[l][k];
     const int64_t nc = dc[0] * dc[1] * dc[2];
     if (!nc) continue;
-    k_restrict<<<small_grid(nc), 256, 0, c->stream>>>(M->r[l - 1]->d[k], b->d[k], M->Axf[l]->d[k], nc, dc[0], dc[1], df[0], df[1]);
+    if (fused) {
+      const MatPart &m = M->A[l]->parts[k];
+      const int64_t grid = std::min<int64_t>((nc + 31) / 32, 148 * 8);
+      if (m.ptr64)
+        k_residual_restrict<int64_t><<<(unsigned)grid, 256, 0, c->stream>>>(M->r[l - 1]->d[k], b->d[k], x->d[k], (const int64_t *)m.d_rowptr, m.d_colval, m.d_nzval,
+                                                                          nc, dc[0], dc[1], df[0], df[1]);
+      else
+        k_residual_restrict<int32_t><<<(unsigned)grid, 256, 0, c->stream>>>(M->r[l - 1]->d[k], b->d[k], x->d[k], (const int32_t *)m.d_rowptr, m.d_colval, m.d_nzval,
+                                                                          nc, dc[0], dc[1], df[0], df[1]);
+    } else {
+      k_restrict<<<small_grid(nc), 256, 0, c->stream>>>(M->r[l - 1]->d[k], b->d[k], M->Axf[l]->d[k], nc, dc[0], dc[1], df[0], df[1]);
+    }
     c->launches++;
   }
   PA_CUDA(cudaGetLastError());

@@ -19,7 +19,7 @@ struct XchgPart {
   bool has_src_off = false, set = false;
   int64_t *d_rcv_ptrs = nullptr, *d_src_off = nullptr;
   int32_t *d_slot = nullptr;                // neighbour slot of every source
-  unsigned long long *d_rcv = nullptr;      // receive buffer (8-byte elements)
+  unsigned char *d_rcv = nullptr;           // receive buffer (elem bytes per element)
 };
 
 struct pa_xchg {
@@ -27,15 +27,17 @@ struct pa_xchg {
   pa_plan *plan = nullptr;  // neighbour sets for the epoch signalling (no index data)
   std::vector<XchgPart> parts;
   uint64_t snd_off = 0, snd_bytes = 0;
+  int elem = 8;  // bytes per element (1, 2, 4 or 8)
   bool committed = false;
 };
 
 // one CTA column per source segment (blockIdx.y), grid-stride over its elements
-__global__ void k_exchange(unsigned long long *rcv, const int64_t *__restrict__ rcv_ptrs, const int32_t *__restrict__ slot,
+template <typename T>
+__global__ void k_exchange(T *rcv, const int64_t *__restrict__ rcv_ptrs, const int32_t *__restrict__ slot,
                            const int64_t *__restrict__ src_off, PeerPtrs peers) {
   const int i = blockIdx.y;
   const int64_t lo = rcv_ptrs[i], n = rcv_ptrs[i + 1] - lo;
-  const unsigned long long *src = reinterpret_cast<const unsigned long long *>(peers.p[slot[i]]) + src_off[i];
+  const T *src = reinterpret_cast<const T *>(peers.p[slot[i]]) + src_off[i];
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
     rcv[lo + j] = __ldcg(src + j);
 }
@@ -46,6 +48,15 @@ extern "C" int pa_xchg_create(pa_ctx *ctx, pa_xchg **out) {
   x->ctx = ctx;
   x->parts.resize(ctx->nlocal);
   *out = x;
+  return PA_OK;
+}
+
+/* Element size of the payload in bytes: 8 (default; Float64 / Int64), 4 (Int32 / Float32 — the reference's index lists are
+ * JaggedArray{Int32,Int32}, src/p_range.jl:489-531), 2 or 1.  Before pa_xchg_commit; ptrs and offsets count ELEMENTS. */
+extern "C" int pa_xchg_set_elem_size(pa_xchg *x, int32_t bytes) {
+  PA_CHECK(x && !x->committed, PA_ESTATE, "pa_xchg_set_elem_size: exchange missing or already committed");
+  PA_CHECK(bytes == 1 || bytes == 2 || bytes == 4 || bytes == 8, PA_EINVAL, "pa_xchg_set_elem_size: %d bytes per element not supported (1, 2, 4, 8)", bytes);
+  x->elem = bytes;
   return PA_OK;
 }
 
@@ -138,7 +149,7 @@ extern "C" int pa_xchg_commit(pa_xchg *x, int64_t sym_snd_len) {
     PA_CUDA(cudaMalloc((void **)&p.d_rcv_ptrs, (nr + 1) * sizeof(int64_t)));
     PA_CUDA(cudaMalloc((void **)&p.d_src_off, std::max<size_t>(nr, 1) * sizeof(int64_t)));
     PA_CUDA(cudaMalloc((void **)&p.d_slot, std::max<size_t>(nr, 1) * sizeof(int32_t)));
-    PA_CUDA(cudaMalloc((void **)&p.d_rcv, std::max<int64_t>(p.rcv_ptrs.back(), 1) * sizeof(unsigned long long)));
+    PA_CUDA(cudaMalloc((void **)&p.d_rcv, (size_t)std::max<int64_t>(p.rcv_ptrs.back(), 1) * x->elem));
     PA_CUDA(cudaMemcpyAsync(p.d_rcv_ptrs, p.rcv_ptrs.data(), (nr + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     if (nr) {
       PA_CUDA(cudaMemcpyAsync(p.d_src_off, p.rcv_src_off.data(), nr * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
@@ -146,7 +157,7 @@ extern "C" int pa_xchg_commit(pa_xchg *x, int64_t sym_snd_len) {
     }
     PA_CUDA(cudaStreamSynchronize(c->stream));
   }
-  x->snd_bytes = ((uint64_t)std::max<int64_t>(sym_snd_len, 1) * 8 + 511) / 512 * 512;
+  x->snd_bytes = ((uint64_t)std::max<int64_t>(sym_snd_len, 1) * x->elem + 511) / 512 * 512;
   PA_TRY(pa_arena_alloc(c, x->snd_bytes, &x->snd_off));
   x->committed = true;
   return PA_OK;
@@ -180,7 +191,7 @@ extern "C" int pa_xchg_upload_snd(pa_xchg *x, int32_t k, const void *data, int64
            (long long)(k >= 0 && k < c->nlocal ? x->parts[k].snd_ptrs.back() : -1));
   PA_CUDA(cudaSetDevice(c->device));
   PA_TRY(pa_before_write(c));  // nobody may still be reading the previous contents
-  if (n) PA_CUDA(cudaMemcpyAsync(c->arena[k] + x->snd_off, data, n * 8, cudaMemcpyHostToDevice, c->stream));
+  if (n) PA_CUDA(cudaMemcpyAsync(c->arena[k] + x->snd_off, data, (size_t)n * x->elem, cudaMemcpyHostToDevice, c->stream));
   return PA_OK;
 }
 
@@ -203,7 +214,12 @@ extern "C" int pa_xchg_exchange(pa_xchg *x) {
     for (size_t i = 0; i < pp.nbrs.size(); ++i)
       PA_CHECK(c->peer_base[pp.nbrs[i]], PA_ESTATE, "part %d's arena was never imported (pa_ctx_arena_import)", pp.nbrs[i] + 1);
     const dim3 grid((unsigned)std::min<int64_t>((longest + 255) / 256, 148 * 4), (unsigned)nr);
-    k_exchange<<<grid, 256, 0, c->stream>>>(p.d_rcv, p.d_rcv_ptrs, p.d_slot, p.d_src_off, peers);
+    switch (x->elem) {
+      case 8: k_exchange<<<grid, 256, 0, c->stream>>>((unsigned long long *)p.d_rcv, p.d_rcv_ptrs, p.d_slot, p.d_src_off, peers); break;
+      case 4: k_exchange<<<grid, 256, 0, c->stream>>>((uint32_t *)p.d_rcv, p.d_rcv_ptrs, p.d_slot, p.d_src_off, peers); break;
+      case 2: k_exchange<<<grid, 256, 0, c->stream>>>((uint16_t *)p.d_rcv, p.d_rcv_ptrs, p.d_slot, p.d_src_off, peers); break;
+      default: k_exchange<<<grid, 256, 0, c->stream>>>((uint8_t *)p.d_rcv, p.d_rcv_ptrs, p.d_slot, p.d_src_off, peers); break;
+    }
     c->launches++;
   }
   PA_CUDA(cudaGetLastError());
@@ -217,7 +233,7 @@ extern "C" int pa_xchg_download_rcv(pa_xchg *x, int32_t k, void *data, int64_t n
            "pa_xchg_download_rcv: %lld elements asked, the receive buffer holds %lld", (long long)n,
            (long long)(k >= 0 && k < c->nlocal ? x->parts[k].rcv_ptrs.back() : -1));
   PA_CUDA(cudaSetDevice(c->device));
-  if (n) PA_CUDA(cudaMemcpyAsync(data, x->parts[k].d_rcv, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (n) PA_CUDA(cudaMemcpyAsync(data, x->parts[k].d_rcv, (size_t)n * x->elem, cudaMemcpyDeviceToHost, c->stream));
   PA_CUDA(cudaStreamSynchronize(c->stream));
   return pa_check_device_error(c);
 }

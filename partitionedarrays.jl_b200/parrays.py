@@ -506,15 +506,22 @@ def exchange_layout(graph: ExchangeGraph, snd_len: Sequence[Sequence[int]]):
 
 def exchange(snd: Sequence[Sequence], graph: ExchangeGraph) -> List[List[np.ndarray]]:
     """rcv = fetch(exchange(snd, graph)) (src/primitives.jl:876-925, 992-1042): ``snd[k][j]`` (a scalar or a vector of
-    Float64 / Int64) goes to part ``graph.snd[k][j]``; ``rcv[k][i]`` is what part ``graph.rcv[k][i]`` sent here.  The
+    Float64 / Int64 / Int32 / Float32 / ...) goes to part ``graph.snd[k][j]``; ``rcv[k][i]`` is what part ``graph.rcv[k][i]`` sent here.  The
     payload moves on the device: each receiver reads its segments from the senders' HBM (pa_xchg_*)."""
     b = graph.backend
     L = _capi.lib()
     nl = len(b.parts)
     segs = [[np.atleast_1d(np.asarray(v)) for v in s] for s in snd]
-    # 8-byte elements on the device: Float64 when any part sends floats, Int64 otherwise (all processes must agree)
-    kinds = sorted({("f" if a.dtype.kind == "f" else "i") for s in segs for a in s})
-    dtype = np.float64 if any("f" in k for k in b.gather_all([kinds])) else np.int64
+    # element type on the device = the common type of everything any part sends (all processes must agree): Int32 / Float32
+    # payloads (the reference's index lists are JaggedArray{Int32,Int32}) travel as 4-byte elements, Int16 / Int8 / Bool as
+    # 2 / 1 bytes; everything else as Float64 when any part sends floats, Int64 otherwise
+    names = sorted({a.dtype.str for s in segs for a in s})
+    every = sorted({n for part in b.gather_all([names]) for n in part})
+    dtype = np.result_type(*[np.dtype(n) for n in every]) if every else np.dtype(np.int64)
+    if dtype.kind == "b":
+        dtype = np.dtype(np.uint8)
+    if dtype.kind not in "iuf" or dtype.itemsize not in (1, 2, 4, 8) or dtype == np.float16:
+        dtype = np.dtype(np.float64) if dtype.kind == "f" else np.dtype(np.int64)
     for k in range(nl):
         if len(segs[k]) != len(graph.snd[k]):
             raise ValueError("exchange: one send item per destination")
@@ -523,6 +530,7 @@ def exchange(snd: Sequence[Sequence], graph: ExchangeGraph) -> List[List[np.ndar
     h = C.c_void_p()
     check(L.pa_xchg_create(b.h, C.byref(h)))
     try:
+        check(L.pa_xchg_set_elem_size(h, dtype.itemsize))
         for k in range(nl):
             si, ri = i32(graph.snd[k]), i32(graph.rcv[k])
             sp, rp, so = _ptrs1(snd_len[k]), _ptrs1(rcv_len[k]), i64(rcv_off[k])

@@ -66,8 +66,10 @@ def test_symmetric_gauss_seidel_is_bit_exact(pa, npd, nloc, hint, lanes):
     b.close()
 
 
-def test_v_cycle_is_bit_exact(pa):
-    """ldiv!(x, P, b) (mg_preconditioner.jl:202-206,314-328): 3 levels, 4 parts, all pieces bit-exact => V-cycle bit-exact."""
+@pytest.mark.parametrize("fused_restrict", [1, 0])
+def test_v_cycle_is_bit_exact(pa, fused_restrict):
+    """ldiv!(x, P, b) (mg_preconditioner.jl:202-206,314-328): 3 levels, 4 parts, all pieces bit-exact => V-cycle bit-exact.
+    fused_restrict = 1 (default): the residual is computed at the injection points only (same bits as mul_no_lat! + restrict!)."""
     npd, n, levels = (2, 2, 1), 16, 3
     mg = hpcg_mg.MG(npd, levels, n, n, n)
     L = mg.levels[levels - 1]
@@ -77,6 +79,7 @@ def test_v_cycle_is_bit_exact(pa):
     want = [np.zeros(i.n_local) for i in L.part]
     mg.ldiv(want, [v.copy() for v in r])
     b = pa.CUDAArray(4, arena_bytes=64 << 20)
+    b.set_knob("mg_fused_restrict", fused_restrict)
     P = pa.pc_setup(b, levels, n, n, n, *npd)
     rv = _vec(pa, P.A.cols, r)
     x = pa.pzeros(P.A.cols)

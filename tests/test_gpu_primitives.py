@@ -37,6 +37,27 @@ def test_exchange_docstring_and_reference_tests(pa):
     b.close()
 
 
+@pytest.mark.parametrize("dtype", [np.int32, np.float32, np.int16, np.uint8, np.int64])
+def test_exchange_payload_element_types(pa, dtype):
+    """exchange! with Int32 payloads (the element type of the reference's index lists, src/p_range.jl:489-531 — odd segment
+    lengths and offsets, so 4-byte segments start off 8-byte boundaries), Float32 and narrower types: same values, same type."""
+    rng = np.random.default_rng(11)
+    P = 5
+    b = pa.CUDAArray(P, arena_bytes=16 << 20)
+    snd_ids = [[2, 3, 5], [1], [1, 2, 4, 5], [], [3]]
+    hi = 100 if np.dtype(dtype).itemsize == 1 else 30000
+    segs = [[(rng.integers(0, hi, size=int(rng.integers(1, 700)) | 1)).astype(dtype) for _ in s] for s in snd_ids]
+    graph = pa.ExchangeGraph(b, snd_ids)
+    want = o.exchange([o.jagged_from_lists(s, dtype) for s in segs], snd_ids, graph.rcv)
+    got = pa.exchange(segs, graph)
+    for r in range(P):
+        assert len(got[r]) == len(graph.rcv[r])
+        for i in range(len(got[r])):
+            assert got[r][i].dtype == np.dtype(dtype)
+            assert np.array_equal(got[r][i], want[r].segment(i))
+    b.close()
+
+
 def test_exchange_random_graph_matches_oracle(pa):
     rng = np.random.default_rng(7)
     P = 6
