@@ -78,6 +78,9 @@ struct GsOrder {
   uint32_t *d_lev_tot = nullptr;          // [nlev] (fenced gate variant)
   unsigned long long *d_done2 = nullptr;  // [nlev]
   unsigned long long sweeps = 0, sweeps2 = 0;
+  // strip order (k_gs_strip): ntask tasks of nsteps slices each, task-major
+  int ntask = 0;
+  int64_t nsteps = 0;
 };
 #define GS_COL_FRESH (1 << 30)
 #define GS_COL_OWN (1 << 29)
@@ -747,6 +750,217 @@ __global__ void __launch_bounds__(GS_THREADS, (MODE == 1 ? 2 : (MODE == 0 ? GS_C
 }
 
 
+// ------------------------------------------------------------------ the strip kernel of the lexicographic order
+// The wavefront of a box operator, cut so that a WARP owns a piece of it for a long time.  A task = one strip of 32
+// consecutive grid lines (y) of one plane (z); lane l walks line 32Y+l along x, w1 steps behind lane l-1 (27-pt: 2, so
+// that (x+1, y-1) is finished when (x, y) starts; 7-pt: 1): step s of a task is the slice of rows (s - w1*l, 32Y+l, z),
+// all on the wavefront level x + w1*y + w2*z = s + 32*w1*Y + w2*z — independent of each other.  The smoother's matrix is
+// copied once in (task, step, lane) order (SELL-32: every entry slot of a step is one coalesced load, the stream of a
+// warp is sequential in HBM).  Every row performs the reference's arithmetic on exactly the inputs of the sequential
+// sweep (NEW values of lower-numbered own neighbours, OLD values of the others): bit-identical results.
+//   * the NEW value of the row the lane finished one step ago (x-1) comes from a register;
+//   * all other NEW values are read as published (value, sweep epoch) pairs: correctness never rests on a fence or on
+//     the order in which warps run — a value is used only when both halves carry this sweep's epoch;
+//   * OLD values are read through L1: a lane re-reads the same sectors of x for four steps in a row, and nobody
+//     overwrites an OLD value before all its readers are done (anti-dependencies of a symmetric pattern follow the
+//     true ones), so whatever an L1 line holds for a not-yet-updated row is the value wanted.
+// Tasks are numbered by their start level 32*w1*Y + w2*z and dealt round robin to the resident warps; a step only
+// depends on steps of smaller level, which belong to tasks at most (strips x 32*w1/w2) numbers ahead: as long as the grid
+// holds that many warps (checked on the host) the lowest unfinished level can always proceed.
+//   * sliding window: consecutive steps of a lane are consecutive rows of a grid line, so entry k of this step names the
+//     column that entry k+1 (backward: k-1) of the previous step named — its value is taken from a per-warp table in shared
+//     memory ([slot][lane], conflict free) instead of being gathered again: 9 instead of 26 gathers per row of the 27-pt
+//     operator.  The test is on the column ids themselves (no assumption about the stencil): a match means "the same
+//     column one row later", and a value that was NEW (OLD) for the previous row of the line is still NEW (OLD) for this
+//     one, except the previous row itself, which is served from the register first.  The gathers of a wavefront slice go
+//     to 32 different lines, and the L1 takes about one such request per cycle: the request count, not HBM, bounds this
+//     sweep (profiles/), which is why the window matters.
+#define GS_STRIP_SMEM(W) ((size_t)(GS_THREADS / 32) * (W) * 32 * 12)
+template <int W, bool TRACE = false>
+__global__ void __launch_bounds__(GS_THREADS, 2) k_gs_strip(const GsSellArgs a, const int ntask, const int64_t nsteps) {
+  constexpr int B = W == 27 ? 9 : (W == 7 ? 7 : 8);
+  extern __shared__ __align__(16) unsigned char gss_smem[];
+  long long tk_load = 0, tk_gather = 0, tk_chain = 0, tk_rest = 0, tk0 = 0, tk1 = 0, tk_first = 0, tk_firstsum = 0, tk_old = 0;
+  int tk_npoll = 0, tk_nfresh = 0;
+  const int WD = W ? W : a.W;
+  const int lane = threadIdx.x & 31;
+  // the window of this warp: value and column of every entry slot of the lane's previous row
+  double *sx = reinterpret_cast<double *>(gss_smem) + (size_t)(threadIdx.x >> 5) * WD * 32 + lane;
+  int32_t *sc = reinterpret_cast<int32_t *>(gss_smem + (size_t)(GS_THREADS / 32) * WD * 32 * 8) + (size_t)(threadIdx.x >> 5) * WD * 32 + lane;
+  const int64_t nw = (int64_t)gridDim.x * (GS_THREADS / 32);
+  const int64_t w = (int64_t)blockIdx.x * (GS_THREADS / 32) + (threadIdx.x >> 5);
+  const unsigned epoch = (unsigned)a.epoch;
+  const uint64_t pol = gs_stream_policy(), keep = gs_keep_policy(1);
+  const int dk = a.backward ? -1 : 1;  // the previous row's slot that names the same column
+  for (int64_t t = w; t < ntask; t += nw) {
+    const int64_t tq = a.backward ? ntask - 1 - t : t;
+    int32_t prev_row = -1;
+    double prev_val = 0.0;
+    for (int k = 0; k < WD; ++k) sc[k * 32] = -1;  // empty window
+    const int64_t gstep = a.backward ? -1 : 1;
+    int64_t g = tq * nsteps + (a.backward ? nsteps - 1 : 0);
+    int32_t row = a.rows[g * 32 + lane];
+    double bv = row >= 0 ? __ldg(a.b + row) : 0.0;
+    for (int64_t st = 0; st < nsteps; ++st, g += gstep) {
+      const int32_t *cp = a.cols + g * WD * 32 + lane;
+      const double *vp = a.vals + g * WD * 32 + lane;
+      int32_t row_n = -1;
+      if (st + 1 < nsteps) {  // the next step of this task: its row ids now, its matrix slice on the way to L2
+        const int64_t gn = g + gstep;
+        row_n = __ldg(a.rows + gn * 32 + lane);
+        // ONE bulk prefetch per array (cp.async.bulk.prefetch.L2): per-line prefetch instructions (81 lines per slice, issued as
+        // divergent LSU requests) queue up in front of the gathers — the first pair came back after ~2400 cycles with them
+        if (a.gate == 1) {
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.vals + gn * WD * 32), "r"(WD * 32 * 8) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.cols + gn * WD * 32), "r"(WD * 32 * 4) : "memory");
+            if (st + 2 < nsteps) gs_prefetch_l2(a.rows + (gn + gstep) * 32);
+          }
+        } else if (a.gate == 2) {
+          const char *nv = reinterpret_cast<const char *>(a.vals + gn * WD * 32), *nc = reinterpret_cast<const char *>(a.cols + gn * WD * 32);
+          for (int l = lane; l < 2 * WD; l += 32) gs_prefetch_l2(nv + (size_t)l * 128);
+          if (lane < WD) gs_prefetch_l2(nc + (size_t)lane * 128);
+          if (lane == 0 && st + 2 < nsteps) gs_prefetch_l2(a.rows + (gn + gstep) * 32);
+        }
+      }
+      if (TRACE) tk0 = clock64();
+      if (row >= 0) {
+        double s = bv, d = 0.0, xold = 0.0;
+        int32_t carry_c = -1;  // backward: the slot below the batch, saved before the batch before it overwrote it
+        double carry_x = 0.0;
+#pragma unroll 1
+        for (int k0 = 0; k0 < WD; k0 += B) {
+          int32_t code[B], pc[B];
+          double v[B], xv[B], px[B];
+          unsigned long long w0[B], w1[B];
+          bool fresh[B], use[B];
+          if (TRACE) tk1 = clock64();
+#pragma unroll
+          for (int u = 0; u < B; ++u) {
+            const bool in = W ? (k0 + u < W) : (k0 + u < WD);
+            code[u] = in ? gs_ld_stream(cp + (k0 + u) * 32, pol) : -1;
+            v[u] = in ? gs_ld_stream(vp + (k0 + u) * 32, pol) : 0.0;
+          }
+          // the window slots this batch compares with, read before the batch overwrites its own slots
+#pragma unroll
+          for (int u = 0; u < B; ++u) {
+            const int kp = k0 + u + dk;
+            const bool in = kp >= 0 && kp < WD && (dk > 0 || u > 0);
+            pc[u] = in ? sc[kp * 32] : -1;
+            px[u] = in ? sx[kp * 32] : 0.0;
+          }
+          if (dk < 0) {
+            pc[0] = carry_c;
+            px[0] = carry_x;
+            const int kl = min(k0 + B - 1, WD - 1);
+            carry_c = sc[kl * 32];
+            carry_x = sx[kl * 32];
+          }
+          if (TRACE) {
+#pragma unroll
+            for (int u = 0; u < B; ++u) asm volatile("" ::"r"(code[u]), "d"(v[u]));
+            const long long t2 = clock64();
+            tk_load += t2 - tk1;
+            tk1 = t2;
+          }
+#pragma unroll
+          for (int u = 0; u < B; ++u) {
+            const bool valid = code[u] >= 0;
+            const int32_t c = valid ? (code[u] & GS_COL_MASK) : -1;
+            const bool ff = valid && (code[u] & GS_COL_FRESH), own = valid && (code[u] & GS_COL_OWN);
+            const bool nw_ = a.backward ? (own && !ff && c != row) : ff;  // a value of THIS sweep is needed
+            use[u] = valid && (!a.zero_guess || ff);
+            const bool mine = valid && c == prev_row, hit = valid && c == pc[u];
+            const bool reg = mine || hit;
+            xv[u] = mine ? prev_val : (hit ? px[u] : 0.0);
+            fresh[u] = nw_ && !reg;
+            w0[u] = w1[u] = 0ull;
+            // Both loads are PREDICATED instructions, not branches: the destination registers are initialised above and keep
+            // their value in the lanes that do not load.  (With `if (fresh) load; else w = 0` the compiler zeroes the registers
+            // in the else path AFTER the load was issued for the other lanes: a write-after-write on the warp-wide scoreboard,
+            // i.e. one full memory round trip per entry slot whenever the lanes of a slice disagree — rows on a box face
+            // have fewer entries than their neighbours, so some lane always does.)
+            const int32_t cs = valid ? c : 0;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t@p ld.relaxed.gpu.global.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;\n\t}"
+                         : "+l"(w0[u]), "+l"(w1[u]) : "l"(a.xe + cs), "l"(keep), "r"((unsigned)fresh[u]) : "memory");
+            const unsigned ld_old = use[u] && !nw_ && !reg;  // OLD value: L1 allowed
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.f64 %0, [%1];\n\t}" : "+d"(xv[u]) : "l"(a.x + cs), "r"(ld_old) : "memory");
+          }
+#pragma unroll
+          for (int u = 0; u < B; ++u) {
+            if (fresh[u]) {
+              const int32_t c = code[u] & GS_COL_MASK;
+              long long t0 = 0;
+              if (TRACE) {
+                if (!tk_first) {
+                  asm volatile("" ::"l"(w0[u]));
+                  tk_first = clock64() - tk1;
+                }
+                tk_nfresh++;
+              }
+              while ((unsigned)(w0[u] >> 32) != epoch || (unsigned)(w1[u] >> 32) != epoch) {
+                if (TRACE) tk_npoll++;
+                asm volatile("ld.relaxed.gpu.global.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(w0[u]), "=l"(w1[u]) : "l"(a.xe + c), "l"(keep) : "memory");
+                if (!t0) {
+                  t0 = clock64();
+                } else if (clock64() - t0 > GS_SPIN_LIMIT) {
+                  *a.err = 3;
+                  break;
+                }
+              }
+              xv[u] = __longlong_as_double((long long)((w1[u] << 32) | (w0[u] & 0xffffffffull)));
+            }
+          }
+          if (TRACE) {
+            const long long t3 = clock64();
+#pragma unroll
+            for (int u = 0; u < B; ++u) asm volatile("" ::"d"(xv[u]));
+            const long long t2 = clock64();
+            tk_gather += t2 - tk1;
+            tk_old += t2 - t3;
+            tk_firstsum += tk_first;
+            tk_first = 0;
+            tk1 = t2;
+          }
+#pragma unroll
+          for (int u = 0; u < B; ++u) {  // the window of the next row, then s -= a*x[col] in CSR order
+            if (W ? (k0 + u < W) : (k0 + u < WD)) {
+              sc[(k0 + u) * 32] = code[u] >= 0 ? (code[u] & GS_COL_MASK) : -1;
+              sx[(k0 + u) * 32] = xv[u];
+            }
+            const double t2 = __dsub_rn(s, __dmul_rn(v[u], xv[u]));
+            s = use[u] ? t2 : s;
+            const bool dg = code[u] >= 0 && (code[u] & GS_COL_MASK) == row;
+            d = dg ? v[u] : d;
+            xold = dg ? xv[u] : xold;
+          }
+          if (TRACE) {
+            asm volatile("" ::"d"(s));
+            tk_chain += clock64() - tk1;
+          }
+        }
+        if (!a.zero_guess) s = __dadd_rn(s, __dmul_rn(d, xold));  // s += d*x[row]
+        s = __ddiv_rn(s, d);
+        gs_publish(a.xe + row, a.x + row, s, epoch, keep);
+        prev_row = row;
+        prev_val = s;
+      }
+      row = row_n;
+      bv = row >= 0 ? __ldg(a.b + row) : 0.0;
+      __syncwarp();
+      if (TRACE) {
+        tk_rest += clock64() - tk0;
+        if ((st & 63) == 63 && lane == 8 && (t == 0 || t == 40 || t == 300)) {
+          printf("gs-strip task %lld step %lld (64 steps, lane 8): load %lld gather+poll %lld (first pair back after %lld, waiting for OLD values after the polls %lld; %d pair loads, %d re-polls) chain %lld total %lld cycles per step\n", (long long)t, (long long)st,
+                 tk_load / 64, tk_gather / 64, tk_firstsum / 64, tk_old / 64, tk_nfresh, tk_npoll, tk_chain / 64, tk_rest / 64);
+          tk_load = tk_gather = tk_chain = tk_rest = tk_firstsum = tk_old = 0;
+          tk_npoll = tk_nfresh = 0;
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ the multi-colour kernel: SELL slices through a TMA ring
 // One launch per colour, like k_gs_sell<W, 0>, but the matrix never passes through registers on its way in: the slices
 // of a colour are contiguous in the SELL copy, so a persistent CTA streams tiles of NW slices (values + column words,
@@ -1205,6 +1419,72 @@ static int gs_build_sell(pa_ctx *c, const MatPart &m, GsPart &p, const int32_t *
   return PA_OK;
 }
 
+// strip order of a box: slice (task, step) holds rows (step - w1*lane, 32*Y + lane, z); -1 where that leaves the box
+__global__ void k_rows_strip(int32_t *rows, int64_t nslices, int64_t nsteps, const int32_t *task_y, const int32_t *task_z, int64_t nx, int64_t ny, int w1) {
+  for (int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pos < nslices * 32; pos += (int64_t)gridDim.x * blockDim.x) {
+    const int lane = (int)(pos & 31);
+    const int64_t sl = pos >> 5, task = sl / nsteps, st = sl % nsteps;
+    const int64_t y = 32 * (int64_t)task_y[task] + lane, x = st - (int64_t)w1 * lane;
+    rows[pos] = (y < ny && x >= 0 && x < nx) ? (int32_t)(x + nx * (y + ny * (int64_t)task_z[task])) : -1;
+  }
+}
+
+static int gs_make_strip_order(pa_ctx *c, const MatPart &m, GsPart &p, const int32_t *d_lev, GsOrder **out) {
+  const int64_t nx = p.dims[0], ny = p.dims[1], nz = p.dims[2];
+  const int w1 = (int)p.w[1], w2 = (int)p.w[2];
+  const int64_t nstrips = (ny + 31) / 32;
+  GsOrder *o = new GsOrder();
+  o->nlev = p.nlev;
+  o->W = std::max(p.maxlen, 1);
+  o->ntask = (int)(nstrips * nz);
+  o->nsteps = nx + 31 * (int64_t)w1;
+  std::vector<std::array<int64_t, 3>> key((size_t)o->ntask);  // (start level, strip, plane)
+  for (int64_t z = 0; z < nz; ++z)
+    for (int64_t Y = 0; Y < nstrips; ++Y) key[(size_t)(z * nstrips + Y)] = {32 * w1 * Y + w2 * z, Y, z};
+  std::sort(key.begin(), key.end());
+  std::vector<int32_t> ty((size_t)o->ntask), tz((size_t)o->ntask);
+  for (int q = 0; q < o->ntask; ++q) {
+    ty[q] = (int32_t)key[q][1];
+    tz[q] = (int32_t)key[q][2];
+  }
+  const int64_t nslices = (int64_t)o->ntask * o->nsteps;
+  o->npad = nslices * 32;
+  int32_t *d_ty = nullptr, *d_tz = nullptr;
+  cudaError_t e = cudaMalloc((void **)&d_ty, ty.size() * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_tz, tz.size() * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&o->d_rows, o->npad * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&o->d_cols, (size_t)o->npad * o->W * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&o->d_vals, (size_t)o->npad * o->W * sizeof(double));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(d_ty); cudaFree(d_tz);
+    gs_free_order(o);
+    pa_set_error("pa_gs: cannot allocate the strip-ordered matrix copy (%.2f GiB): %s", (double)nslices * 32 * p.maxlen * 12 / 1073741824.0, cudaGetErrorString(e));
+    return PA_ENOMEM;
+  }
+  PA_CUDA(cudaMemcpyAsync(d_ty, ty.data(), ty.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  PA_CUDA(cudaMemcpyAsync(d_tz, tz.data(), tz.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  k_rows_strip<<<148 * 8, 256, 0, c->stream>>>(o->d_rows, nslices, o->nsteps, d_ty, d_tz, nx, ny, w1);
+  if (m.ptr64)
+    k_gs_build_sell<int64_t><<<148 * 8, 256, 0, c->stream>>>((const int64_t *)m.d_rowptr, m.d_colval, m.d_nzval, o->d_rows, o->npad, o->W, p.n, d_lev, o->d_cols, o->d_vals);
+  else
+    k_gs_build_sell<int32_t><<<148 * 8, 256, 0, c->stream>>>((const int32_t *)m.d_rowptr, m.d_colval, m.d_nzval, o->d_rows, o->npad, o->W, p.n, d_lev, o->d_cols, o->d_vals);
+  PA_CUDA(cudaGetLastError());
+  PA_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_ty); cudaFree(d_tz);
+  c->launches += 2;
+  *out = o;
+  return PA_OK;
+}
+
+// tasks that can be co-dependent: strips x (32*w1/w2) start levels; the grid must hold that many warps (see k_gs_strip)
+static bool gs_strip_ok(const GsPart &p, const MatPart &m, int64_t n_local_cols, int64_t resident_warps) {
+  if (!p.geom || p.maxlen < 1 || p.maxlen > 32 || m.nnz == 0 || n_local_cols >= (1ll << 29)) return false;
+  const int64_t nstrips = (p.dims[1] + 31) / 32;
+  const int64_t nslices = nstrips * p.dims[2] * (p.dims[0] + 31 * p.w[1]);
+  return nstrips * (32 * p.w[1] / std::max<int64_t>(p.w[2], 1) + 1) * 2 <= resident_warps && nslices * 32 < (1ll << 31) * 4;
+}
+
 static bool gs_sell_ok(const GsPart &p, const MatPart &m, int64_t n_local_cols) {
   return p.maxlen >= 1 && p.maxlen <= 32 && m.nnz > 0 && n_local_cols < (1ll << 29);
 }
@@ -1362,6 +1642,10 @@ extern "C" int pa_gs_commit(pa_gs *g) {
     if (gs_sell_ok(p, m, g->A->cols->parts[k].n_local) && pa_knob(c, "gs_kernel", 0) == 2) {
       PA_TRY(gs_build_sell(c, m, p, d_lev, d_lev2, d_rows1, cnt, p.nlev, &p.ord[0]));
     }
+    // gs_kernel = 3: strip order (a warp owns 32 grid lines of a plane) + k_gs_strip
+    if (pa_knob(c, "gs_kernel", 0) == 3 && gs_strip_ok(p, m, g->A->cols->parts[k].n_local, 148 * 2 * (GS_THREADS / 32))) {
+      PA_TRY(gs_make_strip_order(c, m, p, d_lev, &p.ord[0]));
+    }
     // batch kernel tables (only when that kernel is selected: it is not the default): level l occupies
     // ceil(cnt_l / GSB_ROWS) consecutive batches
     if (p.maxlen <= 32 && m.nnz > 0 && pa_knob(c, "gs_kernel", 0) == 1) {
@@ -1427,7 +1711,8 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
     const MatPart &m = g->A->parts[k];
     if (p.n == 0) continue;
     p.epoch += 1;
-    GsOrder *o = g->order == PA_GS_MULTICOLOR ? p.ord[1] : (pa_knob(c, "gs_kernel", 0) == 2 ? p.ord[0] : nullptr);
+    const int64_t gsk = pa_knob(c, "gs_kernel", 0);
+    GsOrder *o = g->order == PA_GS_MULTICOLOR ? p.ord[1] : ((gsk == 2 || gsk == 3) ? p.ord[0] : nullptr);
     PA_CHECK(g->order != PA_GS_MULTICOLOR || o, PA_ESTATE, "gs_sweep: the multi-colour copy of the matrix is missing");
     if (o) {
       PA_CHECK(!(zero_guess && backward), PA_ESTATE, "gs_sweep: the zero-guess sweep is a forward sweep");
@@ -1498,6 +1783,24 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
           kern<<<(unsigned)grid, GS_THREADS, 0, c->stream>>>(a);
           c->launches++;
         }
+      } else if (o->ntask) {
+        void (*kern)(const GsSellArgs, int, int64_t) = o->W == 27 ? (pa_knob(c, "gs_trace", 0) ? k_gs_strip<27, true> : k_gs_strip<27>)
+                                                                 : (o->W == 7 ? k_gs_strip<7> : k_gs_strip<0>);
+        const size_t smem = GS_STRIP_SMEM(o->W);
+        a.gate = (int)pa_knob(c, "gs_strip_prefetch", 1);  // 1 = bulk L2 prefetch of the next slice, 2 = per-line prefetches, 0 = none
+        PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int ctas_per_sm = 0;
+        PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, GS_THREADS, smem));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        const int64_t cap = pa_knob(c, "gs_ctas", 0);
+        if (cap > 0 && cap < ctas_per_sm) ctas_per_sm = (int)cap;
+        a.g0 = 0;
+        a.g1 = a.ngroups;
+        // all CTAs co-resident (see k_gs_strip): the grid never exceeds what the device holds at once
+        const int64_t grid = std::min<int64_t>((o->ntask + wpc - 1) / wpc, (int64_t)nsm * ctas_per_sm);
+        PA_CHECK(gs_strip_ok(p, m, g->A->cols->parts[k].n_local, grid * wpc) || grid * wpc >= o->ntask, PA_ESTATE, "gs_sweep: the strip kernel needs more resident warps than the device holds");
+        kern<<<(unsigned)grid, GS_THREADS, smem, c->stream>>>(a, o->ntask, o->nsteps);
+        c->launches++;
       } else {
         // gs_sell_mode 3 (default): staged dataflow kernel (relaxed level gate + per-row pairs); 2: fenced level gate; 1: per-row pairs only
         const int mode = (int)pa_knob(c, "gs_sell_mode", 3);

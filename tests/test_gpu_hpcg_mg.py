@@ -22,17 +22,19 @@ def _vec(pa, rows, vals):
 
 # every variant of the sweep kernel: default choice, warp-per-row dataflow kernel with 0 (any row length) / 4 / 8 / 16 / 32 lanes per
 # row, and the batch kernel (32 rows of one level per warp) with and without the L2 prefetch
-@pytest.mark.parametrize("lanes", [None, "sell-flow", "sell-rows", "sell-gate", 0, 4, 8, 16, 32, "batch", "batch-noprefetch"])
+@pytest.mark.parametrize("lanes", [None, "strip", "sell-flow", "sell-rows", "sell-gate", 0, 4, 8, 16, 32, "batch", "batch-noprefetch"])
 @pytest.mark.parametrize("npd,nloc,hint", [((2, 2, 1), (8, 6, 4), True), ((1, 2, 2), (4, 4, 6), False), ((1, 1, 1), (10, 9, 8), True),
                                            ((2, 1, 1), (40, 32, 24), True)])
 def test_symmetric_gauss_seidel_is_bit_exact(pa, npd, nloc, hint, lanes):
     """smooth! (smoothers.jl:98-125): wavefront sweeps == the reference's sequential per-part sweeps, bit for bit."""
-    if nloc[0] >= 40 and lanes not in (None, "sell-flow", "sell-rows", "sell-gate", 16, "batch", "batch-noprefetch"):
+    if nloc[0] >= 40 and lanes not in (None, "strip", "sell-flow", "sell-rows", "sell-gate", 16, "batch", "batch-noprefetch"):
         pytest.skip("the large case runs the default, the 16-lane and the batch kernels")
     lev = hpcg_mg.Level(*nloc, npd)
     P = len(lev.part)
     b = pa.CUDAArray(P, arena_bytes=32 << 20)
-    if lanes in ("sell-flow", "sell-rows", "sell-gate"):  # thread-per-row kernels on the sweep-ordered SELL copy: staged dataflow / per-row pairs / fenced gate
+    if lanes == "strip":  # a warp owns 32 grid lines of a plane (k_gs_strip); without the box hint the default kernel runs
+        b.set_knob("gs_kernel", 3)
+    elif lanes in ("sell-flow", "sell-rows", "sell-gate"):  # thread-per-row kernels on the sweep-ordered SELL copy: staged dataflow / per-row pairs / fenced gate
         b.set_knob("gs_kernel", 2)
         b.set_knob("gs_sell_mode", {"sell-flow": 3, "sell-rows": 1, "sell-gate": 2}[lanes])
     elif isinstance(lanes, str):
@@ -130,7 +132,7 @@ def _smooth_and_compare(pa, lev, A, gs, seed):
         x.free(); bv.free()
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 2])  # 0 = warp-per-row dataflow kernel (default), 1 = batch kernel, 2 = SELL thread-per-row kernel
+@pytest.mark.parametrize("kernel", [0, 1, 2, 3])  # 0 = warp-per-row dataflow kernel (default), 1 = batch kernel, 2 = SELL thread-per-row kernel, 3 = strip kernel
 @pytest.mark.parametrize("case", ["fdm7-box", "fdm7-generic", "fem9"])
 def test_gauss_seidel_on_short_rows_is_bit_exact(pa, case, kernel):
     """Rows of <= 8 entries (7-pt gallery operator, closed-form and host-computed levels) and <= 16 entries (the Q1 FEM
