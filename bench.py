@@ -533,6 +533,19 @@ def run_ours(args):
     windows.append(w)
     torch.cuda.synchronize()
     err = max(err, float(np.abs(hbuf[(args.steps - 1) % 2][1].numpy()[:n_rows] - 1.0).max()))
+    # the floor the host side sets: the same copies (b up, x down, both directions at once, all ranks at once) with no solve in
+    # between.  On a box whose GPUs share one host memory system this grows with N and bounds e2e from below.
+    def transfers_only(K):
+        s_h2d.wait_stream(stream); s_d2h.wait_stream(stream)
+        for sidx in range(K):
+            q = sidx % 2
+            pa._capi.check(L.pa_vec_upload_async(pairs[q][1].h, 0, hbuf[q][0].data_ptr(), n_local, s_h2d.cuda_stream))
+            pa._capi.check(L.pa_vec_download_async(pairs[q][0].h, 0, hbuf[q][1].data_ptr(), n_local, s_d2h.cuda_stream))
+        stream.wait_stream(s_d2h); stream.wait_stream(s_h2d)
+    transfers_only(1)
+    ms_xfer, w = timed(lambda: transfers_only(args.steps))
+    windows.append(w)
+    torch.cuda.synchronize()
     e2e_value = flops_iter * args.iters / (ms_e2e / args.steps * 1e-3) / 1e9
     e2e_serial_value = flops_iter * args.iters / (ms_e2e_serial / args.steps * 1e-3) / 1e9
     h2d, d2h = n_local * 8, n_local * 8 + (args.iters + 1) * 8
@@ -623,7 +636,10 @@ def run_ours(args):
                          "cg_iter_bytes_model": B + 120 * n_rows, "cg_frac_of_peak": (B + 120 * n_rows) * args.iters / (ms_step * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                     "schedule": "pipelined: upload of the next b and download of the previous x on copy streams, overlapped with the running solve",
-                    "serial_value": e2e_serial_value, "serial_ms_per_step": ms_e2e_serial / args.steps},
+                    "serial_value": e2e_serial_value, "serial_ms_per_step": ms_e2e_serial / args.steps,
+                    "transfers_only_ms_per_step": ms_xfer / args.steps,
+                    "host_link_gbs_per_gpu": (h2d + d2h) / (ms_xfer / args.steps) / 1e6, "host_link_gbs_all_gpus": N * (h2d + d2h) / (ms_xfer / args.steps) / 1e6,
+                    "note": "transfers_only = the same H2D + D2H copies of every rank at once with no solve in between: the floor the host memory system sets for e2e at this N"},
             "gpu_launches": int(launches), "launches_per_cg_iteration": launches / (args.steps * args.iters), "spmv_region_launches": int(spmv_launches),
             "clocks": clocks, "cpu_baseline": cpu,
         }
@@ -649,7 +665,9 @@ def mg_section(pa, backend, n, sh, timed, windows, all_sum, peak):
     mg_flops = sum(10 * z for z in nnz_l[1:]) + 4 * nnz_l[0]
     ind = P.A.cols.indices[0]
     sweep_bytes = 2 * (spmv_bytes(ind.n_own, P.A.nnz(0), ind.n_local) + 8 * ind.n_own)  # forward + backward: matrix, x, b in, x out
-    out = {"workload": f"HPCG 27-pt {n}^3 per GPU, parts {sh}, 4-level MG (symmetric Gauss-Seidel), ref_cg! Pl=MG, {mg_iters} iterations"}
+    out = {"workload": f"HPCG 27-pt {n}^3 per GPU, parts {sh}, 4-level MG (symmetric Gauss-Seidel), ref_cg! Pl=MG, {mg_iters} iterations",
+           "residual_restrict": "the residual between the smoothers is computed at the injection points only (same bits as mul_no_lat! + restrict!)",
+           "symgs_bytes_model": "2 x (12*nnz + rowptr + 8*n_cols + 8*n + 8*n) per symmetric application (matrix, x, b in, x out, both sweeps)"}
     for order in ("lexicographic", "multicolor"):
         P.set_order(order)
         pa.ref_cg_pc_(xm, P.A, P.b, P, maxiter=2)

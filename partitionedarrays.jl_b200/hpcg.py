@@ -137,7 +137,8 @@ def ref_cg_pc_(x: PVector, A: PSparseMatrix, b: PVector, Pl: Optional[MgPrecondi
 def smoother_name(P: "MgPreconditioner") -> str:
     """Which Gauss-Seidel schedule a preconditioner runs (reported by bench.py)."""
     if P.order == "multicolor":
-        return "multi-colour Gauss-Seidel (8 colours, one launch per colour; convergence-level parity: different iterates than the reference)"
+        return ("multi-colour Gauss-Seidel (8 colours, one launch per colour, SELL-32 slices streamed through a TMA ring; convergence-level "
+                "parity: different iterates than the reference)")
     return "bit-exact wavefront Gauss-Seidel (same iterates as the reference's sequential sweeps)"
 
 

@@ -2,7 +2,9 @@
   1. 2 parts x-split on ONE GPU (400^3 rows each): mul! default (k_consistent_sync is not used with 2 local parts: k_consistent
      + k_spmv_tma MODE 0) and PA_SPMV_FUSED_EXCHANGE (k_spmv_tma MODE 4, per-tile ghost gating)
   2. 7-pt 512^3, 1 part: 3 iterations of the folded CG (k_cg_direction, k_spmv_tma with the folded dot epilogue, k_cg_update_fold)
-  3. 27-pt 256^3: one symmetric Gauss-Seidel application in both orders (k_gs_flow_pipe; k_gs_sell<27,0> per colour)"""
+  3. 27-pt 256^3: one symmetric Gauss-Seidel application in both orders (k_gs_flow_pipe; k_gs_sell<27,0> per colour)
+  4. "mg": 27-pt GS_N^3 (default 512), 2 levels, multi-colour order: one V-cycle (k_gs_color_tma per colour, k_residual_restrict,
+     k_prolong) — the kernels of the second half of round 2"""
 import os
 import sys
 
@@ -42,5 +44,13 @@ if which in ("all", "gs"):
     gs.smooth_(x, rhs, False)
     gs.set_order("multicolor")
     gs.smooth_(x, rhs, False)
+    b.sync()
+    b.close()
+if which == "mg":
+    n = int(os.environ.get("GS_N", "512"))
+    b = pa.CUDAArray(1, arena_bytes=14 * (n + 2) ** 3 * 8)
+    P = pa.pc_setup(b, 2, n, n, n, 1, 1, 1, order="multicolor")
+    c = pa.pzeros(P.A.cols)
+    P.ldiv_(c, P.b)
     b.sync()
     b.close()
