@@ -169,6 +169,12 @@ struct MatPart {
   unsigned long long *d_arrive = nullptr;  // fused consistent! (SpMV MODE 4): CTAs counted in, over all launches
   std::map<int, unsigned char *> tile_ghost;  // MODE 4: per tile size, "tile holds a ghost column" flags
   int64_t arrive_grid = 0;
+  // row patterns (column stream compression of the TMA SpMV): pat[row] = id of the row's (length, column - row) tuple in
+  // ptab, 255 = the row reads its columns from colval.  0 = not tried, 1 = available, -1 = does not pay for this matrix
+  int pat_state = 0;
+  unsigned char *d_pat = nullptr;
+  int32_t *d_ptab = nullptr;  // [npat][pat_w]
+  int npat = 0, pat_w = 0;
   // COO pattern cache (the reference's K of sparse_matrix(...; reuse=true)): sorted permutation + segment starts
   int32_t *d_coo_perm = nullptr, *d_coo_seg = nullptr;
   unsigned char *d_coo_valid = nullptr;

@@ -15,6 +15,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <map>
 #include <cstdio>
 #include <array>
 
@@ -78,6 +79,13 @@ struct GsOrder {
   uint32_t *d_lev_tot = nullptr;          // [nlev] (fenced gate variant)
   unsigned long long *d_done2 = nullptr;  // [nlev]
   unsigned long long sweeps = 0, sweeps2 = 0;
+  // row patterns of the colour kernel (one byte per row instead of a column word per entry): per level a table of
+  // [npat][W] packed words ((col - row) mod 2^29 | flags, -1 = empty slot); pat[pos] = id within the row's level, 255 = none
+  unsigned char *d_pat = nullptr;      // [npad]
+  int32_t *d_ptab = nullptr;           // tables of all levels, back to back
+  std::vector<int> lev_npat;           // [nlev]
+  std::vector<int64_t> lev_ptab_off;   // [nlev] first word of the level's table
+  bool patterns = false;
   // strip order (k_gs_strip): ntask tasks of nsteps slices each, task-major
   int ntask = 0;
   int64_t nsteps = 0;
@@ -623,6 +631,10 @@ struct GsSellArgs {
   int gate, trace;
   const uint32_t *lev_tot;   // MODE 2: slices per level, one counter per level
   unsigned long long *done2;
+  // colour kernel with row patterns
+  const unsigned char *pat;
+  const int32_t *ptab;       // the launch's level
+  int npat;
 };
 
 // minBlocksPerSM is explicit: with maxThreads alone ptxas aims at full occupancy and sinks every load next to its use,
@@ -969,16 +981,22 @@ __global__ void __launch_bounds__(GS_THREADS, 2) k_gs_strip(const GsSellArgs a, 
 // free), gather x and run the ordered chain.  Only the x gathers, b and the row ids go through the LSU.
 // Rows of a colour never read a value another row of the colour writes, so x is read with plain loads and the slices are
 // walked in ascending order in both sweep directions (the order inside a colour is immaterial: same bits either way).
-template <int W, int B>
+// PAT: the column words of a slice (a third of the stream) are replaced by ONE BYTE per row, the id of the row's pattern
+// (column - row and flags of every slot) in a per-colour table held in shared memory; rows without a table entry (id 255:
+// ghost columns, rare box positions) read their column words from global memory.  Same words, same arithmetic.
+template <int W, int B, bool PAT = false>
 __global__ void __launch_bounds__(288, 2) k_gs_color_tma(const GsSellArgs a, const int NW, const int S) {
   extern __shared__ __align__(128) unsigned char gsc_smem[];
   const int WD = W ? W : a.W;
   const int tile_e = NW * WD * 32;  // entries per stage
   double *val_s = reinterpret_cast<double *>(gsc_smem);
-  int32_t *col_s = reinterpret_cast<int32_t *>(val_s + (size_t)S * tile_e);
-  uint64_t *full = reinterpret_cast<uint64_t *>(col_s + (size_t)S * tile_e);
+  int32_t *col_s = reinterpret_cast<int32_t *>(val_s + (size_t)S * tile_e);  // PAT: pattern ids, NW*32 bytes per stage
+  uint64_t *full = reinterpret_cast<uint64_t *>(col_s + (size_t)S * (PAT ? NW * 8 : tile_e));
   uint64_t *empty = full + S;
+  int32_t *ptab_s = reinterpret_cast<int32_t *>(empty + S);
   const int tid = threadIdx.x, nthr_c = NW * 32;
+  if (PAT)
+    for (int i = tid; i < a.npat * WD; i += blockDim.x) ptab_s[i] = a.ptab[i];
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full + s, 1);
@@ -999,10 +1017,16 @@ __global__ void __launch_bounds__(288, 2) k_gs_color_tma(const GsSellArgs a, con
         if (s == S) { s = 0; ph ^= 1u; }
         if (j >= S) mbar_wait(empty + s, ph);
         const int64_t g = a.g0 + (first + j * stride) * NW;
-        const uint32_t ne = (uint32_t)(min((int64_t)NW, a.g1 - g) * WD * 32);
-        mbar_expect_tx(full + s, ne * 12u);
-        tma_load_1d(val_s + (size_t)s * tile_e, a.vals + g * WD * 32, ne * 8u, full + s, pol);
-        tma_load_1d(col_s + (size_t)s * tile_e, a.cols + g * WD * 32, ne * 4u, full + s, pol);
+        const uint32_t nsl_t = (uint32_t)min((int64_t)NW, a.g1 - g), ne = nsl_t * WD * 32;
+        if (PAT) {
+          mbar_expect_tx(full + s, ne * 8u + nsl_t * 32u);
+          tma_load_1d(val_s + (size_t)s * tile_e, a.vals + g * WD * 32, ne * 8u, full + s, pol);
+          tma_load_1d(reinterpret_cast<unsigned char *>(col_s) + (size_t)s * NW * 32, a.pat + g * 32, nsl_t * 32u, full + s, pol);
+        } else {
+          mbar_expect_tx(full + s, ne * 12u);
+          tma_load_1d(val_s + (size_t)s * tile_e, a.vals + g * WD * 32, ne * 8u, full + s, pol);
+          tma_load_1d(col_s + (size_t)s * tile_e, a.cols + g * WD * 32, ne * 4u, full + s, pol);
+        }
       }
     }
     return;
@@ -1027,6 +1051,10 @@ __global__ void __launch_bounds__(288, 2) k_gs_color_tma(const GsSellArgs a, con
       const double *vs = val_s + (size_t)s * tile_e + wrp * WD * 32 + lane;
       const int32_t *cs = col_s + (size_t)s * tile_e + wrp * WD * 32 + lane;
       double sum = bv, d = 0.0, xo = 0.0;
+      const unsigned pid = PAT ? (unsigned)reinterpret_cast<const unsigned char *>(col_s)[(size_t)s * NW * 32 + wrp * 32 + lane] : 0u;
+      const bool esc = PAT && pid == 255u;
+      const int32_t *tab = ptab_s + (esc ? 0u : pid) * (unsigned)WD;
+      const int32_t *gcode = a.cols + (a.g0 + (first + j * stride) * NW + wrp) * WD * 32 + lane;  // this row's column words in HBM
 #pragma unroll 1
       for (int k0 = 0; k0 < WD; k0 += B) {
         int32_t code[B];
@@ -1034,7 +1062,13 @@ __global__ void __launch_bounds__(288, 2) k_gs_color_tma(const GsSellArgs a, con
 #pragma unroll
         for (int u = 0; u < B; ++u) {
           const int kk = W ? min(k0 + u, W - 1) : min(k0 + u, WD - 1);  // past the end: a redundant read of the last slot
-          code[u] = cs[kk * 32];
+          if (PAT) {
+            const int32_t pk = tab[kk];
+            code[u] = pk < 0 ? -1 : (((row + (pk & GS_COL_MASK)) & GS_COL_MASK) | (pk & (GS_COL_FRESH | GS_COL_OWN)));
+            if (esc) code[u] = __ldg(gcode + kk * 32);
+          } else {
+            code[u] = cs[kk * 32];
+          }
           v[u] = vs[kk * 32];
         }
 #pragma unroll
@@ -1302,6 +1336,8 @@ static void gs_free_order(GsOrder *&o) {
   cudaFree(o->d_lev_first);
   cudaFree(o->d_lev_tot);
   cudaFree(o->d_done2);
+  cudaFree(o->d_pat);
+  cudaFree(o->d_ptab);
   delete o;
   o = nullptr;
 }
@@ -1489,6 +1525,104 @@ static bool gs_sell_ok(const GsPart &p, const MatPart &m, int64_t n_local_cols) 
   return p.maxlen >= 1 && p.maxlen <= 32 && m.nnz > 0 && n_local_cols < (1ll << 29);
 }
 
+// ---- row patterns of a SELL copy, per level (colour)
+__device__ __forceinline__ int32_t gs_pack_code(int32_t code, int32_t row) {
+  return code < 0 ? -1 : ((((code & GS_COL_MASK) - row) & GS_COL_MASK) | (code & (GS_COL_FRESH | GS_COL_OWN)));
+}
+__global__ void k_gs_pat_sample(const int32_t *rows, const int32_t *cols, int W, int64_t pos0, int64_t npos, int64_t nsample, int32_t *out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsample; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t stride = npos / nsample > 0 ? npos / nsample : 1;
+    int64_t q = i * stride + (int64_t)((unsigned long long)(i * 2654435761ull) % (unsigned long long)stride);
+    if (q >= npos) q = npos - 1;
+    const int64_t pos = pos0 + q;
+    const int32_t row = rows[pos];
+    int32_t *o = out + i * (1 + W);
+    o[0] = row >= 0 ? 1 : 0;
+    for (int k = 0; k < W; ++k) o[1 + k] = row >= 0 ? gs_pack_code(cols[((pos >> 5) * W + k) * 32 + (pos & 31)], row) : 0;
+  }
+}
+__global__ void k_gs_pat_assign(const int32_t *rows, const int32_t *cols, int W, int64_t pos0, int64_t npos, const int32_t *ptab, int npat, unsigned char *pat,
+                                unsigned long long *n_esc) {
+  unsigned long long esc = 0;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < npos; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pos = pos0 + q;
+    const int32_t row = rows[pos];
+    int id = 255;
+    if (row >= 0) {
+      const int32_t *cp = cols + ((pos >> 5) * W) * 32 + (pos & 31);
+      const int32_t first = gs_pack_code(cp[0], row), last = gs_pack_code(cp[(W - 1) * 32], row);
+      for (int t = 0; t < npat && id == 255; ++t) {
+        if (ptab[t * W] != first || ptab[t * W + W - 1] != last) continue;
+        bool same = true;
+        for (int k = 1; k < W - 1; ++k) same &= ptab[t * W + k] == gs_pack_code(cp[k * 32], row);
+        if (same) id = t;
+      }
+      esc += id == 255;
+    }
+    pat[pos] = (unsigned char)id;
+  }
+  if (esc) atomicAdd(n_esc, esc);
+}
+
+static int gs_build_patterns(pa_ctx *c, GsOrder *o, int64_t n_rows) {
+  const int W = o->W, nlev = o->nlev;
+  o->patterns = false;
+  if (W < 2 || n_rows < pa_knob(c, "gs_pattern_min_rows", 4096)) return PA_OK;
+  const int max_pat = std::min(254, (16 * 1024) / (W * 4));  // the level's table lives in shared memory
+  o->lev_npat.assign(nlev, 0);
+  o->lev_ptab_off.assign(nlev, 0);
+  std::vector<int32_t> all;
+  const int64_t nsample = 16384;
+  int32_t *d_s = nullptr;
+  PA_CUDA(cudaMalloc((void **)&d_s, nsample * (1 + W) * sizeof(int32_t)));
+  std::vector<int32_t> hs((size_t)nsample * (1 + W));
+  for (int l = 0; l < nlev; ++l) {
+    const int64_t pos0 = o->lev_group[l] * 32, npos = (o->lev_group[l + 1] - o->lev_group[l]) * 32;
+    o->lev_ptab_off[l] = (int64_t)all.size();
+    if (npos == 0) continue;
+    const int64_t ns = std::min<int64_t>(nsample, npos);
+    k_gs_pat_sample<<<64, 256, 0, c->stream>>>(o->d_rows, o->d_cols, W, pos0, npos, ns, d_s);
+    PA_CUDA(cudaMemcpyAsync(hs.data(), d_s, (size_t)ns * (1 + W) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    PA_CUDA(cudaStreamSynchronize(c->stream));
+    std::map<std::vector<int32_t>, int64_t> freq;
+    for (int64_t i = 0; i < ns; ++i) {
+      const int32_t *q = hs.data() + i * (1 + W);
+      if (q[0]) freq[std::vector<int32_t>(q + 1, q + 1 + W)]++;
+    }
+    std::vector<std::pair<int64_t, std::vector<int32_t>>> order;
+    for (auto &kv : freq) order.emplace_back(-kv.second, kv.first);
+    std::sort(order.begin(), order.end());
+    if ((int)order.size() > max_pat) order.resize(max_pat);
+    o->lev_npat[l] = (int)order.size();
+    for (auto &e : order) all.insert(all.end(), e.second.begin(), e.second.end());
+  }
+  cudaFree(d_s);
+  if (all.empty()) return PA_OK;
+  unsigned long long *d_esc = nullptr, h_esc = 0;
+  PA_CUDA(cudaMalloc((void **)&o->d_ptab, all.size() * sizeof(int32_t)));
+  PA_CUDA(cudaMalloc((void **)&o->d_pat, (size_t)o->npad + 512));
+  PA_CUDA(cudaMalloc((void **)&d_esc, sizeof(unsigned long long)));
+  PA_CUDA(cudaMemcpyAsync(o->d_ptab, all.data(), all.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  PA_CUDA(cudaMemsetAsync(o->d_pat, 255, (size_t)o->npad + 512, c->stream));
+  PA_CUDA(cudaMemsetAsync(d_esc, 0, sizeof(unsigned long long), c->stream));
+  for (int l = 0; l < nlev; ++l) {
+    const int64_t pos0 = o->lev_group[l] * 32, npos = (o->lev_group[l + 1] - o->lev_group[l]) * 32;
+    if (npos == 0 || o->lev_npat[l] == 0) continue;
+    k_gs_pat_assign<<<148 * 8, 256, 0, c->stream>>>(o->d_rows, o->d_cols, W, pos0, npos, o->d_ptab + o->lev_ptab_off[l], o->lev_npat[l], o->d_pat, d_esc);
+  }
+  PA_CUDA(cudaMemcpyAsync(&h_esc, d_esc, sizeof(h_esc), cudaMemcpyDeviceToHost, c->stream));
+  PA_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_esc);
+  c->launches += 2 * nlev;
+  if ((double)h_esc > 0.08 * (double)n_rows) {  // too many rows without a pattern: keep the column words
+    cudaFree(o->d_pat); cudaFree(o->d_ptab);
+    o->d_pat = nullptr; o->d_ptab = nullptr;
+    return PA_OK;
+  }
+  o->patterns = true;
+  return PA_OK;
+}
+
 // the multi-colour order of a box operator (built on first use: it costs a second copy of the matrix)
 static int gs_make_color_order(pa_gs *g, int k) {
   pa_ctx *c = g->A->ctx;
@@ -1518,6 +1652,7 @@ static int gs_make_color_order(pa_gs *g, int k) {
   int rc = gs_build_sell(c, m, p, d_lev, d_lev2, d_rows1, cnt, nlev, &p.ord[1]);
   cudaFree(d_tmp); cudaFree(d_lev); cudaFree(d_lev2); cudaFree(d_rows0); cudaFree(d_rows1); cudaFree(d_cnt);
   c->launches += 3;
+  if (rc == PA_OK && pa_knob(c, "gs_color_patterns", 1) != 0) rc = gs_build_patterns(c, p.ord[1], p.n);
   return rc;
 }
 
@@ -1746,16 +1881,22 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
         void (*kern)(const GsSellArgs) = o->W == 27 ? k_gs_sell<27, 0> : (o->W == 7 ? k_gs_sell<7, 0> : k_gs_sell<0, 0>);
         // gs_color_kernel 1 (default): the slices stream through a TMA ring (k_gs_color_tma); 0: every lane loads its own entries
         const bool ring = pa_knob(c, "gs_color_kernel", 1) != 0;
-        const int batch = (int)pa_knob(c, "gs_color_batch", 14);
+        const bool pat0 = pa_knob(c, "gs_color_kernel", 1) != 0 && o->patterns && pa_knob(c, "gs_color_patterns", 1) != 0 && (o->W == 27 || o->W == 7);
+        // measured at 27-pt 512^3 (symmetric sweep): column words 2 slices x 2 stages x 14: 18.7 ms; row patterns 4 x 2 x 27: 14.0 ms
+        const int batch = (int)pa_knob(c, "gs_color_batch", pat0 ? 27 : 14);
         void (*tk)(const GsSellArgs, int, int) = o->W == 27 ? (batch >= 27 ? k_gs_color_tma<27, 27> : (batch >= 14 ? k_gs_color_tma<27, 14> : k_gs_color_tma<27, 9>))
                                                  : (o->W == 7 ? k_gs_color_tma<7, 7> : k_gs_color_tma<0, 8>);
-        int NW = (int)pa_knob(c, "gs_color_slices", 2), S = (int)pa_knob(c, "gs_color_stages", 2);
+        const bool pat = ring && o->patterns && pa_knob(c, "gs_color_patterns", 1) != 0 && (o->W == 27 || o->W == 7);
+        if (pat) tk = o->W == 27 ? (batch >= 27 ? k_gs_color_tma<27, 27, true> : (batch >= 14 ? k_gs_color_tma<27, 14, true> : k_gs_color_tma<27, 9, true>)) : k_gs_color_tma<7, 7, true>;
+        int NW = (int)pa_knob(c, "gs_color_slices", pat ? 4 : 2), S = (int)pa_knob(c, "gs_color_stages", 2);
         NW = std::max(1, std::min(NW, 8));
         S = std::max(2, std::min(S, 8));
         size_t smem = 0;
         int per_sm = 1;
         if (ring) {
-          while ((smem = (size_t)S * ((size_t)NW * o->W * 32 * 12 + 16)) > 200 * 1024 && (NW > 1 || S > 2)) {
+          int max_npat = 0;
+          if (pat) for (int l = 0; l < o->nlev; ++l) max_npat = std::max(max_npat, o->lev_npat[l]);
+          while ((smem = (size_t)S * ((size_t)NW * o->W * 32 * (pat ? 8 : 12) + (pat ? NW * 32 : 0) + 16) + (size_t)max_npat * o->W * 4) > 200 * 1024 && (NW > 1 || S > 2)) {
             if (NW > 1) NW /= 2; else --S;
           }
           PA_CHECK(smem <= 220 * 1024, PA_ESTATE, "gs_sweep: a slice of the multi-colour copy does not fit shared memory");
@@ -1772,6 +1913,9 @@ static int gs_sweep(pa_gs *g, pa_vec *x, const pa_vec *b, int backward, int zero
           if (ring) {
             a.g0 = s0;
             a.g1 = s1;
+            a.pat = pat ? o->d_pat : nullptr;
+            a.ptab = pat ? o->d_ptab + o->lev_ptab_off[l] : nullptr;
+            a.npat = pat ? o->lev_npat[l] : 0;
             const int64_t grid = std::min<int64_t>((s1 - s0 + NW - 1) / NW, (int64_t)nsm * per_sm);
             tk<<<(unsigned)grid, NW * 32 + 32, smem, c->stream>>>(a, NW, S);
             c->launches++;

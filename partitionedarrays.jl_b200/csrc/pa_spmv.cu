@@ -5,6 +5,8 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <map>
+#include <vector>
 
 #include "pa_device.cuh"
 #include "pa_internal.h"
@@ -46,6 +48,10 @@ struct SpmvArgs {
   unsigned *dot_ticket;
   RedPush push;
   const unsigned char *tile_ghost;  // MODE 4: tile t holds a row with a ghost column (computed once per matrix and tile size)
+  // PAT: the column stream is replaced by one byte per row (see build_patterns)
+  const unsigned char *pat;
+  const int32_t *ptab;
+  int npat, pat_w;
 };
 
 // The matrix stream is read exactly once: keep it out of L1 and mark it evict-first in L2 so the
@@ -193,18 +199,26 @@ __device__ __forceinline__ void spmv_wait_gather(const unsigned long long *arriv
 //         slots, fences and counts itself in; rows that touch a ghost column wait (once per thread) until all CTAs
 //         are counted in and read the slots through L2.  Own-block products never wait: on a banded operator only
 //         the first tiles of the persistent grid can meet the gather still in flight.
-template <typename PtrT, int MODE, int BATCH>
+// PAT (MODE 0 only): rows of a structured operator repeat a handful of column patterns (column - row for every entry:
+//      27 box positions of a stencil).  The kernel then streams ONE BYTE per row — the pattern id — instead of four bytes per
+//      entry; the patterns live in shared memory (every interior thread of a warp reads the same word: a broadcast).  Rows
+//      whose pattern is not in the table (ghost columns, rare boundary classes) carry id 255 and read colval from global
+//      memory.  Matrix stream 12 -> 8 bytes per entry + 1 per row; same products, same order, same bits.
+template <typename PtrT, int MODE, int BATCH, bool PAT = false>
 __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MODE == 1 ? 3 : 4)))) k_spmv_tma(const SpmvArgs<PtrT> a, const TmaCfg cfg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int ROWS = cfg.rows, CAP = cfg.cap, S = cfg.stages;
-  // layout: val[S][CAP+2] | col[S][CAP+8] | p0[S] (int64) | full[S] | empty[S]
+  // layout: val[S][CAP+2] | col[S][CAP+8] (PAT: pattern ids [S][ROWS+16 bytes]) | p0[S] (int64) | full[S] | empty[S] | PAT: table
   double *val_s = reinterpret_cast<double *>(smem_raw);
   int32_t *col_s = reinterpret_cast<int32_t *>(val_s + (size_t)S * (CAP + 2));
-  int64_t *p0_s = reinterpret_cast<int64_t *>(col_s + (size_t)S * (CAP + 8));
+  int64_t *p0_s = reinterpret_cast<int64_t *>(col_s + (size_t)S * (PAT ? (ROWS + 16) / 4 : (CAP + 8)));
   uint64_t *full = reinterpret_cast<uint64_t *>(p0_s + S);
   uint64_t *empty = full + S;
+  int32_t *ptab_s = reinterpret_cast<int32_t *>(empty + S);
   const int tid = threadIdx.x;
   __shared__ unsigned long long gather_target;
+  if (PAT)
+    for (int i = tid; i < a.npat * a.pat_w; i += blockDim.x) ptab_s[i] = a.ptab[i];
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full + s, 1);
@@ -234,10 +248,17 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
       const int64_t pv = p0 & ~(int64_t)1, pc = p0 & ~(int64_t)3;
       const uint32_t bv = (uint32_t)(((p1 - pv + 1) & ~(int64_t)1) * 8), bc = (uint32_t)(((p1 - pc + 3) & ~(int64_t)3) * 4);
       const bool any = p1 > p0;
-      mbar_expect_tx(full + s, any ? bv + bc : 0u);
-      if (any) {
-        tma_load_1d(val_s + (size_t)s * (CAP + 2), a.nzval + pv, bv, full + s, pol);
-        tma_load_1d(col_s + (size_t)s * (CAP + 8), a.colval + pc, bc, full + s, pol);
+      if (PAT) {
+        const uint32_t bp = (uint32_t)(((r1 - r0) + 15) & ~(int64_t)15);  // pattern ids of the tile's rows (r0 is a multiple of 32)
+        mbar_expect_tx(full + s, (any ? bv : 0u) + bp);
+        if (any) tma_load_1d(val_s + (size_t)s * (CAP + 2), a.nzval + pv, bv, full + s, pol);
+        tma_load_1d(reinterpret_cast<unsigned char *>(col_s) + (size_t)s * (ROWS + 16), a.pat + r0, bp, full + s, pol);
+      } else {
+        mbar_expect_tx(full + s, any ? bv + bc : 0u);
+        if (any) {
+          tma_load_1d(val_s + (size_t)s * (CAP + 2), a.nzval + pv, bv, full + s, pol);
+          tma_load_1d(col_s + (size_t)s * (CAP + 8), a.colval + pc, bc, full + s, pol);
+        }
       }
     };
     const uint64_t pol = stream_policy();
@@ -310,6 +331,11 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
       const int32_t *cs = col_s + (size_t)s * (CAP + 8) + (rs - (p0 & ~(int64_t)3));
       const int len = (int)(re - rs);
       double acc = 0.0;
+      // PAT: pattern id of this row; 255 = columns from global memory
+      const unsigned pid = PAT ? (unsigned)reinterpret_cast<const unsigned char *>(col_s)[(size_t)s * (ROWS + 16) + tid] : 0u;
+      const bool esc = PAT && pid == 255u;
+      const int32_t *tab = ptab_s + (esc ? 0u : pid) * (unsigned)a.pat_w;
+      const int32_t *gc = a.colval + rs;
       // BATCH independent (col,val) shared-memory reads and x gathers are issued before the dependent,
       // strictly in-order accumulation; indices past the row end are clamped to the last entry (a
       // redundant, cached load) instead of predicating the loads.
@@ -319,7 +345,12 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
 #pragma unroll
         for (int u = 0; u < BATCH; ++u) {
           const int kk = min(k0 + u, len - 1);
-          c[u] = cs[kk];
+          if (PAT) {
+            c[u] = (int32_t)row + tab[esc ? 0 : kk];
+            if (esc) c[u] = __ldg(gc + kk);
+          } else {
+            c[u] = cs[kk];
+          }
           v[u] = vs[kk];
         }
         bool ghost = false;
@@ -454,9 +485,12 @@ static int max_tile_nnz(pa_ctx *c, MatPart &m, int rows, int64_t *out) {
 
 template <typename PtrT>
 static int launch_spmv_tma(pa_ctx *c, MatPart &m, const SpmvArgs<PtrT> &a, int mode, const TmaCfg &cfg, int ctas_per_sm, int64_t *grid_out) {
-  const size_t smem = (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (cfg.cap + 8) * 4 + 8 + 16) + 128;
+  const bool pat = mode == 0 && a.pat != nullptr;
+  const size_t smem = pat ? (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (cfg.rows + 16) + 8 + 16) + (size_t)a.npat * a.pat_w * 4 + 128
+                          : (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (cfg.cap + 8) * 4 + 8 + 16) + 128;
   const int batch = cfg.batch;
-  auto kern = mode == 1 ? (batch >= 32 ? k_spmv_tma<PtrT, 1, 32> : batch >= 16 ? k_spmv_tma<PtrT, 1, 16> : k_spmv_tma<PtrT, 1, 8>)
+  auto kern = pat ? (batch >= 32 ? k_spmv_tma<PtrT, 0, 32, true> : batch >= 16 ? k_spmv_tma<PtrT, 0, 16, true> : k_spmv_tma<PtrT, 0, 8, true>)
+            : mode == 1 ? (batch >= 32 ? k_spmv_tma<PtrT, 1, 32> : batch >= 16 ? k_spmv_tma<PtrT, 1, 16> : k_spmv_tma<PtrT, 1, 8>)
             : mode == 4 ? (batch >= 32 ? k_spmv_tma<PtrT, 4, 32> : batch >= 16 ? k_spmv_tma<PtrT, 4, 16> : k_spmv_tma<PtrT, 4, 8>)
             : mode == 2 ? (batch >= 32 ? k_spmv_tma<PtrT, 2, 32> : batch >= 16 ? k_spmv_tma<PtrT, 2, 16> : k_spmv_tma<PtrT, 2, 8>)
                         : (batch >= 32 ? k_spmv_tma<PtrT, 0, 32> : batch >= 16 ? k_spmv_tma<PtrT, 0, 16> : k_spmv_tma<PtrT, 0, 8>);
@@ -575,6 +609,150 @@ __global__ void k_sum_parts(const double *part, int n, double *out) {
 }
 
 // dotw/d_out (nullable): fused epilogue *d_out = sum_parts dot(y_own, dotw_own), only with mode 0/1 on the TMA kernel
+// ------------------------------------------------------------------ row patterns (column stream compression)
+// pattern of a row = (length, column - row of every entry).  A structured operator has a handful (a stencil on a box: one per
+// box position, 27); rows with ghost columns or rare boundary classes keep reading colval.  Built lazily for the TMA kernel:
+// the candidates come from a sample of rows (host side: a dictionary of at most 254 tuples), then ONE pass over the matrix
+// assigns every row the id of the tuple it matches EXACTLY, or 255.
+#define PA_PAT_ESC 255
+#define PA_PAT_MAXW 32
+template <typename PtrT>
+__global__ void k_pat_sample(const PtrT *rowptr, const int32_t *colval, int64_t nrows, int64_t nsample, int32_t *out /* [nsample][1 + MAXW] */) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsample; i += (int64_t)gridDim.x * blockDim.x) {
+    // evenly spread rows with a pseudo-random offset inside every stride, plus the rows next to both ends
+    const int64_t stride = nrows / nsample > 0 ? nrows / nsample : 1;
+    int64_t row = i * stride + (int64_t)((unsigned long long)(i * 2654435761ull) % (unsigned long long)stride);
+    if (i < 512) row = i;
+    else if (i < 1024) row = nrows - 1 - (i - 512);
+    if (row >= nrows) row = nrows - 1;
+    if (row < 0) row = 0;
+    const int64_t p0 = (int64_t)rowptr[row], len = (int64_t)rowptr[row + 1] - p0;
+    int32_t *o = out + i * (1 + PA_PAT_MAXW);
+    o[0] = len <= PA_PAT_MAXW ? (int32_t)len : -1;
+    for (int k = 0; k < PA_PAT_MAXW; ++k) o[1 + k] = (k < len && len <= PA_PAT_MAXW) ? colval[p0 + k] - (int32_t)row : 0;
+  }
+}
+__device__ __forceinline__ unsigned long long pat_hash(int len, const int32_t *d) {
+  unsigned long long h = 0x9E3779B97F4A7C15ull ^ (unsigned long long)len;
+  for (int k = 0; k < len; ++k) {
+    h ^= (unsigned long long)(unsigned)d[k] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h *= 0xBF58476D1CE4E5B9ull;
+  }
+  return h;
+}
+template <typename PtrT>
+__global__ void k_pat_assign(const PtrT *rowptr, const int32_t *colval, int64_t nrows, const int32_t *ptab, const int32_t *plen, const unsigned long long *phash,
+                             int npat, int pat_w, unsigned char *pat, unsigned long long *n_esc) {
+  extern __shared__ unsigned long long sh_hash[];  // [npat] then lengths
+  int32_t *sh_len = reinterpret_cast<int32_t *>(sh_hash + npat);
+  for (int i = threadIdx.x; i < npat; i += blockDim.x) {
+    sh_hash[i] = phash[i];
+    sh_len[i] = plen[i];
+  }
+  __syncthreads();
+  unsigned long long esc = 0;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p0 = (int64_t)rowptr[row];
+    const int len = (int)((int64_t)rowptr[row + 1] - p0);
+    int id = PA_PAT_ESC;
+    if (len <= pat_w) {
+      int32_t d[PA_PAT_MAXW];
+      for (int k = 0; k < len; ++k) d[k] = colval[p0 + k] - (int32_t)row;
+      const unsigned long long h = pat_hash(len, d);
+      for (int q = 0; q < npat && id == PA_PAT_ESC; ++q) {
+        if (sh_hash[q] != h || sh_len[q] != len) continue;
+        bool same = true;
+        for (int k = 0; k < len; ++k) same &= ptab[q * pat_w + k] == d[k];  // exact: a hash collision must not change a column
+        if (same) id = q;
+      }
+    }
+    pat[row] = (unsigned char)id;
+    esc += id == PA_PAT_ESC;
+  }
+  if (esc) atomicAdd(n_esc, esc);
+}
+
+static unsigned long long pat_hash_host(int len, const int32_t *d) {
+  unsigned long long h = 0x9E3779B97F4A7C15ull ^ (unsigned long long)len;
+  for (int k = 0; k < len; ++k) {
+    h ^= (unsigned long long)(unsigned)d[k] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h *= 0xBF58476D1CE4E5B9ull;
+  }
+  return h;
+}
+
+static int build_patterns(pa_ctx *c, MatPart &m) {
+  m.pat_state = -1;
+  if (m.nrows < pa_knob(c, "spmv_pattern_min_rows", 4096) || m.nnz == 0) return PA_OK;  // nothing to gain on small parts
+  const int64_t nsample = std::min<int64_t>(m.nrows, 65536);
+  int32_t *d_s = nullptr;
+  PA_CUDA(cudaMalloc((void **)&d_s, nsample * (1 + PA_PAT_MAXW) * sizeof(int32_t)));
+  if (m.ptr64) k_pat_sample<int64_t><<<256, 256, 0, c->stream>>>((const int64_t *)m.d_rowptr, m.d_colval, m.nrows, nsample, d_s);
+  else k_pat_sample<int32_t><<<256, 256, 0, c->stream>>>((const int32_t *)m.d_rowptr, m.d_colval, m.nrows, nsample, d_s);
+  std::vector<int32_t> hs((size_t)nsample * (1 + PA_PAT_MAXW));
+  PA_CUDA(cudaMemcpyAsync(hs.data(), d_s, hs.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  PA_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_s);
+  c->launches++;
+  // dictionary of the sampled tuples, most frequent first
+  std::map<std::vector<int32_t>, int64_t> freq;
+  int wmax = 0;
+  for (int64_t i = 0; i < nsample; ++i) {
+    const int32_t *o = hs.data() + i * (1 + PA_PAT_MAXW);
+    if (o[0] < 0) continue;
+    std::vector<int32_t> key(o, o + 1 + o[0]);
+    freq[key]++;
+  }
+  std::vector<std::pair<int64_t, std::vector<int32_t>>> order;
+  for (auto &kv : freq) order.emplace_back(-kv.second, kv.first);
+  std::sort(order.begin(), order.end());
+  if (order.empty()) return PA_OK;
+  if (order.size() > 254) order.resize(254);
+  for (auto &e : order) wmax = std::max(wmax, e.second[0]);
+  while (order.size() > 1 && order.size() * (size_t)std::max(wmax, 1) * 4 > 12 * 1024) order.pop_back();  // the table lives in shared memory
+  wmax = 1;
+  for (auto &e : order) wmax = std::max(wmax, e.second[0]);
+  const int npat = (int)order.size();
+  std::vector<int32_t> tab((size_t)npat * wmax, 0), len(npat);
+  std::vector<unsigned long long> hash(npat);
+  for (int q = 0; q < npat; ++q) {
+    len[q] = order[q].second[0];
+    for (int k = 0; k < len[q]; ++k) tab[(size_t)q * wmax + k] = order[q].second[1 + k];
+    hash[q] = pat_hash_host(len[q], tab.data() + (size_t)q * wmax);
+  }
+  int32_t *d_len = nullptr;
+  unsigned long long *d_hash = nullptr, *d_esc = nullptr, h_esc = 0;
+  PA_CUDA(cudaMalloc((void **)&m.d_ptab, tab.size() * sizeof(int32_t)));
+  PA_CUDA(cudaMalloc((void **)&m.d_pat, (size_t)m.nrows + 512));
+  PA_CUDA(cudaMalloc((void **)&d_len, npat * sizeof(int32_t)));
+  PA_CUDA(cudaMalloc((void **)&d_hash, npat * sizeof(unsigned long long)));
+  PA_CUDA(cudaMalloc((void **)&d_esc, sizeof(unsigned long long)));
+  PA_CUDA(cudaMemcpyAsync(m.d_ptab, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  PA_CUDA(cudaMemcpyAsync(d_len, len.data(), npat * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  PA_CUDA(cudaMemcpyAsync(d_hash, hash.data(), npat * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+  PA_CUDA(cudaMemsetAsync(d_esc, 0, sizeof(unsigned long long), c->stream));
+  PA_CUDA(cudaMemsetAsync(m.d_pat, PA_PAT_ESC, (size_t)m.nrows + 512, c->stream));
+  const size_t sh = (size_t)npat * (sizeof(unsigned long long) + sizeof(int32_t));
+  if (m.ptr64)
+    k_pat_assign<int64_t><<<148 * 8, 256, sh, c->stream>>>((const int64_t *)m.d_rowptr, m.d_colval, m.nrows, m.d_ptab, d_len, d_hash, npat, wmax, m.d_pat, d_esc);
+  else
+    k_pat_assign<int32_t><<<148 * 8, 256, sh, c->stream>>>((const int32_t *)m.d_rowptr, m.d_colval, m.nrows, m.d_ptab, d_len, d_hash, npat, wmax, m.d_pat, d_esc);
+  PA_CUDA(cudaMemcpyAsync(&h_esc, d_esc, sizeof(h_esc), cudaMemcpyDeviceToHost, c->stream));
+  PA_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_len); cudaFree(d_hash); cudaFree(d_esc);
+  c->launches++;
+  // rows without a pattern pay a global read of their columns: worth it only when they are few
+  if ((double)h_esc > 0.08 * (double)m.nrows) {
+    cudaFree(m.d_pat); cudaFree(m.d_ptab);
+    m.d_pat = nullptr; m.d_ptab = nullptr;
+    return PA_OK;
+  }
+  m.npat = npat;
+  m.pat_w = wmax;
+  m.pat_state = 1;
+  return PA_OK;
+}
+
 int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, int mode, const pa_vec *dotw, double *d_out, int fold) {
   pa_ctx *c = A->ctx;
   PA_CHECK(!fold || (dotw && pa_fold_ok(c)), PA_ESTATE, "folded dot epilogue needs one local part with mapped peers");
@@ -591,7 +769,16 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, in
     if (rows != 256 && rows != 128 && rows != 64 && rows != 32) rows = m.rows_per_cta;
     // TMA pipeline configuration (knobs allow sweeping on the GPU without recompiling)
     TmaCfg cfg;
-    cfg.rows = (int)pa_knob(c, "tma_rows", m.nnz > 12 * m.nrows ? 64 : 256);  // measured best: 7-pt 256, 27-pt 64 (profiles/)
+    // spmv_patterns: -1 (default) = where rows are long enough for the column bytes to matter (more than 12 entries on
+    // average: 27-pt 7.40 -> 5.42 ms; the 7-pt kernel is bound by its per-row work, 1.96 ms plain vs 2.04 ms with patterns),
+    // 1 = wherever the rows repeat patterns, 0 = never
+    const int64_t pat_knob = pa_knob(c, "spmv_patterns", -1);
+    const bool long_rows = m.nnz > 12 * m.nrows;
+    bool want_pat = kmode == 0 && (pat_knob > 0 || (pat_knob < 0 && long_rows)) && m.tma_ok && pa_knob(c, "spmv_kernel", 3) == 3;
+    if (want_pat && m.pat_state == 0) PA_TRY(build_patterns(c, m));
+    want_pat = want_pat && m.pat_state == 1;
+    // measured best (profiles/): 7-pt 256 rows per tile, 27-pt 64 with the column stream / 128 with row patterns
+    cfg.rows = (int)pa_knob(c, "tma_rows", long_rows ? (want_pat ? 128 : 64) : 256);
     cfg.stages = (int)pa_knob(c, "tma_stages", 2);
     cfg.batch = (int)pa_knob(c, "tma_batch", m.nnz > 8 * m.nrows ? 16 : 8);
     int ctas = (int)pa_knob(c, "tma_ctas", 0);
@@ -605,6 +792,7 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, in
       if (smem > 200 * 1024) use_tma = false;  // a tile does not fit: irregular rows -> chunked kernel
     }
     PA_CHECK(use_tma || (kmode != 2 && kmode != 4), PA_ESTATE, "own-block / fused-exchange modes need the TMA kernel");
+    const bool use_pat = want_pat && use_tma && kmode == 0;
     if (kmode == 4 && !m.d_arrive) PA_CUDA(cudaMalloc((void **)&m.d_arrive, sizeof(unsigned long long)));
     const unsigned char *tile_flags = nullptr;
     if (kmode == 4) {
@@ -644,6 +832,10 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, in
       a.dot_ticket = m.d_dot_ticket;
       if (fold) a.push = pa_red_push(c);
       a.tile_ghost = tile_flags;
+      a.pat = use_pat ? m.d_pat : nullptr;
+      a.ptab = m.d_ptab;
+      a.npat = m.npat;
+      a.pat_w = m.pat_w;
     };
     if (dotw) {
       PA_CHECK(use_tma && mode != 2 && mode != 3 && rp.prefix && alpha == 1.0 && beta == 0.0, PA_ESTATE, "dot epilogue unavailable for this configuration");
@@ -838,6 +1030,8 @@ static void free_part(MatPart &m) {
   cudaFree(m.d_dotpart);
   cudaFree(m.d_dot_ticket);
   cudaFree(m.d_arrive);
+  cudaFree(m.d_pat);
+  cudaFree(m.d_ptab);
   cudaFree(m.d_grows);
   cudaFree(m.d_rowptr);
   cudaFree(m.d_colval);

@@ -164,7 +164,8 @@ def test_gauss_seidel_on_short_rows_is_bit_exact(pa, case, kernel):
 
 # colour kernel: "lanes" = every lane loads its own entries (k_gs_sell<W,0>); (slices per tile, stages, batch) = the slices
 # stream through a TMA ring (k_gs_color_tma, the default: 2 slices, 2 stages, batches of 14)
-@pytest.mark.parametrize("ckern", ["lanes", (2, 2, 14), (1, 3, 9), (4, 2, 27), (3, 4, 14)])
+# a fourth entry 0 switches the row patterns off (column words streamed instead of one byte per row)
+@pytest.mark.parametrize("ckern", ["lanes", (2, 2, 14), (1, 3, 9), (4, 2, 27), (3, 4, 14), (2, 2, 14, 0), (4, 2, 9, 0)])
 @pytest.mark.parametrize("npd,nloc", [((2, 2, 1), (8, 6, 4)), ((1, 1, 1), (10, 9, 8)), ((2, 1, 1), (40, 32, 24))])
 def test_multicolor_gauss_seidel_matches_the_oracle_order(pa, npd, nloc, ckern):
     """The opt-in multi-colour order (8 colours, one launch per colour): same per-row arithmetic as the reference's
@@ -191,11 +192,11 @@ def _set_color_kernel(b, ckern):
         b.set_knob("gs_color_kernel", 0)
     else:
         b.set_knob("gs_color_kernel", 1)
-        for key, val in zip(("gs_color_slices", "gs_color_stages", "gs_color_batch"), ckern):
+        for key, val in zip(("gs_color_slices", "gs_color_stages", "gs_color_batch", "gs_color_patterns"), ckern):
             b.set_knob(key, val)
 
 
-@pytest.mark.parametrize("ckern", ["lanes", (2, 2, 14), (8, 3, 14)])
+@pytest.mark.parametrize("ckern", ["lanes", (2, 2, 14), (8, 3, 14), (2, 2, 14, 0)])
 @pytest.mark.parametrize("case", ["fdm7-redblack", "fdm27-thin"])
 def test_multicolor_gauss_seidel_other_row_widths(pa, case, ckern):
     """Red/black order of the 7-pt gallery operator (rows of <= 7 entries) and the 8-colour order on a box one cell thick

@@ -70,6 +70,12 @@ def main():
         run("tma default", spmv_kernel=3)
         b.close()
         return
+    if os.environ.get("SWEEP_COMBOS"):  # "rows:stages:ctas:batch,..." with the current PA_SPMV_PATTERNS setting
+        for item in os.environ["SWEEP_COMBOS"].split(","):
+            rows, stages, ctas, batch = (int(q) for q in item.split(":"))
+            run(f"tma rows={rows} stages={stages} ctas={ctas} batch={batch}", spmv_kernel=3, tma_rows=rows, tma_stages=stages, tma_ctas=ctas, tma_batch=batch)
+        b.close()
+        return
     run("v1 stream kernel", spmv_kernel=1)
     if kind == 7:
         combos = [(256, 2, 0, 8), (256, 2, 0, 16), (128, 2, 0, 8), (256, 3, 0, 8), (192, 2, 0, 8), (224, 2, 0, 8), (256, 2, 4, 8), (256, 2, 3, 8)]
