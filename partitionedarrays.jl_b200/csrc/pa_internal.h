@@ -174,7 +174,7 @@ struct MatPart {
   int pat_state = 0;
   unsigned char *d_pat = nullptr;
   int32_t *d_ptab = nullptr;  // [npat][pat_w]
-  int npat = 0, pat_w = 0;
+  int npat = 0, pat_w = 0, pat_len0 = 0;  // pat_len0: length of the most frequent pattern (id 0)
   // COO pattern cache (the reference's K of sparse_matrix(...; reuse=true)): sorted permutation + segment starts
   int32_t *d_coo_perm = nullptr, *d_coo_seg = nullptr;
   unsigned char *d_coo_valid = nullptr;

@@ -156,6 +156,9 @@ static void launch_spmv_t(const SpmvArgs<PtrT> &a, int rows, cudaStream_t st) {
 struct TmaCfg {
   int rows, cap, stages, batch;
   int64_t ntiles;
+  int rpt = 1;  // rows per consumer thread (k_spmv_pat)
+  int fl = 0;   // length of the most frequent row pattern when the fixed-length path is compiled for it (7, 27), else 0
+  bool use_pat_kernel = false;
 };
 
 __device__ __forceinline__ void keep_live8(const double *x) {
@@ -199,6 +202,48 @@ __device__ __forceinline__ void spmv_wait_gather(const unsigned long long *arriv
 //         slots, fences and counts itself in; rows that touch a ghost column wait (once per thread) until all CTAs
 //         are counted in and read the slots through L2.  Own-block products never wait: on a banded operator only
 //         the first tiles of the persistent grid can meet the gather still in flight.
+// fused dot epilogue of the TMA kernels (consumers only: the producer warp has left): fixed-order block reduction, one partial
+// per CTA; folded variant: the last CTA adds the partials in a fixed order and posts the part's value to every part of the job
+template <typename PtrT>
+__device__ __forceinline__ void spmv_dot_epilogue(const SpmvArgs<PtrT> &a, double dsum, const int tid, const int ROWS) {
+  if (a.dotw) {  // consumers only (the producer warp has left): fixed-order block reduction, one partial per CTA
+    __shared__ double red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    if ((tid & 31) == 0) red[tid >> 5] = dsum;
+    asm volatile("bar.sync 1, %0;" ::"r"(ROWS) : "memory");
+    __shared__ bool last_cta;
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (ROWS >> 5); ++w) t += red[w];
+      a.dot_part[blockIdx.x] = t;
+      if (a.fold) {
+        __threadfence();
+        last_cta = atomicInc(a.dot_ticket, gridDim.x - 1) == gridDim.x - 1;  // wraps to 0: self resetting
+      }
+    }
+    if (a.fold) {
+      // the last CTA to finish adds all partials (thread t: partials t, t+ROWS, ... then a fixed tree: deterministic) and
+      // posts the part's value to every part of the job: no k_sum_parts launch, no all-reduce launch
+      asm volatile("bar.sync 1, %0;" ::"r"(ROWS) : "memory");
+      if (last_cta) {
+        __threadfence();
+        double s = 0.0;
+        for (int i = tid; i < (int)gridDim.x; i += ROWS) s += __ldcg(a.dot_part + i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((tid & 31) == 0) red[tid >> 5] = s;
+        asm volatile("bar.sync 1, %0;" ::"r"(ROWS) : "memory");
+        if (tid < 32) {
+          double t = 0.0;
+          for (int w = 0; w < (ROWS >> 5); ++w) t += red[w];
+          pa_red_post(a.push, t, tid);
+        }
+      }
+    }
+  }
+}
+
 // PAT (MODE 0 only): rows of a structured operator repeat a handful of column patterns (column - row for every entry:
 //      27 box positions of a stencil).  The kernel then streams ONE BYTE per row — the pattern id — instead of four bytes per
 //      entry; the patterns live in shared memory (every interior thread of a warp reads the same word: a broadcast).  Rows
@@ -410,42 +455,177 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
       mbar_arrive(empty + s);
     }
   }
-  if (a.dotw) {  // consumers only (the producer warp has left): fixed-order block reduction, one partial per CTA
-    __shared__ double red[8];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-    if ((tid & 31) == 0) red[tid >> 5] = dsum;
-    asm volatile("bar.sync 1, %0;" ::"r"(ROWS) : "memory");
-    __shared__ bool last_cta;
-    if (tid == 0) {
-      double t = 0.0;
-      for (int w = 0; w < (ROWS >> 5); ++w) t += red[w];
-      a.dot_part[blockIdx.x] = t;
-      if (a.fold) {
-        __threadfence();
-        last_cta = atomicInc(a.dot_ticket, gridDim.x - 1) == gridDim.x - 1;  // wraps to 0: self resetting
+  spmv_dot_epilogue(a, dsum, tid, ROWS);
+}
+
+// ------------------------------------------------------------------ pattern kernel for SHORT rows: RPT rows per thread
+// With the column stream gone, the 7-pt product is no longer bound by HBM but by how many gathers a consumer thread keeps in
+// flight: one row of 7 entries per tile and thread.  Here a tile holds RPT x ROWS rows and every consumer thread owns RPT of
+// them (tid, tid + ROWS, ...): their entries are read, their x values gathered and their sums advanced side by side —
+// RPT x BATCH loads in flight per thread, the same products in the same order per row.  MODE 0 only (columns are local).
+// FL > 0: rows of exactly FL entries whose pattern is in the table take a FIXED-LENGTH path when the whole warp agrees (the
+// interior of a stencil operator): no clamped indices, no predicated accumulation, shared-memory offsets are immediates —
+// ~8 instead of ~14 instructions per entry (ncu: the generic loop issues 300-370 warp instructions per 7-entry row and keeps
+// the issue slots 56-66 % busy, which is what bounds the kernel once the column stream is gone).
+template <typename PtrT, int BATCH, int RPT, int MINB, int FL>
+__global__ void __launch_bounds__(288, MINB) k_spmv_pat(const SpmvArgs<PtrT> a, const TmaCfg cfg) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int ROWS = cfg.rows, CAP = cfg.cap, S = cfg.stages, TR = ROWS * RPT;
+  // layout: val[S][CAP+2] | pattern ids [S][TR+16 bytes] | p0[S] (int64) | full[S] | empty[S] | table
+  double *val_s = reinterpret_cast<double *>(smem_raw);
+  unsigned char *pat_s = reinterpret_cast<unsigned char *>(val_s + (size_t)S * (CAP + 2));
+  int64_t *p0_s = reinterpret_cast<int64_t *>(pat_s + (size_t)S * (TR + 16));
+  uint64_t *full = reinterpret_cast<uint64_t *>(p0_s + S);
+  uint64_t *empty = full + S;
+  int32_t *ptab_s = reinterpret_cast<int32_t *>(empty + S);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < a.npat * a.pat_w; i += blockDim.x) ptab_s[i] = a.ptab[i];
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, ROWS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int64_t nloc = first < cfg.ntiles ? (cfg.ntiles - first + stride - 1) / stride : 0;
+  if (tid >= ROWS) {
+    if (tid == ROWS) {  // producer: one elected lane drives the TMA ring
+      const uint64_t pol = stream_policy();
+      int s = 0;
+      uint32_t ph = 1;
+      for (int64_t j = 0; j < nloc; ++j, ++s) {
+        if (s == S) { s = 0; ph ^= 1u; }
+        if (j >= S) mbar_wait(empty + s, ph);
+        const int64_t t = first + j * stride;
+        const int64_t r0 = t * TR, r1 = min(r0 + (int64_t)TR, a.nrows);
+        const int64_t p0 = (int64_t)a.rowptr[r0], p1 = (int64_t)a.rowptr[r1];
+        p0_s[s] = p0;
+        const int64_t pv = p0 & ~(int64_t)1;
+        const uint32_t bv = (uint32_t)(((p1 - pv + 1) & ~(int64_t)1) * 8), bp = (uint32_t)(((r1 - r0) + 15) & ~(int64_t)15);
+        const bool any = p1 > p0;
+        mbar_expect_tx(full + s, (any ? bv : 0u) + bp);
+        if (any) tma_load_1d(val_s + (size_t)s * (CAP + 2), a.nzval + pv, bv, full + s, pol);
+        tma_load_1d(pat_s + (size_t)s * (TR + 16), a.pat + r0, bp, full + s, pol);
       }
     }
-    if (a.fold) {
-      // the last CTA to finish adds all partials (thread t: partials t, t+ROWS, ... then a fixed tree: deterministic) and
-      // posts the part's value to every part of the job: no k_sum_parts launch, no all-reduce launch
-      asm volatile("bar.sync 1, %0;" ::"r"(ROWS) : "memory");
-      if (last_cta) {
-        __threadfence();
-        double s = 0.0;
-        for (int i = tid; i < (int)gridDim.x; i += ROWS) s += __ldcg(a.dot_part + i);
+    return;
+  }
+  double dsum = 0.0;
+  int64_t rs_n[RPT], re_n[RPT];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if ((tid & 31) == 0) red[tid >> 5] = s;
-        asm volatile("bar.sync 1, %0;" ::"r"(ROWS) : "memory");
-        if (tid < 32) {
-          double t = 0.0;
-          for (int w = 0; w < (ROWS >> 5); ++w) t += red[w];
-          pa_red_post(a.push, t, tid);
+  for (int q = 0; q < RPT; ++q) {
+    rs_n[q] = re_n[q] = 0;
+    const int64_t row = first * TR + q * ROWS + tid;
+    if (nloc > 0 && row < a.nrows) {
+      rs_n[q] = (int64_t)a.rowptr[row];
+      re_n[q] = (int64_t)a.rowptr[row + 1];
+    }
+  }
+  int s = 0;
+  uint32_t ph = 0;
+  for (int64_t j = 0; j < nloc; ++j, ++s) {
+    if (s == S) { s = 0; ph ^= 1u; }
+    const int64_t t = first + j * stride;
+    int64_t rs[RPT];
+    int len[RPT];
+    int32_t row[RPT];
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+      rs[q] = rs_n[q];
+      len[q] = (int)(re_n[q] - rs_n[q]);
+      row[q] = (int32_t)(t * TR + q * ROWS + tid);
+      rs_n[q] = re_n[q] = 0;
+      const int64_t rown = (t + stride) * TR + q * ROWS + tid;  // the next tile's row pointers while this tile is processed
+      if (j + 1 < nloc && rown < a.nrows) {
+        rs_n[q] = (int64_t)a.rowptr[rown];
+        re_n[q] = (int64_t)a.rowptr[rown + 1];
+      }
+    }
+    mbar_wait(full + s, ph);
+    const int64_t p0 = p0_s[s];
+    const double *vs[RPT];
+    const int32_t *tab[RPT], *gc[RPT];
+    bool esc[RPT];
+    double acc[RPT];
+    int maxlen = 0;
+    bool fixed = FL > 0;
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+      vs[q] = val_s + (size_t)s * (CAP + 2) + (len[q] > 0 ? rs[q] - (p0 & ~(int64_t)1) : 0);
+      // (rows past the end of the matrix: the TMA copy stops at the last row, what lies behind it in the stage is stale)
+      const unsigned pid = (int64_t)row[q] < a.nrows ? (unsigned)pat_s[(size_t)s * (TR + 16) + q * ROWS + tid] : 255u;
+      esc[q] = pid == 255u;
+      tab[q] = ptab_s + (esc[q] ? 0u : pid) * (unsigned)a.pat_w;
+      gc[q] = a.colval + rs[q];
+      acc[q] = 0.0;
+      maxlen = max(maxlen, len[q]);  // (rows past the end of the matrix have length 0)
+      fixed = fixed && len[q] == FL && !esc[q];
+    }
+    if (FL > 0 && __all_sync(0xffffffffu, fixed)) {
+      // ---- fixed-length path: FB entries of every row in flight, constant offsets
+      constexpr int FB = FL > 0 ? (FL <= 9 ? FL : 9) : 1;
+#pragma unroll
+      for (int k0 = 0; k0 < FL; k0 += FB) {
+        double v[RPT][FB], xv[RPT][FB];
+#pragma unroll
+        for (int q = 0; q < RPT; ++q)
+#pragma unroll
+          for (int u = 0; u < FB; ++u)
+            if (k0 + u < FL) {
+              v[q][u] = vs[q][k0 + u];
+              xv[q][u] = __ldg(a.x + (row[q] + tab[q][k0 + u]));
+            }
+#pragma unroll
+        for (int q = 0; q < RPT; ++q)
+#pragma unroll
+          for (int u = 0; u < FB; ++u)
+            if (k0 + u < FL) acc[q] = __dadd_rn(acc[q], __dmul_rn(v[q][u], xv[q][u]));  // strictly in column order
+      }
+    } else {
+      for (int k0 = 0; k0 < maxlen; k0 += BATCH) {
+        double v[RPT][BATCH], xv[RPT][BATCH];
+#pragma unroll
+        for (int q = 0; q < RPT; ++q)
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u) {
+            const int kk = max(min(k0 + u, len[q] - 1), 0);  // past the row end: a redundant, cached read of its last entry
+            int32_t c = row[q] + tab[q][esc[q] ? 0 : kk];
+            if (esc[q]) c = __ldg(gc[q] + kk);
+            v[q][u] = vs[q][kk];
+            xv[q][u] = __ldg(a.x + (len[q] > 0 ? c : 0));
+          }
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) {
+          keep_live(xv[q]);
+          keep_live(v[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < RPT; ++q)
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u) {  // branch-free, strictly in column order
+            const double t2 = __dadd_rn(acc[q], __dmul_rn(v[q][u], xv[q][u]));
+            acc[q] = (k0 + u < len[q]) ? t2 : acc[q];
+          }
+      }
+    }
+    mbar_arrive(empty + s);
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+      if ((int64_t)row[q] < a.nrows) {
+        const int64_t yi = a.rowmap ? (int64_t)a.rowmap[row[q]] : (int64_t)row[q];
+        if (a.alpha == 1.0 && a.beta == 0.0) {
+          a.y[yi] = acc[q];
+          if (a.dotw) dsum = __dadd_rn(dsum, __dmul_rn(acc[q], __ldg(a.dotw + yi)));
+        } else {
+          const double by = a.beta == 0.0 ? 0.0 : __dmul_rn(a.beta, a.y[yi]);
+          a.y[yi] = __dadd_rn(__dmul_rn(a.alpha, acc[q]), by);
         }
       }
     }
   }
+  spmv_dot_epilogue(a, dsum, tid, ROWS);
 }
 
 __global__ void k_tile_ghost_flags(const int32_t *grows, int64_t n, int rows, unsigned char *flag) {
@@ -486,6 +666,26 @@ static int max_tile_nnz(pa_ctx *c, MatPart &m, int rows, int64_t *out) {
 template <typename PtrT>
 static int launch_spmv_tma(pa_ctx *c, MatPart &m, const SpmvArgs<PtrT> &a, int mode, const TmaCfg &cfg, int ctas_per_sm, int64_t *grid_out) {
   const bool pat = mode == 0 && a.pat != nullptr;
+  if (pat && cfg.use_pat_kernel) {
+    const size_t smem2 = (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (cfg.rows * cfg.rpt + 16) + 8 + 16) + (size_t)a.npat * a.pat_w * 4 + 128;
+    void (*k2)(const SpmvArgs<PtrT>, const TmaCfg) = nullptr;
+    // (rows per thread, fixed length): 7-entry rows 2 x 7 or 1 x 7, 27-entry rows 1 x 27; everything else the generic loop
+    if (cfg.fl == 7) k2 = cfg.rpt == 2 ? k_spmv_pat<PtrT, 8, 2, 2, 7> : k_spmv_pat<PtrT, 8, 1, 3, 7>;
+    else if (cfg.fl == 27) k2 = k_spmv_pat<PtrT, 16, 1, 2, 27>;
+    else k2 = cfg.rpt == 2 ? k_spmv_pat<PtrT, 8, 2, 2, 0> : (cfg.batch >= 16 ? k_spmv_pat<PtrT, 16, 1, 2, 0> : k_spmv_pat<PtrT, 8, 1, 3, 0>);
+    PA_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    if (ctas_per_sm <= 0) {
+      PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k2, cfg.rows + 32, smem2));
+      if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    int nsm2 = 148;
+    cudaDeviceGetAttribute(&nsm2, cudaDevAttrMultiProcessorCount, c->device);
+    const int64_t grid2 = std::min<int64_t>(cfg.ntiles, (int64_t)nsm2 * ctas_per_sm);
+    PA_CHECK(!a.dotw || grid2 <= PA_DOT_PARTS, PA_ESTATE, "dot epilogue: grid larger than the partial buffer");
+    k2<<<(unsigned)grid2, cfg.rows + 32, smem2, c->stream>>>(a, cfg);
+    *grid_out = grid2;
+    return PA_OK;
+  }
   const size_t smem = pat ? (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (cfg.rows + 16) + 8 + 16) + (size_t)a.npat * a.pat_w * 4 + 128
                           : (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (cfg.cap + 8) * 4 + 8 + 16) + 128;
   const int batch = cfg.batch;
@@ -749,6 +949,7 @@ static int build_patterns(pa_ctx *c, MatPart &m) {
   }
   m.npat = npat;
   m.pat_w = wmax;
+  m.pat_len0 = len[0];
   m.pat_state = 1;
   return PA_OK;
 }
@@ -769,26 +970,33 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, in
     if (rows != 256 && rows != 128 && rows != 64 && rows != 32) rows = m.rows_per_cta;
     // TMA pipeline configuration (knobs allow sweeping on the GPU without recompiling)
     TmaCfg cfg;
-    // spmv_patterns: -1 (default) = where rows are long enough for the column bytes to matter (more than 12 entries on
-    // average: 27-pt 7.40 -> 5.42 ms; the 7-pt kernel is bound by its per-row work, 1.96 ms plain vs 2.04 ms with patterns),
-    // 1 = wherever the rows repeat patterns, 0 = never
-    const int64_t pat_knob = pa_knob(c, "spmv_patterns", -1);
+    // spmv_patterns: 1 (default) = wherever the rows repeat patterns (build_patterns decides per part), 0 = never
+    const int64_t pat_knob = pa_knob(c, "spmv_patterns", 1);
     const bool long_rows = m.nnz > 12 * m.nrows;
-    bool want_pat = kmode == 0 && (pat_knob > 0 || (pat_knob < 0 && long_rows)) && m.tma_ok && pa_knob(c, "spmv_kernel", 3) == 3;
+    bool want_pat = kmode == 0 && pat_knob != 0 && m.tma_ok && pa_knob(c, "spmv_kernel", 3) == 3;
     if (want_pat && m.pat_state == 0) PA_TRY(build_patterns(c, m));
     want_pat = want_pat && m.pat_state == 1;
     // measured best (profiles/): 7-pt 256 rows per tile, 27-pt 64 with the column stream / 128 with row patterns
-    cfg.rows = (int)pa_knob(c, "tma_rows", long_rows ? (want_pat ? 128 : 64) : 256);
-    cfg.stages = (int)pa_knob(c, "tma_stages", 2);
+    // with row patterns (k_spmv_pat, fixed-length path): 27-pt 96 rows x 2 stages (4.60 ms; column stream 7.40), 7-pt 2 x 128 rows per
+    // tile x 3 stages (1.72 ms; column stream 1.96)
+    cfg.rows = (int)pa_knob(c, "tma_rows", long_rows ? (want_pat ? 96 : 64) : (want_pat ? 128 : 256));
+    cfg.rpt = want_pat ? (int)pa_knob(c, "spmv_pattern_rpt", long_rows ? 1 : 2) : 1;  // rows per consumer thread of the pattern kernel
+    if (cfg.rpt != 2) cfg.rpt = 1;
+    // spmv_pattern_kernel 1 (default) = k_spmv_pat (fixed-length path for the dominant pattern), 0 = k_spmv_tma<PAT> (generic loop)
+    cfg.use_pat_kernel = want_pat && pa_knob(c, "spmv_pattern_kernel", 1) != 0;
+    if (!cfg.use_pat_kernel) cfg.rpt = 1;
+    cfg.fl = (cfg.use_pat_kernel && pa_knob(c, "spmv_pattern_fixed", 1) != 0 && (m.pat_len0 == 7 || m.pat_len0 == 27)) ? m.pat_len0 : 0;
+    if (cfg.fl == 27) cfg.rpt = 1;
+    cfg.stages = (int)pa_knob(c, "tma_stages", (want_pat && !long_rows) ? 3 : 2);
     cfg.batch = (int)pa_knob(c, "tma_batch", m.nnz > 8 * m.nrows ? 16 : 8);
     int ctas = (int)pa_knob(c, "tma_ctas", 0);
     bool use_tma = mode != 3 && m.tma_ok && pa_knob(c, "spmv_kernel", 3) == 3 && cfg.rows >= 32 && cfg.rows <= 256 && cfg.rows % 32 == 0 && cfg.stages >= 2;
     if (use_tma) {
       int64_t mt = 0;
-      PA_TRY(max_tile_nnz(c, m, cfg.rows, &mt));
+      PA_TRY(max_tile_nnz(c, m, cfg.rows * cfg.rpt, &mt));
       cfg.cap = (int)((std::max<int64_t>(mt, 64) + 63) / 64 * 64);
-      cfg.ntiles = (m.nrows + cfg.rows - 1) / cfg.rows;
-      const size_t smem = (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (cfg.cap + 8) * 4 + 8 + 16) + 128;
+      cfg.ntiles = (m.nrows + (int64_t)cfg.rows * cfg.rpt - 1) / ((int64_t)cfg.rows * cfg.rpt);
+      const size_t smem = (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (want_pat ? (cfg.rows * cfg.rpt + 16) : (cfg.cap + 8) * 4) + 8 + 16) + 128 + (want_pat ? 16 * 1024 : 0);
       if (smem > 200 * 1024) use_tma = false;  // a tile does not fit: irregular rows -> chunked kernel
     }
     PA_CHECK(use_tma || (kmode != 2 && kmode != 4), PA_ESTATE, "own-block / fused-exchange modes need the TMA kernel");

@@ -35,7 +35,6 @@ def test_pattern_kernel_equals_plain_kernel_and_oracle(pa, kind, gn, npd):
         b = pa.CUDAArray(P, arena_bytes=64 << 20)
         b.set_knob("spmv_patterns", 1 if mode == "patterns" else 0)
         b.set_knob("spmv_pattern_min_rows", 1)
-        b.set_knob("tma_rows", 64)  # same tiles in both modes: the partial sums of the fused dot are grouped by tile
         A, rhs = pa.stencil_matrix(kind, gn, npd, b)
         outs[mode] = [_mul_all(pa, A, 5), _mul_all(pa, A, 6, pa.PA_SPMV_OVERLAP)]
         # 5-argument mul! and the CG loop (SpMV with the fused dot epilogue) on the same path
@@ -48,8 +47,12 @@ def test_pattern_kernel_equals_plain_kernel_and_oracle(pa, kind, gn, npd):
         outs[mode].append(np.asarray(res.history))
         outs[mode].append(xs.collect())
         b.close()
-    for got, want in zip(outs["patterns"], outs["plain"]):
+    for got, want in zip(outs["patterns"][:3], outs["plain"][:3]):  # mul! (3- and 5-argument, two schedules): bit for bit
         assert np.array_equal(got, want)
+    # CG: the fused dot adds per-tile partial sums, and the pattern kernel may use other tiles (two rows per thread): the
+    # histories agree to rounding, not to the bit
+    np.testing.assert_allclose(outs["patterns"][3], outs["plain"][3], rtol=1e-12)
+    np.testing.assert_allclose(outs["patterns"][4], outs["plain"][4], rtol=1e-9, atol=1e-12)
     # and against the oracle's sequential loops
     if kind == 7:
         I, J, V, rows, cols = o.laplacian_fdm(gn, npd)
