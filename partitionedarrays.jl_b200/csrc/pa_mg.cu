@@ -1065,7 +1065,7 @@ __global__ void __launch_bounds__(288, 2) k_gs_color_tma(const GsSellArgs a, con
           if (PAT) {
             const int32_t pk = tab[kk];
             code[u] = pk < 0 ? -1 : (((row + (pk & GS_COL_MASK)) & GS_COL_MASK) | (pk & (GS_COL_FRESH | GS_COL_OWN)));
-            if (esc) code[u] = __ldg(gcode + kk * 32);
+            if (esc || pk == -2) code[u] = __ldg(gcode + kk * 32);
           } else {
             code[u] = cs[kk * 32];
           }
@@ -1526,8 +1526,11 @@ static bool gs_sell_ok(const GsPart &p, const MatPart &m, int64_t n_local_cols) 
 }
 
 // ---- row patterns of a SELL copy, per level (colour)
+// -2 = a ghost column (no OWN flag): ghost ids follow no pattern, the kernel reads that word from the SELL copy
 __device__ __forceinline__ int32_t gs_pack_code(int32_t code, int32_t row) {
-  return code < 0 ? -1 : ((((code & GS_COL_MASK) - row) & GS_COL_MASK) | (code & (GS_COL_FRESH | GS_COL_OWN)));
+  if (code < 0) return -1;
+  if (!(code & GS_COL_OWN)) return -2;
+  return (((code & GS_COL_MASK) - row) & GS_COL_MASK) | (code & (GS_COL_FRESH | GS_COL_OWN));
 }
 __global__ void k_gs_pat_sample(const int32_t *rows, const int32_t *cols, int W, int64_t pos0, int64_t npos, int64_t nsample, int32_t *out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsample; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1589,8 +1592,10 @@ static int gs_build_patterns(pa_ctx *c, GsOrder *o, int64_t n_rows) {
       const int32_t *q = hs.data() + i * (1 + W);
       if (q[0]) freq[std::vector<int32_t>(q + 1, q + 1 + W)]++;
     }
+    const int64_t min_count = std::max<int64_t>(1, ns / 4096);  // one-off tuples (ghost columns) keep their column words
     std::vector<std::pair<int64_t, std::vector<int32_t>>> order;
-    for (auto &kv : freq) order.emplace_back(-kv.second, kv.first);
+    for (auto &kv : freq)
+      if (kv.second >= min_count) order.emplace_back(-kv.second, kv.first);
     std::sort(order.begin(), order.end());
     if ((int)order.size() > max_pat) order.resize(max_pat);
     o->lev_npat[l] = (int)order.size();

@@ -12,6 +12,9 @@
 #include "pa_internal.h"
 
 #define SPMV_BLOCK 256
+// table word of an entry whose column is a ghost: ghost ids follow no pattern (they number the part's halo), so the kernel reads
+// that one column from colval — the rows on a part face then share a pattern (and the fixed-length path) like all the others
+#define PA_PAT_GHOST ((int32_t)0x80000000)
 
 // ------------------------------------------------------------------ the SpMV kernel
 // CSR-stream: a CTA owns ROWS consecutive rows.  All 256 threads stream the CTA's contiguous slice of
@@ -391,8 +394,9 @@ __global__ void __launch_bounds__(288, (BATCH >= 32 ? 1 : (BATCH >= 16 ? 2 : (MO
         for (int u = 0; u < BATCH; ++u) {
           const int kk = min(k0 + u, len - 1);
           if (PAT) {
-            c[u] = (int32_t)row + tab[esc ? 0 : kk];
-            if (esc) c[u] = __ldg(gc + kk);
+            const int32_t tw = tab[esc ? 0 : kk];
+            c[u] = (int32_t)row + tw;
+            if (esc || tw == PA_PAT_GHOST) c[u] = __ldg(gc + kk);
           } else {
             c[u] = cs[kk];
           }
@@ -575,7 +579,10 @@ __global__ void __launch_bounds__(288, MINB) k_spmv_pat(const SpmvArgs<PtrT> a, 
           for (int u = 0; u < FB; ++u)
             if (k0 + u < FL) {
               v[q][u] = vs[q][k0 + u];
-              xv[q][u] = __ldg(a.x + (row[q] + tab[q][k0 + u]));
+              const int32_t tw = tab[q][k0 + u];
+              int32_t c = row[q] + tw;
+              if (tw == PA_PAT_GHOST) c = __ldg(gc[q] + (k0 + u));  // a ghost column (rows on a part face): one read of colval
+              xv[q][u] = __ldg(a.x + c);
             }
 #pragma unroll
         for (int q = 0; q < RPT; ++q)
@@ -591,8 +598,9 @@ __global__ void __launch_bounds__(288, MINB) k_spmv_pat(const SpmvArgs<PtrT> a, 
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) {
             const int kk = max(min(k0 + u, len[q] - 1), 0);  // past the row end: a redundant, cached read of its last entry
-            int32_t c = row[q] + tab[q][esc[q] ? 0 : kk];
-            if (esc[q]) c = __ldg(gc[q] + kk);
+            const int32_t tw = tab[q][esc[q] ? 0 : kk];
+            int32_t c = row[q] + tw;
+            if (esc[q] || tw == PA_PAT_GHOST) c = __ldg(gc[q] + kk);
             v[q][u] = vs[q][kk];
             xv[q][u] = __ldg(a.x + (len[q] > 0 ? c : 0));
           }
@@ -817,7 +825,7 @@ __global__ void k_sum_parts(const double *part, int n, double *out) {
 #define PA_PAT_ESC 255
 #define PA_PAT_MAXW 32
 template <typename PtrT>
-__global__ void k_pat_sample(const PtrT *rowptr, const int32_t *colval, int64_t nrows, int64_t nsample, int32_t *out /* [nsample][1 + MAXW] */) {
+__global__ void k_pat_sample(const PtrT *rowptr, const int32_t *colval, int64_t nrows, int64_t n_own_cols, int64_t nsample, int32_t *out /* [nsample][1 + MAXW] */) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsample; i += (int64_t)gridDim.x * blockDim.x) {
     // evenly spread rows with a pseudo-random offset inside every stride, plus the rows next to both ends
     const int64_t stride = nrows / nsample > 0 ? nrows / nsample : 1;
@@ -829,7 +837,14 @@ __global__ void k_pat_sample(const PtrT *rowptr, const int32_t *colval, int64_t 
     const int64_t p0 = (int64_t)rowptr[row], len = (int64_t)rowptr[row + 1] - p0;
     int32_t *o = out + i * (1 + PA_PAT_MAXW);
     o[0] = len <= PA_PAT_MAXW ? (int32_t)len : -1;
-    for (int k = 0; k < PA_PAT_MAXW; ++k) o[1 + k] = (k < len && len <= PA_PAT_MAXW) ? colval[p0 + k] - (int32_t)row : 0;
+    for (int k = 0; k < PA_PAT_MAXW; ++k) {
+      int32_t dlt = 0;
+      if (k < len && len <= PA_PAT_MAXW) {
+        const int32_t col = colval[p0 + k];
+        dlt = col >= n_own_cols ? PA_PAT_GHOST : col - (int32_t)row;  // a ghost column: "read it from colval"
+      }
+      o[1 + k] = dlt;
+    }
   }
 }
 __device__ __forceinline__ unsigned long long pat_hash(int len, const int32_t *d) {
@@ -841,7 +856,7 @@ __device__ __forceinline__ unsigned long long pat_hash(int len, const int32_t *d
   return h;
 }
 template <typename PtrT>
-__global__ void k_pat_assign(const PtrT *rowptr, const int32_t *colval, int64_t nrows, const int32_t *ptab, const int32_t *plen, const unsigned long long *phash,
+__global__ void k_pat_assign(const PtrT *rowptr, const int32_t *colval, int64_t nrows, int64_t n_own_cols, const int32_t *ptab, const int32_t *plen, const unsigned long long *phash,
                              int npat, int pat_w, unsigned char *pat, unsigned long long *n_esc) {
   extern __shared__ unsigned long long sh_hash[];  // [npat] then lengths
   int32_t *sh_len = reinterpret_cast<int32_t *>(sh_hash + npat);
@@ -857,7 +872,10 @@ __global__ void k_pat_assign(const PtrT *rowptr, const int32_t *colval, int64_t 
     int id = PA_PAT_ESC;
     if (len <= pat_w) {
       int32_t d[PA_PAT_MAXW];
-      for (int k = 0; k < len; ++k) d[k] = colval[p0 + k] - (int32_t)row;
+      for (int k = 0; k < len; ++k) {
+        const int32_t col = colval[p0 + k];
+        d[k] = col >= n_own_cols ? PA_PAT_GHOST : col - (int32_t)row;
+      }
       const unsigned long long h = pat_hash(len, d);
       for (int q = 0; q < npat && id == PA_PAT_ESC; ++q) {
         if (sh_hash[q] != h || sh_len[q] != len) continue;
@@ -881,14 +899,14 @@ static unsigned long long pat_hash_host(int len, const int32_t *d) {
   return h;
 }
 
-static int build_patterns(pa_ctx *c, MatPart &m) {
+static int build_patterns(pa_ctx *c, MatPart &m, int64_t n_own_cols) {
   m.pat_state = -1;
   if (m.nrows < pa_knob(c, "spmv_pattern_min_rows", 4096) || m.nnz == 0) return PA_OK;  // nothing to gain on small parts
   const int64_t nsample = std::min<int64_t>(m.nrows, 65536);
   int32_t *d_s = nullptr;
   PA_CUDA(cudaMalloc((void **)&d_s, nsample * (1 + PA_PAT_MAXW) * sizeof(int32_t)));
-  if (m.ptr64) k_pat_sample<int64_t><<<256, 256, 0, c->stream>>>((const int64_t *)m.d_rowptr, m.d_colval, m.nrows, nsample, d_s);
-  else k_pat_sample<int32_t><<<256, 256, 0, c->stream>>>((const int32_t *)m.d_rowptr, m.d_colval, m.nrows, nsample, d_s);
+  if (m.ptr64) k_pat_sample<int64_t><<<256, 256, 0, c->stream>>>((const int64_t *)m.d_rowptr, m.d_colval, m.nrows, n_own_cols, nsample, d_s);
+  else k_pat_sample<int32_t><<<256, 256, 0, c->stream>>>((const int32_t *)m.d_rowptr, m.d_colval, m.nrows, n_own_cols, nsample, d_s);
   std::vector<int32_t> hs((size_t)nsample * (1 + PA_PAT_MAXW));
   PA_CUDA(cudaMemcpyAsync(hs.data(), d_s, hs.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   PA_CUDA(cudaStreamSynchronize(c->stream));
@@ -903,8 +921,12 @@ static int build_patterns(pa_ctx *c, MatPart &m) {
     std::vector<int32_t> key(o, o + 1 + o[0]);
     freq[key]++;
   }
+  // tuples seen only once or twice in a large sample are rows of their own kind (ghost columns on a part face): keeping them
+  // would only grow the table (shared memory per CTA, occupancy) — they read colval instead
+  const int64_t min_count = std::max<int64_t>(1, nsample / 8192);
   std::vector<std::pair<int64_t, std::vector<int32_t>>> order;
-  for (auto &kv : freq) order.emplace_back(-kv.second, kv.first);
+  for (auto &kv : freq)
+    if (kv.second >= min_count) order.emplace_back(-kv.second, kv.first);
   std::sort(order.begin(), order.end());
   if (order.empty()) return PA_OK;
   if (order.size() > 254) order.resize(254);
@@ -934,9 +956,9 @@ static int build_patterns(pa_ctx *c, MatPart &m) {
   PA_CUDA(cudaMemsetAsync(m.d_pat, PA_PAT_ESC, (size_t)m.nrows + 512, c->stream));
   const size_t sh = (size_t)npat * (sizeof(unsigned long long) + sizeof(int32_t));
   if (m.ptr64)
-    k_pat_assign<int64_t><<<148 * 8, 256, sh, c->stream>>>((const int64_t *)m.d_rowptr, m.d_colval, m.nrows, m.d_ptab, d_len, d_hash, npat, wmax, m.d_pat, d_esc);
+    k_pat_assign<int64_t><<<148 * 8, 256, sh, c->stream>>>((const int64_t *)m.d_rowptr, m.d_colval, m.nrows, n_own_cols, m.d_ptab, d_len, d_hash, npat, wmax, m.d_pat, d_esc);
   else
-    k_pat_assign<int32_t><<<148 * 8, 256, sh, c->stream>>>((const int32_t *)m.d_rowptr, m.d_colval, m.nrows, m.d_ptab, d_len, d_hash, npat, wmax, m.d_pat, d_esc);
+    k_pat_assign<int32_t><<<148 * 8, 256, sh, c->stream>>>((const int32_t *)m.d_rowptr, m.d_colval, m.nrows, n_own_cols, m.d_ptab, d_len, d_hash, npat, wmax, m.d_pat, d_esc);
   PA_CUDA(cudaMemcpyAsync(&h_esc, d_esc, sizeof(h_esc), cudaMemcpyDeviceToHost, c->stream));
   PA_CUDA(cudaStreamSynchronize(c->stream));
   cudaFree(d_len); cudaFree(d_hash); cudaFree(d_esc);
@@ -974,7 +996,7 @@ int pa_spmv_local(pa_mat *A, pa_vec *x, pa_vec *y, double alpha, double beta, in
     const int64_t pat_knob = pa_knob(c, "spmv_patterns", 1);
     const bool long_rows = m.nnz > 12 * m.nrows;
     bool want_pat = kmode == 0 && pat_knob != 0 && m.tma_ok && pa_knob(c, "spmv_kernel", 3) == 3;
-    if (want_pat && m.pat_state == 0) PA_TRY(build_patterns(c, m));
+    if (want_pat && m.pat_state == 0) PA_TRY(build_patterns(c, m, cp.prefix ? cp.n_own : cp.n_local));
     want_pat = want_pat && m.pat_state == 1;
     // measured best (profiles/): 7-pt 256 rows per tile, 27-pt 64 with the column stream / 128 with row patterns
     // with row patterns (k_spmv_pat, fixed-length path): 27-pt 96 rows x 2 stages (4.60 ms; column stream 7.40), 7-pt 2 x 128 rows per
