@@ -482,8 +482,21 @@ __global__ void __launch_bounds__(288, MINB) k_spmv_pat(const SpmvArgs<PtrT> a, 
   uint64_t *full = reinterpret_cast<uint64_t *>(p0_s + S);
   uint64_t *empty = full + S;
   int32_t *ptab_s = reinterpret_cast<int32_t *>(empty + S);
+  unsigned char *pg_s = reinterpret_cast<unsigned char *>(ptab_s + a.npat * a.pat_w);  // [256] pattern reads colval (ghost marker / none)
+  // EARLY (long rows): the pattern id is ALSO read from global memory one tile ahead, like the row pointers, so that rows which
+  // will read columns from colval (ghost marker, no pattern) can bring those lines into L1 before the tile arrives: the read
+  // sits in front of an x gather and one late row holds up its whole tile.  (27-pt, two parts: 2.96 -> 2.77 ms.  For 7-entry
+  // rows the extra byte load and test per row cost more than they save: 1.68 -> 2.03 ms, so short rows do without.)
+  constexpr bool EARLY = FL >= 16 || BATCH >= 16;
   const int tid = threadIdx.x;
   for (int i = tid; i < a.npat * a.pat_w; i += blockDim.x) ptab_s[i] = a.ptab[i];
+  if (EARLY)
+    for (int p = tid; p < 256; p += blockDim.x) {
+      bool g = p >= a.npat;
+      if (!g)
+        for (int k2 = 0; k2 < a.pat_w; ++k2) g |= a.ptab[p * a.pat_w + k2] == PA_PAT_GHOST;
+      pg_s[p] = g ? 1 : 0;
+    }
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full + s, 1);
@@ -518,13 +531,16 @@ __global__ void __launch_bounds__(288, MINB) k_spmv_pat(const SpmvArgs<PtrT> a, 
   }
   double dsum = 0.0;
   int64_t rs_n[RPT], re_n[RPT];
+  unsigned pid_n[RPT];
 #pragma unroll
   for (int q = 0; q < RPT; ++q) {
     rs_n[q] = re_n[q] = 0;
+    pid_n[q] = 255u;
     const int64_t row = first * TR + q * ROWS + tid;
     if (nloc > 0 && row < a.nrows) {
       rs_n[q] = (int64_t)a.rowptr[row];
       re_n[q] = (int64_t)a.rowptr[row + 1];
+      if (EARLY) pid_n[q] = (unsigned)__ldg(a.pat + row);
     }
   }
   int s = 0;
@@ -540,11 +556,17 @@ __global__ void __launch_bounds__(288, MINB) k_spmv_pat(const SpmvArgs<PtrT> a, 
       rs[q] = rs_n[q];
       len[q] = (int)(re_n[q] - rs_n[q]);
       row[q] = (int32_t)(t * TR + q * ROWS + tid);
+      if (EARLY && len[q] > 0 && pg_s[pid_n[q]]) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.colval + rs[q]));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.colval + rs[q] + len[q] - 1));
+      }
       rs_n[q] = re_n[q] = 0;
+      pid_n[q] = 255u;
       const int64_t rown = (t + stride) * TR + q * ROWS + tid;  // the next tile's row pointers while this tile is processed
       if (j + 1 < nloc && rown < a.nrows) {
         rs_n[q] = (int64_t)a.rowptr[rown];
         re_n[q] = (int64_t)a.rowptr[rown + 1];
+        if (EARLY) pid_n[q] = (unsigned)__ldg(a.pat + rown);
       }
     }
     mbar_wait(full + s, ph);
@@ -675,7 +697,7 @@ template <typename PtrT>
 static int launch_spmv_tma(pa_ctx *c, MatPart &m, const SpmvArgs<PtrT> &a, int mode, const TmaCfg &cfg, int ctas_per_sm, int64_t *grid_out) {
   const bool pat = mode == 0 && a.pat != nullptr;
   if (pat && cfg.use_pat_kernel) {
-    const size_t smem2 = (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (cfg.rows * cfg.rpt + 16) + 8 + 16) + (size_t)a.npat * a.pat_w * 4 + 128;
+    const size_t smem2 = (size_t)cfg.stages * ((cfg.cap + 2) * 8 + (cfg.rows * cfg.rpt + 16) + 8 + 16) + (size_t)a.npat * a.pat_w * 4 + 256 + 128;
     void (*k2)(const SpmvArgs<PtrT>, const TmaCfg) = nullptr;
     // (rows per thread, fixed length): 7-entry rows 2 x 7 or 1 x 7, 27-entry rows 1 x 27; everything else the generic loop
     if (cfg.fl == 7) k2 = cfg.rpt == 2 ? k_spmv_pat<PtrT, 8, 2, 2, 7> : k_spmv_pat<PtrT, 8, 1, 3, 7>;
