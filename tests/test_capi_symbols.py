@@ -67,6 +67,14 @@ def test_sass_has_no_fma_in_spmv_accumulate():
     tma = [b for b in blocks if b.startswith("_Z10k_spmv_tmaIiLi0ELi8E")]
     assert tma, "k_spmv_tma<int,0,8> not found in the library"
     assert "UBLKCP" in tma[0] and "SYNCS" in tma[0] and "DMUL" in tma[0] and "DADD" in tma[0] and "DFMA" not in tma[0]
+    # the row-pattern kernels (round 2), every instantiation: TMA ring, separate DMUL/DADD, no DFMA in the products
+    pat = [b for b in blocks if b.startswith("_Z10k_spmv_patI")]
+    assert len(pat) >= 6, "k_spmv_pat instantiations missing"
+    for b in pat:
+        assert "UBLKCP" in b and "SYNCS" in b and "DMUL" in b and "DADD" in b and "DFMA" not in b, b.split("\n")[0]
+    # the multi-colour Gauss-Seidel kernel streams its slices with TMA too (its DFMAs are the division sequence)
+    col = [b for b in blocks if b.startswith("_Z14k_gs_color_tmaILi27E")]
+    assert col and all("UBLKCP" in b and "SYNCS" in b and "DMUL" in b and "DADD" in b for b in col)
     gs = [b for b in blocks if b.startswith("_Z9k_gs_flowIiE")]
     # Gauss-Seidel sweeps: separate DMUL / DADD for s -= a*x (the only DFMAs belong to the IEEE division sequence of __ddiv_rn)
     assert gs and "DMUL" in gs[0] and "DADD" in gs[0] and "MUFU.RCP64H" in gs[0]

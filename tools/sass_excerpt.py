@@ -9,9 +9,13 @@ import sys
 
 SO = sys.argv[1] if len(sys.argv) > 1 else "partitionedarrays.jl_b200/lib/libpa_b200.so"
 KERNELS = [
-    ("k_spmv_tma<int32 rowptr, MODE 0 (local), BATCH 8>", "_Z10k_spmv_tmaIiLi0ELi8EEv8SpmvArgsIT_E6TmaCfg"),
-    ("k_spmv_tma<int64 rowptr, MODE 0, BATCH 16> (27-pt 512^3)", "_Z10k_spmv_tmaIlLi0ELi16EEv8SpmvArgsIT_E6TmaCfg"),
-    ("k_spmv_tma<int32, MODE 4 (consistent! fused in), BATCH 8>", "_Z10k_spmv_tmaIiLi4ELi8EEv8SpmvArgsIT_E6TmaCfg"),
+    ("k_spmv_pat<int32 rowptr, BATCH 8, 2 rows per thread, fixed length 7> (7-pt 512^3, row patterns)", "_Z10k_spmv_patIiLi8ELi2ELi2ELi7EEv8SpmvArgsIT_E6TmaCfg"),
+    ("k_spmv_pat<int64 rowptr, BATCH 16, 1 row per thread, fixed length 27> (27-pt 512^3, row patterns)", "_Z10k_spmv_patIlLi16ELi1ELi2ELi27EEv8SpmvArgsIT_E6TmaCfg"),
+    ("k_spmv_tma<int32 rowptr, MODE 0 (local), BATCH 8> (column stream)", "_Z10k_spmv_tmaIiLi0ELi8ELb0EEv8SpmvArgsIT_E6TmaCfg"),
+    ("k_spmv_tma<int64 rowptr, MODE 0, BATCH 16> (27-pt 512^3, column stream)", "_Z10k_spmv_tmaIlLi0ELi16ELb0EEv8SpmvArgsIT_E6TmaCfg"),
+    ("k_spmv_tma<int32, MODE 4 (consistent! fused in), BATCH 8>", "_Z10k_spmv_tmaIiLi4ELi8ELb0EEv8SpmvArgsIT_E6TmaCfg"),
+    ("k_gs_color_tma<27, batch 27, row patterns> (multi-colour Gauss-Seidel through the TMA ring)", "_Z14k_gs_color_tmaILi27ELi27ELb1EEv10GsSellArgsii"),
+    ("k_residual_restrict<int64> (residual at the injection points)", "_Z19k_residual_restrictIlEvPdPKdS2_PKT_PKiS2_lllll"),
     ("k_consistent_sync (signal + wait + gather + done)", "_Z17k_consistent_syncPdPKiS1_S1_l8PeerPtrsPy8FlagPtrsS4_S4_iPjPi"),
     ("k_cg_direction_xchg (u = r + beta*u with consistent!(u) inside)", "_Z19k_cg_direction_xchgPdPKdl7RedWaitS_PKi8XchgArgs"),
     ("k_cg_update_fold (x, r update + ||r||^2 + folded all-reduce)", "_Z16k_cg_update_foldPdPKdS_S1_ll7RedWait8DoneWait7RedPushS1_PiS_Pj"),
