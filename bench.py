@@ -453,6 +453,15 @@ def run_ours(args):
     spmv_gbs = B / (ms_spmv * 1e-3) / 1e9
     spmv_gflops = 2 * nnz_total / (ms_spmv * 1e-3) / 1e9
 
+    # --- the same product with the row patterns switched off (values AND column indices streamed: the CSR byte model's kernel)
+    backend.set_knob("spmv_patterns", 0)
+    for _ in range(3):
+        pa.mul_(y, A, u, flags=pa.PA_SPMV_SKIP_GHOST_REFRESH)
+    ms_spmv_plain, w = timed(lambda: [pa.mul_(y, A, u, flags=pa.PA_SPMV_SKIP_GHOST_REFRESH) for _ in range(20)])
+    windows.append(w)
+    ms_spmv_plain /= 20
+    backend.set_knob("spmv_patterns", 1)
+
     # --- every mul! schedule on the same operands (N > 1: they differ only in how the ghost values travel)
     sched_ms = None
     if N > 1:
@@ -577,6 +586,13 @@ def run_ours(args):
         ms27, w = timed(lambda: [pa.mul_(y27, A27, u27) for _ in range(20)])
         windows.append(w)
         ms27 /= 20
+        backend.set_knob("spmv_patterns", 0)
+        for _ in range(2):
+            pa.mul_(y27, A27, u27)
+        ms27_plain, w = timed(lambda: [pa.mul_(y27, A27, u27) for _ in range(10)])
+        windows.append(w)
+        ms27_plain /= 10
+        backend.set_knob("spmv_patterns", 1)
         def st27():
             x27.fill_(0.0)
             return pa.ref_cg_(x27, A27, b27, tolerance=0.0, maxiter=args.iters)
@@ -585,7 +601,7 @@ def run_ours(args):
         windows.append(w)
         B27 = spmv_bytes(ind27.n_own, nnz27, ind27.n_local)
         extra["hpcg27"] = {"workload": f"HPCG 27-pt {n}^3 rows per GPU (global {gn27[0]}x{gn27[1]}x{gn27[2]}), parts {sh}, weak", "parity_check": par27,
-                           "spmv_ms": ms27, "spmv_gflops": 2 * nnz27_t / ms27 / 1e6, "spmv_hbm_gbs_per_gpu": B27 / ms27 / 1e6,
+                           "spmv_ms": ms27, "spmv_ms_column_stream_kernel": ms27_plain, "spmv_gflops": 2 * nnz27_t / ms27 / 1e6, "spmv_hbm_gbs_per_gpu": B27 / ms27 / 1e6,
                            "spmv_frac_of_peak": B27 / ms27 / 1e6 / peak, "cg_iters_per_sec": args.iters / (mscg27 * 1e-3),
                            "cg_gflops": (2 * nnz27_t + 12 * rows_total) * args.iters / mscg27 / 1e6, "nnz_per_gpu": nnz27}
         for v in (x27, y27, u27, b27):
@@ -635,6 +651,8 @@ def run_ours(args):
                          "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak,
                          "note": "achieved = ALGORITHMIC bytes of the CSR product (SURVEY 8d: 12 B per entry) / time; the kernel moves fewer bytes than that (traffic), which is how frac exceeds 1; traffic / time is what to compare with the HBM peak",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": B, "traffic": traffic, "traffic_source": traffic_src,
+                         "column_stream_kernel": {"kernel": "k_spmv_tma (row patterns off: 12 B per entry streamed)", "ms": ms_spmv_plain,
+                                                  "achieved": B / (ms_spmv_plain * 1e-3) / 1e9, "frac": B / (ms_spmv_plain * 1e-3) / 1e9 / peak},
                          "cg_iter_bytes_model": B + 120 * n_rows, "cg_frac_of_peak": (B + 120 * n_rows) * args.iters / (ms_step * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                     "schedule": "pipelined: upload of the next b and download of the previous x on copy streams, overlapped with the running solve",
