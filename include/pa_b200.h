@@ -210,6 +210,10 @@ int pa_mat_set_csc_split(pa_mat *A, int32_t k, int64_t nrows, int32_t index_base
  * precompute_nzindex :434-455) is kept so that pa_mat_update_coo_values = sparse_matrix!(A,V,K) / psparse! (:457-469,
  * src/p_sparse_matrix.jl:1291-1305) refreshes the values of the same pattern with one kernel. */
 int pa_mat_set_coo(pa_mat *A, int32_t k, int64_t n, int32_t idx_bits, const void *I, const void *J, const double *V);
+/* perm[0..n) = stable ascending order of 64-bit keys (device radix sort; host arrays in and out).  Setup-time helper for the
+ * host-side assembly stages: with key = (row << 32) | col it is the entry order of sparse_matrix / compresscoo
+ * (SparseArrays / SparseMatricesCSR, called by src/p_sparse_matrix.jl:1186-1222), duplicates in input order. */
+int pa_sort_perm_u64(pa_ctx *ctx, const uint64_t *keys, int64_t n, int32_t *perm);
 int pa_mat_update_coo_values(pa_mat *A, int32_t k, const double *V, int64_t n);
 /* On-device generators of the benchmark operators for a box partition (own box lo..hi of a gn grid,
  * 0-based, hi exclusive): kind 7 = gallery laplacian_fdm (src/gallery.jl:12-86), kind 27 = HPCG

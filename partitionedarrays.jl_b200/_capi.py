@@ -70,6 +70,7 @@ SIGNATURES = {
     "pa_vec_assemble": [_P],
     "pa_vec_assemble_op": [_P, _I32],
     "pa_vec_reduce_parts": [_P, _I32, _D, _P],
+    "pa_sort_perm_u64": [_P, _P, _I64, _P],
     "pa_xchg_create": [_P, _P],
     "pa_xchg_set_elem_size": [_P, _I32],
     "pa_xchg_set_part": [_P, _I32, _I32, _P, _P, _I32, _P, _P, _P],

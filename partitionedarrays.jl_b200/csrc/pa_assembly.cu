@@ -69,6 +69,46 @@ static void free_coo_cache(MatPart &m) {
   m.n_coo = 0;
 }
 
+/* Setup-time helper of the assembly stages that stay on the host (per-part compression of disassembled triplets, COO -> CSR of
+ * the blocks): perm = the STABLE ascending order of 64-bit keys (row and column packed into one key = the order of
+ * sortperm / the reference's compresscoo).  Device radix sort; keys and permutation travel over PCIe (12 bytes per entry)
+ * instead of a host merge sort of the same array (22 M entries: seconds). */
+__global__ void k_iota32(int32_t *p, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (int32_t)i;
+}
+extern "C" int pa_sort_perm_u64(pa_ctx *c, const uint64_t *keys, int64_t n, int32_t *perm) {
+  PA_CHECK(c && (n == 0 || (keys && perm)) && n >= 0 && n < (1ll << 31), PA_EINVAL, "pa_sort_perm_u64: bad arguments");
+  if (n == 0) return PA_OK;
+  PA_CUDA(cudaSetDevice(c->device));
+  unsigned long long *k1 = nullptr, *k2 = nullptr;
+  int32_t *p1 = nullptr, *p2 = nullptr;
+  void *tmp = nullptr;
+  size_t tb = 0;
+  cudaError_t e = cudaMalloc((void **)&k1, n * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&k2, n * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&p1, n * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&p2, n * 4);
+  if (e == cudaSuccess) {
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, k1, k2, p1, p2, (int)n, 0, 64, c->stream);
+    e = cudaMalloc(&tmp, tb ? tb : 1);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(k1, keys, n * 8, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    k_iota32<<<148 * 4, 256, 0, c->stream>>>(p1, n);
+    e = cub::DeviceRadixSort::SortPairs(tmp, tb, k1, k2, p1, p2, (int)n, 0, 64, c->stream);  // stable
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(perm, p2, n * 4, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(k1); cudaFree(k2); cudaFree(p1); cudaFree(p2); cudaFree(tmp);
+  c->launches += 2;
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    pa_set_error("pa_sort_perm_u64: %s", cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? PA_ENOMEM : PA_ECUDA;
+  }
+  return PA_OK;
+}
+
 /* sparse_matrix(T, I, J, V, m, n; reuse=true) on the device for local part k.
  * I: 1-based OWN row ids, J: 1-based LOCAL column ids (ids < 1 are skipped like the reference), idx_bits 32 or 64.
  * The pattern cache (the reference's K) is kept for pa_mat_update_coo_values. */

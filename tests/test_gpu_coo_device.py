@@ -68,3 +68,26 @@ def test_device_compress_equals_host_and_oracle_and_refresh():
     pa.mul_(y2, A_ref, x3)
     assert np.array_equal(y1.collect(), y2.collect())
     b.close()
+
+
+def test_device_stable_order_equals_lexsort():
+    """pa_sort_perm_u64 behind parrays._stable_order (the host-side assembly stages sort their triplets on the device once they
+    are long): the permutation is np.lexsort's — stable, so duplicates keep their input order and the sums their bits."""
+    import pa_b200 as pa
+    from pa_b200 import parrays
+
+    rng = np.random.default_rng(2)
+    n = (1 << 18) + 12345
+    b = pa.CUDAArray(1, arena_bytes=8 << 20)
+    rows = rng.integers(1, 5000, size=n)
+    cols = np.clip(rows + rng.integers(-3, 4, size=n), 1, None)  # many duplicates
+    got = parrays._stable_order(rows, cols, b)
+    assert got.dtype == np.int32 and np.array_equal(got, np.lexsort((cols, rows)))
+    v = rng.standard_normal(n)
+    ei, ej, ev = parrays._stored_entries(rows.copy(), cols.copy(), v, 5000, 5010, "csr", b)
+    hi, hj, hv = parrays._stored_entries(rows.copy(), cols.copy(), v, 5000, 5010, "csr", None)
+    assert np.array_equal(ei, hi) and np.array_equal(ej, hj) and np.array_equal(ev, hv)
+    # ids the packed key cannot hold fall back to the host sort
+    big = rows.astype(np.int64) + (1 << 33)
+    assert np.array_equal(parrays._stable_order(big, cols, b), np.lexsort((cols, big)))
+    b.close()
