@@ -14,6 +14,9 @@ import pa_b200 as pa  # noqa: E402
 def main():
     for nparts, npd in ((2, (2, 1, 1)), (1, (1, 1, 1))):
         b = pa.CUDAArray(nparts, arena_bytes=16 << 20)
+        # the row-pattern kernels (k_spmv_pat, k_gs_color_tma<PAT>) are built for parts of >= 4096 rows by default: force them here
+        b.set_knob("spmv_pattern_min_rows", 1)
+        b.set_knob("gs_pattern_min_rows", 1)
         for kind in (7, 27):
             A, rhs = pa.stencil_matrix(kind, (12 * npd[0], 10, 8), npd, b)
             x = pa.fill_hash(pa.PVector(A.cols), 3)
@@ -30,7 +33,14 @@ def main():
             gs.smooth_(xs, rhs, False)
             gs.set_order("multicolor")
             gs.smooth_(xs, rhs, False)
+            gs.smooth_(xs, rhs, True)
             gs.free()
+            if kind == 27 and nparts == 1:  # V-cycle: k_residual_restrict, k_prolong
+                P = pa.pc_setup(b, 2, 8, 8, 8, 1, 1, 1, order="multicolor")
+                cvec = pa.pzeros(P.A.cols)
+                P.ldiv_(cvec, P.b)
+                cvec.free()
+                P.free()
             for v in (x, y, xs, rhs):
                 v.free()
             A.free()
