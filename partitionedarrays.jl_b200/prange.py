@@ -168,6 +168,21 @@ class LocalIndices:
                 hit = sg[pos] == gids[rest]
                 out[np.nonzero(rest)[0][hit]] = self.n_own + order[pos[hit]] + 1
             return out.astype(np.int32)
+        # long id lists on a moderate global range (FEM assembly: tens of millions of triplet ids per part): a dense table
+        # gid -> local id, written so that the same copy wins as below (ghosts in ascending local order: the LAST ghost copy
+        # of a gid stays; then the own ids on top); one gather per query instead of a binary search
+        if len(gids) >= (1 << 16) and self.n_global <= (1 << 27):
+            if getattr(self, "_g2l_dense", None) is None:
+                dense = np.zeros(self.n_global + 1, dtype=np.int32)
+                l2g = self.local_to_global
+                gl = np.sort(self.ghost_to_local)
+                dense[l2g[gl - 1]] = gl
+                dense[l2g[self.own_to_local - 1]] = self.own_to_local
+                self._g2l_dense = dense
+            bad = (gids < 1) | (gids > self.n_global)
+            if bad.any():
+                gids = np.where(bad, 0, gids)  # entry 0 of the table is 0
+            return self._g2l_dense[gids]
         if self._g2l is None:  # sorted table of the local gids (vectorised lookup: FEM-size id lists)
             l2g = self.local_to_global
             # duplicate gids (periodic ghost layers): the own id wins, else the LAST ghost copy (the reference's

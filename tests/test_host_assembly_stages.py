@@ -45,3 +45,30 @@ def test_empty_and_degenerate_inputs():
     assert len(ei) == len(ej) == len(ev) == 0
     ei, ej, ev = parrays._stored_entries(np.array([0, -3]), np.array([2, 0]), np.array([1.5, 2.5]), 4, 4, "csr")
     assert ei.tolist() == [1] and ej.tolist() == [1] and ev.tolist() == [0.0]
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_global_to_local_dense_table_equals_the_sorted_table(seed):
+    """LocalIndices.global_to_local switches to a dense gid -> lid table for long queries: same answers as the sorted-table
+    path, including duplicate gids among the ghosts (periodic layers: the LAST ghost copy wins, an own id wins over any ghost,
+    src/p_range.jl:928-935) and ids outside 1..n_global."""
+    from pa_b200 import prange as pr
+
+    rng = np.random.default_rng(seed)
+    ng, part = 5000, 3
+    own = rng.choice(np.arange(1, ng + 1), size=600, replace=False)
+    ghosts = rng.choice(np.setdiff1d(np.arange(1, ng + 1), own), size=300, replace=False)
+    ghosts = np.concatenate([ghosts, ghosts[:40], own[:10]])  # repeated ghost gids and ghost copies of own gids
+    l2g = np.concatenate([own, ghosts])
+    perm = rng.permutation(len(l2g)) if seed % 2 else np.arange(len(l2g))  # own-first and permuted local orders
+    owner = np.concatenate([np.full(len(own), part), rng.integers(4, 9, size=len(ghosts))]).astype(np.int32)
+    ind = pr.LocalIndices(ng, part, l2g[perm], owner[perm])
+    q_short = rng.integers(-5, ng + 10, size=1000)
+    q_long = rng.integers(-5, ng + 10, size=(1 << 16) + 17)
+    want = ind.global_to_local(q_short)           # sorted-table path
+    got_long = ind.global_to_local(q_long)        # dense path
+    assert getattr(ind, "_g2l_dense", None) is not None
+    ref = pr.LocalIndices(ng, part, l2g[perm], owner[perm])
+    ref_long = np.concatenate([ref.global_to_local(q_long[i : i + 1000]) for i in range(0, len(q_long), 1000)])  # sorted path, in chunks
+    assert np.array_equal(got_long, ref_long)
+    assert np.array_equal(ind.global_to_local(q_short), want)
