@@ -24,7 +24,7 @@ import PartitionedArrays: partition, local_values, own_values, ghost_values, con
     gather_impl!, scatter_impl, scatter_impl!, multicast_impl, multicast_impl!, scan_impl, reduction_impl, is_consistent,
     allocate_exchange_impl, setup_exchange_impl, exchange_impl!, scalar_indexing_action, getany, i_am_main, ExchangeGraph, @fake_async
 
-export CUDAArray, with_cuda, distribute_with_cuda, to_device, to_host, DeviceVector, DeviceMatrix, ref_cg!
+export CUDAArray, with_cuda, distribute_with_cuda, to_device, to_host, DeviceVector, DeviceMatrix, ref_cg!, device_gauss_seidel, smooth!, device_mg_preconditioner
 
 const LIB = get(ENV, "PA_B200_LIB", "libpa_b200.so")
 
@@ -348,6 +348,70 @@ function ref_cg!(x::DevicePVector, A::DevicePSparseMatrix, b::DevicePVector; tol
     foreach_part(np) do k
         check(ccall((:pa_cg, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Float64, UInt32, Ptr{PaCgResult}, Ptr{Float64}),
                     partition(A).items[k].h, partition(x).items[k].h, partition(b).items[k].h, maxiter, tolerance, 0, res[k], hist[k]))
+    end
+    x, hist[1][1:res[1][].iters+1], res[1][].residual0, res[1][].residual, res[1][].iters
+end
+
+# ------------------------------------------------------------------ HPCG preconditioner (HPCG/src/mg_preconditioner.jl, PartitionedSolvers smoothers)
+# gauss_seidel(p; iterations=1, sweep=:symmetric) state on the devices.  `order = :lexicographic` (default) runs the reference's
+# sequential sweeps as a wavefront dataflow (bit-identical iterates); `:multicolor` is the fast, convergence-level-parity order.
+mutable struct DeviceGaussSeidel
+    h::Vector{Ptr{Cvoid}}      # one pa_gs per part
+    A::DevicePSparseMatrix
+end
+function device_gauss_seidel(A::DevicePSparseMatrix; box_dims = nothing, kind = 27, order = :lexicographic)
+    np = length(partition(A)); h = Vector{Ptr{Cvoid}}(undef, np)
+    foreach_part(np) do k
+        r = Ref{Ptr{Cvoid}}()
+        check(ccall((:pa_gs_create, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), partition(A).items[k].h, r)); h[k] = r[]
+        if box_dims !== nothing    # local box of the stencil operator, x fastest: closed-form wavefront levels / colours
+            d = Int64[box_dims[k]...]
+            check(ccall((:pa_gs_set_box, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{Int64}), h[k], 0, kind, d))
+        end
+        check(ccall((:pa_gs_commit, LIB), Cint, (Ptr{Cvoid},), h[k]))
+        order === :multicolor && check(ccall((:pa_gs_set_order, LIB), Cint, (Ptr{Cvoid}, Int32), h[k], 1))
+    end
+    g = DeviceGaussSeidel(h, A)
+    finalizer(x -> foreach(q -> ccall((:pa_gs_destroy, LIB), Cint, (Ptr{Cvoid},), q), x.h), g)
+    g
+end
+"smooth!(x, state, b; zero_guess) — one symmetric Gauss-Seidel iteration (PartitionedSolvers/src/smoothers.jl:98-125)"
+function smooth!(x::DevicePVector, g::DeviceGaussSeidel, b::DevicePVector; zero_guess = false)
+    foreach_part(k -> check(ccall((:pa_gs_smooth, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32),
+                                   g.h[k], partition(x).items[k].h, partition(b).items[k].h, zero_guess ? 1 : 0)), length(g.h))
+    x
+end
+
+# Mg_preconditioner (HPCG/src/mg_preconditioner.jl:44-63): A_vec[1] coarsest ... A_vec[l] finest, one smoother per level
+mutable struct DeviceMgPreconditioner
+    h::Vector{Ptr{Cvoid}}      # one pa_mg per part
+    A_vec::Vector{DevicePSparseMatrix}
+    gs::Vector{DeviceGaussSeidel}
+end
+function device_mg_preconditioner(A_vec::Vector{<:DevicePSparseMatrix}, gs::Vector{DeviceGaussSeidel}, dims)   # dims[level][part] = (nx, ny, nz)
+    l = length(A_vec); np = length(partition(A_vec[1])); h = Vector{Ptr{Cvoid}}(undef, np)
+    foreach_part(np) do k
+        mats = Ptr{Cvoid}[partition(A_vec[i]).items[k].h for i in 1:l]; sm = Ptr{Cvoid}[gs[i].h[k] for i in 1:l]
+        d = Int64[dims[i][k][q] for q in 1:3, i in 1:l][:]
+        r = Ref{Ptr{Cvoid}}()
+        check(ccall((:pa_mg_create, LIB), Cint, (Int32, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Ptr{Cvoid}}), l, mats, sm, d, r)); h[k] = r[]
+    end
+    P = DeviceMgPreconditioner(h, A_vec, gs)
+    finalizer(x -> foreach(q -> ccall((:pa_mg_destroy, LIB), Cint, (Ptr{Cvoid},), q), x.h), P)
+    P
+end
+"ldiv!(x, P, b) = fill!(x,0); pc_solve!(x,P,b,l; zero_guess=true) (mg_preconditioner.jl:202-206, 314-328)"
+function LinearAlgebra.ldiv!(x::DevicePVector, P::DeviceMgPreconditioner, b::DevicePVector)
+    foreach_part(k -> check(ccall((:pa_mg_apply, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), P.h[k], partition(x).items[k].h, partition(b).items[k].h)), length(P.h))
+    x
+end
+"ref_cg!(x,A,b; Pl = P) (HPCG/src/ref_cg.jl:40-134) with the multigrid preconditioner on the devices"
+function ref_cg!(x::DevicePVector, A::DevicePSparseMatrix, b::DevicePVector, P::DeviceMgPreconditioner; tolerance = 0.0, maxiter = length(b))
+    np = nparts(x)
+    res = [Ref{PaCgResult}() for _ in 1:np]; hist = [zeros(Float64, maxiter + 1) for _ in 1:np]
+    foreach_part(np) do k
+        check(ccall((:pa_cg_precond, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Float64, UInt32, Ptr{PaCgResult}, Ptr{Float64}),
+                    partition(A).items[k].h, partition(x).items[k].h, partition(b).items[k].h, P.h[k], maxiter, tolerance, 0, res[k], hist[k]))
     end
     x, hist[1][1:res[1][].iters+1], res[1][].residual0, res[1][].residual, res[1][].iters
 end
